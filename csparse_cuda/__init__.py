@@ -1,1 +1,343 @@
-"""placeholder (filled in below)"""
+"""csparse_cuda -- B200-native drop-in for CSparse.py's data-parallel kernels.
+
+Same names, argument meaning and error behaviour as the reference module
+(rwl/CSparse.py, file csparse.py):
+
+    cs            csparse.py:37-54     matrix object (nzmax, m, n, p, i, x, nz)
+    CS_CSC        csparse.py:113-119
+    CS_TRIPLET    csparse.py:122-128
+    cs_cumsum     csparse.py:767-784   p = cumsum(c), c <- p[0..n-1]
+    cs_transpose  csparse.py:2292-2315 C = A'
+    cs_gaxpy      csparse.py:1199-1213 y += A*x
+    cs_multiply   csparse.py:1608-1642 C = A*B
+
+Every function runs on the GPU through libcsparse_b200.so (hand-written sm_100a
+CUDA, include/csparse_b200.h) -- there is no CPU fallback.  ``cs`` objects may be
+backed by Python lists (as in the reference), ``array.array`` or numpy arrays;
+results come back as plain lists, exactly shaped like the reference's.
+
+For repeated use keep matrices on the device: ``upload(A)`` returns a
+``DeviceMatrix`` that every function above accepts in place of a ``cs``; results
+of cs_transpose / cs_multiply on device matrices stay on the device
+(``.download()`` turns them into a ``cs``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import CSparseCudaError  # noqa: F401
+
+__all__ = ["cs", "CS_CSC", "CS_TRIPLET", "cs_cumsum", "cs_transpose", "cs_gaxpy", "cs_multiply",
+           "DeviceMatrix", "upload", "CSparseCudaError"]
+
+
+class cs(object):
+    """Matrix in compressed-column or triplet form (csparse.py:37-54)."""
+
+    def __init__(self):
+        self.nzmax = 0   # maximum number of entries
+        self.m = 0       # number of rows
+        self.n = 0       # number of columns
+        self.p = []      # column pointers (size n+1) or col indices (size nzmax)
+        self.i = []      # row indices, size nzmax
+        self.x = []      # numerical values, size nzmax (None: pattern only)
+        self.nz = 0      # # of entries in triplet matrix, -1 for compressed-col
+
+
+def CS_CSC(A):
+    """True if A is in column-compressed form (csparse.py:113-119)."""
+    return A is not None and A.nz == -1
+
+
+def CS_TRIPLET(A):
+    """True if A is in triplet form (csparse.py:122-128)."""
+    return A is not None and A.nz >= 0
+
+
+# ---- marshalling ------------------------------------------------------------
+
+def _i32(seq, count) -> np.ndarray:
+    """First `count` entries of a list / array / ndarray as contiguous int32."""
+    if isinstance(seq, np.ndarray):
+        a = seq[:count]
+    else:
+        a = np.asarray(seq[:count] if len(seq) != count else seq)
+    if a.size and a.dtype != np.int32:
+        if a.dtype.kind not in "iu":
+            a = a.astype(np.int64)
+        if a.size and (a.max() > 0x7FFFFFFF or a.min() < -0x80000000):
+            raise OverflowError("index does not fit int32")
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(seq, count) -> np.ndarray:
+    if isinstance(seq, np.ndarray):
+        a = seq[:count]
+    else:
+        a = np.asarray(seq[:count] if len(seq) != count else seq, dtype=np.float64)
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceMatrix(object):
+    """A CSC matrix resident in B200 HBM (opaque csb200_mat handle).
+
+    Duck-types the read-only part of ``cs``: ``m``, ``n``, ``nz == -1``,
+    ``nzmax``; ``p``/``i``/``x`` live on the device (see ``download``).
+    """
+
+    nz = -1
+
+    def __init__(self, handle, owner=True):
+        self._h = C.c_void_p(handle)
+        self._owner = owner
+        m, n, nnz, hv = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int()
+        _lib.check(_lib.lib().csb200_mat_dims(self._h, C.byref(m), C.byref(n), C.byref(nnz), C.byref(hv)))
+        self.m, self.n, self.nnz, self.has_values = m.value, n.value, nnz.value, bool(hv.value)
+        self.nzmax = max(self.nnz, 1)
+
+    def __del__(self):
+        try:
+            if self._owner and self._h:
+                _lib.lib().csb200_mat_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def free(self):
+        if self._owner and self._h:
+            _lib.lib().csb200_mat_free(self._h)
+        self._h = None
+
+    def arrays(self):
+        """(p, i, x) as numpy arrays of the logical sizes n+1 / nnz / nnz (x may be None)."""
+        p = np.empty(self.n + 1, np.int32)
+        i = np.empty(self.nnz, np.int32)
+        x = np.empty(self.nnz, np.float64) if self.has_values else None
+        _lib.check(_lib.lib().csb200_mat_download(self._h, _ptr(p), _ptr(i), _ptr(x)), "download")
+        return p, i, x
+
+    def device_pointers(self):
+        """Raw device addresses (p, i, x) for interop with torch / other CUDA code."""
+        dp, di, dx = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(_lib.lib().csb200_mat_dev_ptrs(self._h, C.byref(dp), C.byref(di), C.byref(dx)))
+        return dp.value, di.value, dx.value
+
+    def col_slice(self, j0: int, j1: int) -> "DeviceMatrix":
+        out = C.c_void_p()
+        st = _lib.check(_lib.lib().csb200_mat_col_slice(self._h, j0, j1, C.byref(out)), "col_slice")
+        if st == _lib.ERR_ARG:
+            raise ValueError(_lib.last_error())
+        return DeviceMatrix(out.value)
+
+    def download(self, trim: bool = False) -> cs:
+        """Back to a list-backed ``cs``.  ``trim`` selects cs_multiply's shape
+        convention (nzmax == nnz, possibly 0) instead of cs_spalloc's max(nnz, 1)."""
+        p, i, x = self.arrays()
+        A = cs()
+        A.m, A.n, A.nz = self.m, self.n, -1
+        A.p = p.tolist()
+        A.i = i.tolist()
+        A.x = None if x is None else x.tolist()
+        if trim:
+            A.nzmax = self.nnz
+        else:
+            A.nzmax = max(self.nnz, 1)
+            if self.nnz == 0:
+                A.i = [0]
+                A.x = None if x is None else [0.0]
+        return A
+
+    # device-pointer forms (async on the stream set with set_stream); x / y are raw
+    # device addresses, e.g. torch_tensor.data_ptr()
+    def gaxpy_dev(self, x_ptr: int, y_ptr: int):
+        """y += A*x on device vectors (csb200_gaxpy_dev)."""
+        _lib.check(_lib.lib().csb200_gaxpy_dev(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr)), "gaxpy_dev")
+
+    def gaxpy_t_dev(self, x_ptr: int, y_ptr: int):
+        """y[0..n) += A'*x[0..m): this matrix used directly as a CSR view (csb200_gaxpy_t_dev)."""
+        _lib.check(_lib.lib().csb200_gaxpy_t_dev(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr)), "gaxpy_t_dev")
+
+    # gaxpy plan control (tests / benchmarks)
+    def prepare_gaxpy(self):
+        _lib.check(_lib.lib().csb200_gaxpy_prepare(self._h), "gaxpy_prepare")
+
+    def gaxpy_plan(self) -> str:
+        k = C.c_int()
+        _lib.check(_lib.lib().csb200_gaxpy_plan(self._h, C.byref(k)), "gaxpy_plan")
+        return {1: "stream", 2: "merge"}.get(k.value, "none")
+
+    def force_gaxpy_plan(self, kind: Optional[str]):
+        code = {None: 0, "auto": 0, "stream": 1, "merge": 2}[kind]
+        _lib.check(_lib.lib().csb200_gaxpy_force_plan(self._h, code))
+
+
+def upload(A, validate: bool = True) -> DeviceMatrix:
+    """Copy a CSC ``cs`` (lists, array.array or numpy) into HBM."""
+    if isinstance(A, DeviceMatrix):
+        return A
+    if not CS_CSC(A):
+        raise ValueError("upload: a compressed-column cs is required")
+    n = A.n
+    p = _i32(A.p, n + 1)
+    nnz = int(p[n]) if n + 1 <= len(p) else 0
+    if nnz < 0 or nnz > len(A.i) or (A.x is not None and nnz > len(A.x)):
+        raise ValueError("upload: p[n] exceeds the length of i / x")
+    i = _i32(A.i, nnz)
+    x = None if A.x is None else _f64(A.x, nnz)
+    out = C.c_void_p()
+    st = _lib.check(_lib.lib().csb200_mat_upload(A.m, n, _ptr(p), _ptr(i), _ptr(x), 1 if validate else 0,
+                                                 C.byref(out)), "upload")
+    if st == _lib.ERR_ARG:
+        raise ValueError(_lib.last_error())
+    return DeviceMatrix(out.value)
+
+
+def from_arrays(m, n, p, i, x=None, validate: bool = True) -> DeviceMatrix:
+    """Upload numpy CSC arrays without building a ``cs``."""
+    A = cs()
+    A.m, A.n, A.nz, A.p, A.i, A.x = m, n, -1, p, i, x
+    A.nzmax = max(len(i), 1)
+    return upload(A, validate)
+
+
+def _as_device(A):
+    """(DeviceMatrix, temporary?) for a cs or DeviceMatrix operand."""
+    if isinstance(A, DeviceMatrix):
+        return A, False
+    return upload(A), True
+
+
+# ---- the four reference functions ---------------------------------------------
+
+def cs_cumsum(p, c, n):
+    """p [0..n] = cumulative sum of c [0..n-1], and then copy p [0..n-1] into c.
+
+    Reference: csparse.py:767-784.  Returns sum(c), or -1 if p or c is None.
+    Runs the decoupled look-back scan kernel (csb200_cumsum).
+    """
+    if p is None or c is None:
+        return -1
+    cc = _i32(c, n).copy()
+    pp = np.empty(n + 1, np.int32)
+    total = C.c_int64()
+    _lib.check(_lib.lib().csb200_cumsum(_ptr(pp), _ptr(cc), n, C.byref(total)), "cs_cumsum")
+    if isinstance(p, np.ndarray):
+        p[: n + 1] = pp
+    else:
+        p[: n + 1] = pp.tolist()
+    if n > 0:
+        if isinstance(c, np.ndarray):
+            c[:n] = cc
+        else:
+            c[:n] = cc.tolist()
+    return int(total.value)
+
+
+def cs_transpose(A, values):
+    """Computes the transpose of a sparse matrix, C = A'.
+
+    Reference: csparse.py:2292-2315.  Returns None unless A is compressed-column.
+    The result's p, i and x are bit-identical to the reference's (stable order
+    inside every column).  A DeviceMatrix in gives a DeviceMatrix out.
+    """
+    if not CS_CSC(A):
+        return None
+    dA, tmp = _as_device(A)
+    out = C.c_void_p()
+    _lib.check(_lib.lib().csb200_transpose(dA._h, 1 if values else 0, C.byref(out)), "cs_transpose")
+    dC = DeviceMatrix(out.value)
+    if not tmp:
+        return dC
+    dA.free()
+    return dC.download(trim=False)
+
+
+def cs_gaxpy(A, x, y):
+    """Sparse matrix times dense column vector, y = A*x+y.
+
+    Reference: csparse.py:1199-1213.  Returns False if A is not compressed-column
+    or x / y is None, True otherwise; y is updated in place.  A pattern-only
+    matrix raises TypeError (the reference fails the same way on ``None * x``).
+    """
+    if not CS_CSC(A) or x is None or y is None:
+        return False
+    has_x = A.has_values if isinstance(A, DeviceMatrix) else A.x is not None
+    if not has_x:
+        raise TypeError("cs_gaxpy: matrix has no numerical values (A.x is None)")
+    dA, tmp = _as_device(A)
+    xx = _f64(x, dA.n)
+    inplace = (isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous
+               and y.flags.writeable)
+    ybuf = y[: dA.m] if inplace else np.array(y[: dA.m], dtype=np.float64)
+    _lib.check(_lib.lib().csb200_gaxpy(dA._h, _ptr(xx), _ptr(ybuf)), "cs_gaxpy")
+    if tmp:
+        dA.free()
+    if not inplace:
+        y[: dA.m] = ybuf.tolist() if isinstance(y, list) else ybuf
+    return True
+
+
+def cs_multiply(A, B):
+    """Sparse matrix multiplication, C = A*B.
+
+    Reference: csparse.py:1608-1642 (inner kernel cs_scatter, :1961-1989).
+    Returns None unless both are compressed-column and A.n == B.m.  Structural
+    zeros are kept; the columns of C are in the reference's discovery order;
+    C.x is None when A or B is pattern-only; nzmax == nnz(C) (possibly 0).
+    """
+    if not CS_CSC(A) or not CS_CSC(B):
+        return None
+    if A.n != B.m:
+        return None
+    dA, ta = _as_device(A)
+    dB, tb = (dA, False) if B is A else _as_device(B)
+    out = C.c_void_p()
+    _lib.check(_lib.lib().csb200_multiply(dA._h, dB._h, C.byref(out)), "cs_multiply")
+    dC = DeviceMatrix(out.value)
+    if ta:
+        dA.free()
+    if tb:
+        dB.free()
+    if isinstance(A, DeviceMatrix) and isinstance(B, DeviceMatrix):
+        return dC
+    return dC.download(trim=True)
+
+
+def set_stream(cuda_stream: int = 0):
+    """CUDA stream (raw handle, e.g. torch.cuda.current_stream().cuda_stream) used by this
+    thread's subsequent calls; 0 selects the legacy default stream."""
+    _lib.check(_lib.lib().csb200_set_stream(C.c_void_p(cuda_stream or None)))
+
+
+def set_device(device: int):
+    _lib.check(_lib.lib().csb200_set_device(int(device)), "set_device")
+
+
+def synchronize():
+    _lib.check(_lib.lib().csb200_synchronize(), "synchronize")
+
+
+def gaxpy_host(m, n, Ap, Ai, Ax, x, y):
+    """One-shot cs_gaxpy on host buffers given as raw addresses or numpy arrays
+    (csb200_gaxpy_host: upload + CSR build + SpMV + download of y)."""
+    def ad(a):
+        return C.c_void_p(a) if isinstance(a, int) else _ptr(a)
+    _lib.check(_lib.lib().csb200_gaxpy_host(m, n, ad(Ap), ad(Ai), ad(Ax), ad(x), ad(y)), "gaxpy_host")
+
+
+def last_multiply_flops() -> int:
+    """Multiply-adds performed by the last cs_multiply on this thread."""
+    return int(_lib.lib().csb200_multiply_last_flops())
+
+
+def launch_count() -> int:
+    """Kernels launched by libcsparse_b200.so since it was loaded."""
+    return int(_lib.lib().csb200_launch_count())

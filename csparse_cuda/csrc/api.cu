@@ -1,0 +1,437 @@
+// api.cu -- the extern "C" surface of libcsparse_b200.so (include/csparse_b200.h):
+// library state, matrix handles, and the host-buffer / device-buffer forms of
+// cs_cumsum, cs_transpose, cs_gaxpy and cs_multiply.
+#include "common.cuh"
+
+#include <mutex>
+#include <new>
+
+namespace csb {
+
+std::atomic<int64_t> g_launches{0};
+
+ThreadState &tls()
+{
+    static thread_local ThreadState st;
+    return st;
+}
+
+int set_error(int status, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tls().err, sizeof(tls().err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int ensure_device()
+{
+    static std::mutex mu;
+    static bool tuned[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(CSB200_ERR_CUDA, "no usable CUDA device: %s (libcsparse_b200 has no CPU fallback)",
+                         cudaGetErrorString(e));
+    }
+    if (dev >= 0 && dev < 64 && !tuned[dev]) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!tuned[dev]) {
+            cudaMemPool_t pool;
+            e = cudaDeviceGetDefaultMemPool(&pool, dev);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return set_error(CSB200_ERR_CUDA, "no usable CUDA device: %s (libcsparse_b200 has no CPU fallback)",
+                                 cudaGetErrorString(e));
+            }
+            unsigned long long keep = ~0ull;   // keep freed blocks cached in the pool
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            tuned[dev] = true;
+        }
+    }
+    return CSB200_OK;
+}
+
+// implemented in transpose.cu / spmv.cu / spgemm.cu
+int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out);
+int spmv_run(csb200_mat *AT, const double *d_x, double *d_y);
+int spmv_build_plan(csb200_mat *AT);
+void spmv_plan_free(SpmvPlan *pl);
+int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out);
+int spmv_plan_kind(const SpmvPlan *pl);
+
+// p[0] == 0, p non-decreasing, 0 <= i < m
+__global__ void k_validate(int m, int n, const csi *__restrict__ p, const csi *__restrict__ i, long long nnz, int *bad)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long j = t0; j < n; j += stride)
+        if (p[j] > p[j + 1] || p[j] < 0) *bad = 1;
+    if (t0 == 0 && p[0] != 0) *bad = 1;
+    for (long long q = t0; q < nnz; q += stride) {
+        const int r = i[q];
+        if (r < 0 || r >= m) *bad = 2;
+    }
+}
+
+__global__ void k_rebase(const csi *__restrict__ src, int count, int base, csi *__restrict__ dst)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) dst[k] = src[k] - base;
+}
+
+static int mat_alloc(csi m, csi n, long long nnz, bool has_x, csb200_mat **out)
+{
+    csb200_mat *A = new (std::nothrow) csb200_mat();
+    if (!A) return set_error(CSB200_ERR_NOMEM, "out of host memory");
+    A->m = m; A->n = n; A->nnz = nnz;
+    cudaGetDevice(&A->device);
+    const size_t cap = (size_t)(nnz > 0 ? nnz : 1);
+    int st = dev_alloc(&A->p, (size_t)n + 1);
+    if (st == CSB200_OK) st = dev_alloc(&A->i, cap);
+    if (st == CSB200_OK && has_x) st = dev_alloc(&A->x, cap);
+    if (st != CSB200_OK) { csb200_mat_free(A); return st; }
+    *out = A;
+    return CSB200_OK;
+}
+
+static int ensure_csr(csb200_mat *A)
+{
+    if (A->csr) return CSB200_OK;
+    if (!A->x) return set_error(CSB200_ERR_ARG, "cs_gaxpy: matrix has no values");
+    CSB_TRY(transpose_impl(A, true, &A->csr));
+    A->csr->forced_plan = A->forced_plan;
+    return CSB200_OK;
+}
+
+}  // namespace csb
+
+using namespace csb;
+
+extern "C" {
+
+int csb200_version(void) { return 100; }
+
+const char *csb200_last_error(void) { return tls().err; }
+
+int csb200_device_count(int *count)
+{
+    if (!count) return set_error(CSB200_ERR_ARG, "null argument");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return set_error(CSB200_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return CSB200_OK;
+}
+
+int csb200_set_device(int device)
+{
+    CSB_CUDA(cudaSetDevice(device));
+    return CSB200_OK;
+}
+
+int csb200_set_stream(void *cuda_stream)
+{
+    tls().stream = (cudaStream_t)cuda_stream;
+    return CSB200_OK;
+}
+
+int csb200_synchronize(void)
+{
+    CSB_CUDA(cudaStreamSynchronize(stream()));
+    return CSB200_OK;
+}
+
+int csb200_sm_count(int *count)
+{
+    if (!count) return set_error(CSB200_ERR_ARG, "null argument");
+    int dev = 0;
+    CSB_CUDA(cudaGetDevice(&dev));
+    CSB_CUDA(cudaDeviceGetAttribute(count, cudaDevAttrMultiProcessorCount, dev));
+    return CSB200_OK;
+}
+
+int64_t csb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- cs_cumsum ---------------------------------------------------------------------
+int csb200_cumsum_dev(csi *d_p, csi *d_c, csi n, int64_t *total)
+{
+    if (!d_p || !d_c || n < 0) return set_error(CSB200_ERR_ARG, "cs_cumsum: null array or n < 0");
+    DevBuf<long long> d_total;
+    CSB_TRY(d_total.alloc(1));
+    CSB_TRY(launch_excl_scan(d_p, d_c, n, d_total.ptr, nullptr));
+    long long h = 0;
+    CSB_CUDA(cudaMemcpyAsync(&h, d_total.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream()));
+    CSB_CUDA(cudaStreamSynchronize(stream()));
+    if (total) *total = h;
+    if (h > 0x7fffffffLL || h < -0x80000000LL)
+        return set_error(CSB200_ERR_OVERFLOW, "cs_cumsum: total %lld does not fit int32", h);
+    return CSB200_OK;
+}
+
+int csb200_cumsum(csi *p, csi *c, csi n, int64_t *total)
+{
+    if (!p || !c || n < 0) return set_error(CSB200_ERR_ARG, "cs_cumsum: null array or n < 0");
+    DevBuf<csi> d_p, d_c;
+    CSB_TRY(d_p.alloc((size_t)n + 1));
+    CSB_TRY(d_c.alloc((size_t)n + 1));
+    if (n > 0) CSB_CUDA(cudaMemcpyAsync(d_c.ptr, c, (size_t)n * sizeof(csi), cudaMemcpyHostToDevice, stream()));
+    int st = csb200_cumsum_dev(d_p.ptr, d_c.ptr, n, total);
+    if (st != CSB200_OK && st != CSB200_ERR_OVERFLOW) return st;
+    CSB_CUDA(cudaMemcpyAsync(p, d_p.ptr, ((size_t)n + 1) * sizeof(csi), cudaMemcpyDeviceToHost, stream()));
+    if (n > 0) CSB_CUDA(cudaMemcpyAsync(c, d_c.ptr, (size_t)n * sizeof(csi), cudaMemcpyDeviceToHost, stream()));
+    CSB_CUDA(cudaStreamSynchronize(stream()));
+    return st;
+}
+
+// ---- handles ---------------------------------------------------------------------------
+int csb200_mat_upload(csi m, csi n, const csi *p, const csi *i, const double *x, int validate,
+                      csb200_mat **out)
+{
+    if (!out) return set_error(CSB200_ERR_ARG, "null out");
+    *out = nullptr;
+    if (m < 0 || n < 0 || !p || (!i && p[n] > 0)) return set_error(CSB200_ERR_ARG, "mat_upload: bad arguments");
+    const long long nnz = p[n];
+    if (nnz < 0) return set_error(CSB200_ERR_INDEX, "mat_upload: p[n] < 0");
+    csb200_mat *A = nullptr;
+    CSB_TRY(mat_alloc(m, n, nnz, x != nullptr, &A));
+    cudaStream_t s = stream();
+    cudaError_t e = cudaMemcpyAsync(A->p, p, ((size_t)n + 1) * sizeof(csi), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(A->i, i, (size_t)nnz * sizeof(csi), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && nnz > 0 && x) e = cudaMemcpyAsync(A->x, x, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && nnz == 0) {
+        e = cudaMemsetAsync(A->i, 0, sizeof(csi), s);
+        if (e == cudaSuccess && x) e = cudaMemsetAsync(A->x, 0, sizeof(double), s);
+    }
+    if (e != cudaSuccess) {
+        csb200_mat_free(A);
+        return set_error(CSB200_ERR_CUDA, "mat_upload copy: %s", cudaGetErrorString(e));
+    }
+    if (validate) {
+        DevBuf<int> bad;
+        int st = bad.alloc(1);
+        if (st != CSB200_OK) { csb200_mat_free(A); return st; }
+        cudaMemsetAsync(bad.ptr, 0, sizeof(int), s);
+        const long long work = nnz > n ? nnz : n;
+        const int blocks = (int)(work / 256 + 1 < 148 * 32 ? work / 256 + 1 : 148 * 32);
+        k_validate<<<blocks, 256, 0, s>>>(m, n, A->p, A->i, nnz, bad.ptr);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        int h = 0;
+        e = cudaMemcpyAsync(&h, bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            csb200_mat_free(A);
+            return set_error(CSB200_ERR_CUDA, "mat_upload validate: %s", cudaGetErrorString(e));
+        }
+        if (h) {
+            csb200_mat_free(A);
+            return set_error(CSB200_ERR_INDEX, h == 1 ? "column pointers are not a monotone sequence from 0"
+                                                      : "row index outside [0, m)");
+        }
+    } else {
+        // the host buffers may be reused by the caller as soon as we return
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            csb200_mat_free(A);
+            return set_error(CSB200_ERR_CUDA, "mat_upload: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = A;
+    return CSB200_OK;
+}
+
+int csb200_mat_from_dev(csi m, csi n, const csi *d_p, const csi *d_i, const double *d_x, csb200_mat **out)
+{
+    if (!out) return set_error(CSB200_ERR_ARG, "null out");
+    *out = nullptr;
+    if (m < 0 || n < 0 || !d_p) return set_error(CSB200_ERR_ARG, "mat_from_dev: bad arguments");
+    csi nnz32 = 0;
+    CSB_CUDA(cudaMemcpyAsync(&nnz32, d_p + n, sizeof(csi), cudaMemcpyDeviceToHost, stream()));
+    CSB_CUDA(cudaStreamSynchronize(stream()));
+    const long long nnz = nnz32;
+    if (nnz < 0 || (nnz > 0 && !d_i)) return set_error(CSB200_ERR_ARG, "mat_from_dev: bad nnz / null i");
+    csb200_mat *A = nullptr;
+    CSB_TRY(mat_alloc(m, n, nnz, d_x != nullptr, &A));
+    cudaStream_t s = stream();
+    cudaError_t e = cudaMemcpyAsync(A->p, d_p, ((size_t)n + 1) * sizeof(csi), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(A->i, d_i, (size_t)nnz * sizeof(csi), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && nnz > 0 && d_x) e = cudaMemcpyAsync(A->x, d_x, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) {
+        csb200_mat_free(A);
+        return set_error(CSB200_ERR_CUDA, "mat_from_dev copy: %s", cudaGetErrorString(e));
+    }
+    *out = A;
+    return CSB200_OK;
+}
+
+int csb200_mat_dims(const csb200_mat *A, csi *m, csi *n, int64_t *nnz, int *has_values)
+{
+    if (!A) return set_error(CSB200_ERR_ARG, "null matrix");
+    if (m) *m = A->m;
+    if (n) *n = A->n;
+    if (nnz) *nnz = A->nnz;
+    if (has_values) *has_values = A->x != nullptr;
+    return CSB200_OK;
+}
+
+int csb200_mat_download(const csb200_mat *A, csi *p, csi *i, double *x)
+{
+    if (!A) return set_error(CSB200_ERR_ARG, "null matrix");
+    cudaStream_t s = stream();
+    if (p) CSB_CUDA(cudaMemcpyAsync(p, A->p, ((size_t)A->n + 1) * sizeof(csi), cudaMemcpyDeviceToHost, s));
+    if (i && A->nnz > 0) CSB_CUDA(cudaMemcpyAsync(i, A->i, (size_t)A->nnz * sizeof(csi), cudaMemcpyDeviceToHost, s));
+    if (x && A->x && A->nnz > 0) CSB_CUDA(cudaMemcpyAsync(x, A->x, (size_t)A->nnz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CSB_CUDA(cudaStreamSynchronize(s));
+    return CSB200_OK;
+}
+
+int csb200_mat_dev_ptrs(const csb200_mat *A, csi **d_p, csi **d_i, double **d_x)
+{
+    if (!A) return set_error(CSB200_ERR_ARG, "null matrix");
+    if (d_p) *d_p = A->p;
+    if (d_i) *d_i = A->i;
+    if (d_x) *d_x = A->x;
+    return CSB200_OK;
+}
+
+int csb200_mat_col_slice(const csb200_mat *A, csi j0, csi j1, csb200_mat **out)
+{
+    if (!A || !out || j0 < 0 || j1 < j0 || j1 > A->n) return set_error(CSB200_ERR_ARG, "mat_col_slice: bad range");
+    *out = nullptr;
+    csi h[2] = {0, 0};
+    CSB_CUDA(cudaMemcpyAsync(&h[0], A->p + j0, sizeof(csi), cudaMemcpyDeviceToHost, stream()));
+    CSB_CUDA(cudaMemcpyAsync(&h[1], A->p + j1, sizeof(csi), cudaMemcpyDeviceToHost, stream()));
+    CSB_CUDA(cudaStreamSynchronize(stream()));
+    const long long nnz = (long long)h[1] - h[0];
+    csb200_mat *S = nullptr;
+    CSB_TRY(mat_alloc(A->m, j1 - j0, nnz, A->x != nullptr, &S));
+    cudaStream_t s = stream();
+    const int count = j1 - j0 + 1;
+    k_rebase<<<ceil_div(count, 256), 256, 0, s>>>(A->p + j0, count, h[0], S->p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(S->i, A->i + h[0], (size_t)nnz * sizeof(csi), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && nnz > 0 && A->x) e = cudaMemcpyAsync(S->x, A->x + h[0], (size_t)nnz * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) {
+        csb200_mat_free(S);
+        return set_error(CSB200_ERR_CUDA, "mat_col_slice: %s", cudaGetErrorString(e));
+    }
+    S->canon = A->canon;
+    *out = S;
+    return CSB200_OK;
+}
+
+int csb200_mat_free(csb200_mat *A)
+{
+    if (!A) return CSB200_OK;
+    if (A->csr) csb200_mat_free(A->csr);
+    if (A->plan) spmv_plan_free(A->plan);
+    dev_free(A->p);
+    dev_free(A->i);
+    dev_free(A->x);
+    delete A;
+    return CSB200_OK;
+}
+
+// ---- cs_transpose ---------------------------------------------------------------------
+int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
+{
+    if (!A || !C) return set_error(CSB200_ERR_ARG, "cs_transpose: null argument");
+    *C = nullptr;
+    return transpose_impl(A, values != 0, C);
+}
+
+int csb200_transpose_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
+                          csi *Cp, csi *Ci, double *Cx)
+{
+    if (!Cp || !Ci) return set_error(CSB200_ERR_ARG, "cs_transpose: null output");
+    csb200_mat *A = nullptr, *C = nullptr;
+    CSB_TRY(csb200_mat_upload(m, n, Ap, Ai, (Ax && Cx) ? Ax : nullptr, 1, &A));
+    int st = transpose_impl(A, Cx != nullptr, &C);
+    if (st == CSB200_OK) st = csb200_mat_download(C, Cp, Ci, Cx);
+    csb200_mat_free(A);
+    csb200_mat_free(C);
+    return st;
+}
+
+// ---- cs_gaxpy -------------------------------------------------------------------------
+int csb200_gaxpy_prepare(csb200_mat *A)
+{
+    if (!A) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null matrix");
+    CSB_TRY(ensure_csr(A));
+    return spmv_build_plan(A->csr);
+}
+
+int csb200_gaxpy_plan(csb200_mat *A, int *kind)
+{
+    if (!A || !kind) return set_error(CSB200_ERR_ARG, "null argument");
+    CSB_TRY(csb200_gaxpy_prepare(A));
+    *kind = spmv_plan_kind(A->csr->plan);
+    return CSB200_OK;
+}
+
+int csb200_gaxpy_force_plan(csb200_mat *A, int kind)
+{
+    if (!A || kind < 0 || kind > 2) return set_error(CSB200_ERR_ARG, "bad plan kind");
+    A->forced_plan = kind;
+    if (A->csr) A->csr->forced_plan = kind;
+    return CSB200_OK;
+}
+
+int csb200_gaxpy_dev(csb200_mat *A, const double *d_x, double *d_y)
+{
+    if (!A || !d_x || !d_y) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null argument");
+    CSB_TRY(ensure_csr(A));
+    return spmv_run(A->csr, d_x, d_y);
+}
+
+int csb200_gaxpy_t_dev(csb200_mat *AT, const double *d_x, double *d_y)
+{
+    if (!AT || !d_x || !d_y) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null argument");
+    return spmv_run(AT, d_x, d_y);
+}
+
+int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
+{
+    if (!A || !x || !y) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null argument");
+    if (!A->x) return set_error(CSB200_ERR_ARG, "cs_gaxpy: matrix has no values");
+    DevBuf<double> d_x, d_y;
+    CSB_TRY(d_x.alloc((size_t)A->n));
+    CSB_TRY(d_y.alloc((size_t)A->m));
+    cudaStream_t s = stream();
+    if (A->n > 0) CSB_CUDA(cudaMemcpyAsync(d_x.ptr, x, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (A->m > 0) CSB_CUDA(cudaMemcpyAsync(d_y.ptr, y, (size_t)A->m * sizeof(double), cudaMemcpyHostToDevice, s));
+    CSB_TRY(csb200_gaxpy_dev(A, d_x.ptr, d_y.ptr));
+    if (A->m > 0) CSB_CUDA(cudaMemcpyAsync(y, d_y.ptr, (size_t)A->m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CSB_CUDA(cudaStreamSynchronize(s));
+    return CSB200_OK;
+}
+
+int csb200_gaxpy_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
+                      const double *x, double *y)
+{
+    if (!Ax) return set_error(CSB200_ERR_ARG, "cs_gaxpy: matrix has no values");
+    if (!x || !y) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null vector");
+    csb200_mat *A = nullptr;
+    CSB_TRY(csb200_mat_upload(m, n, Ap, Ai, Ax, 1, &A));
+    int st = csb200_gaxpy(A, x, y);
+    csb200_mat_free(A);
+    return st;
+}
+
+// ---- cs_multiply ------------------------------------------------------------------------
+int csb200_multiply(const csb200_mat *A, const csb200_mat *B, csb200_mat **C)
+{
+    if (!A || !B || !C) return set_error(CSB200_ERR_ARG, "cs_multiply: null argument");
+    *C = nullptr;
+    if (A->n != B->m) return set_error(CSB200_ERR_ARG, "cs_multiply: A.n != B.m");   // csparse.py:1618-1619
+    return multiply_impl(const_cast<csb200_mat *>(A), const_cast<csb200_mat *>(B), C);
+}
+
+int64_t csb200_multiply_last_flops(void) { return tls().last_flops; }
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+// common.cuh -- shared host/device helpers of libcsparse_b200.so (sm_100a only)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/csparse_b200.h"
+
+namespace csb {
+
+// ---- per-thread library state ---------------------------------------------
+struct ThreadState {
+    cudaStream_t stream = nullptr;   // legacy default stream unless csb200_set_stream
+    char err[640] = {0};
+    int64_t last_flops = 0;
+};
+ThreadState &tls();
+extern std::atomic<int64_t> g_launches;
+
+int set_error(int status, const char *fmt, ...);
+
+#define CSB_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return csb::set_error(CSB200_ERR_CUDA, "%s: %s (%s:%d)", #expr,              \
+                                  cudaGetErrorString(e__), __FILE__, __LINE__);          \
+    } while (0)
+
+#define CSB_TRY(expr)                                                                    \
+    do {                                                                                 \
+        int s__ = (expr);                                                                \
+        if (s__ != CSB200_OK) return s__;                                                \
+    } while (0)
+
+// call right after a <<<>>> launch
+#define CSB_LAUNCHED()                                                                   \
+    do {                                                                                 \
+        csb::g_launches.fetch_add(1, std::memory_order_relaxed);                         \
+        CSB_CUDA(cudaGetLastError());                                                    \
+    } while (0)
+
+inline cudaStream_t stream() { return tls().stream; }
+
+// stream-ordered allocation from the device's default memory pool (cached: the
+// release threshold is raised once per device in ensure_device()).
+int ensure_device();
+template <class T>
+inline int dev_alloc(T **p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CSB_TRY(ensure_device());
+    cudaError_t e = cudaMallocAsync((void **)p, count * sizeof(T), stream());
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(e == cudaErrorMemoryAllocation ? CSB200_ERR_NOMEM : CSB200_ERR_CUDA,
+                         "cudaMallocAsync(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+    }
+    return CSB200_OK;
+}
+inline void dev_free(void *p)
+{
+    if (p) cudaFreeAsync(p, stream());
+}
+
+// RAII for temporaries inside an API call
+template <class T>
+struct DevBuf {
+    T *ptr = nullptr;
+    ~DevBuf() { dev_free(ptr); }
+    int alloc(size_t count) { return dev_alloc(&ptr, count); }
+    T *release() { T *r = ptr; ptr = nullptr; return r; }
+    operator T *() const { return ptr; }
+};
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- kernels exported between translation units ----------------------------
+// scan.cu : p[0..n] = exclusive scan(c), c[i] <- p[i]; d_total (int64) and
+//           d_max (max element, may be null) are device scalars.
+int launch_excl_scan(csi *d_p, csi *d_c, csi n, long long *d_total, int *d_max);
+
+}  // namespace csb
+
+// ---- the opaque matrix handle ------------------------------------------------
+struct SpmvPlan;
+struct csb200_mat {
+    csi m = 0, n = 0;
+    int64_t nnz = 0;
+    csi *p = nullptr;      // n+1, device
+    csi *i = nullptr;      // max(nnz,1), device
+    double *x = nullptr;   // max(nnz,1) or null (pattern only)
+    int device = 0;
+    // lazily computed facts / caches (handles are logically immutable)
+    int canon = -1;              // 1: every column strictly increasing (=> no duplicate entries)
+    csi max_col_len = -1;        // longest column
+    csb200_mat *csr = nullptr;   // cached transpose with values == CSR view of this matrix
+    SpmvPlan *plan = nullptr;    // gaxpy plan over this matrix interpreted as a CSR view (columns = rows)
+    int forced_plan = 0;
+};
+
+// ---- device helpers -----------------------------------------------------------
+#ifdef __CUDACC__
+namespace csb {
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+
+// streaming (read-once) loads: bypass L1 allocation
+__device__ __forceinline__ int4 ldg_stream(const int4 *p)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ldg_stream(const double2 *p)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                 : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int ldg_stream(const int *p)
+{
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ldg_stream(const double *p)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+// largest j in [lo, hi] with a[j] <= v  (a non-decreasing, a[lo] <= v assumed)
+__device__ __forceinline__ int upper_row(const int *a, int lo, int hi, int v)
+{
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (a[mid] <= v) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+}  // namespace csb
+#endif

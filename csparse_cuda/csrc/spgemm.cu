@@ -1,0 +1,512 @@
+// spgemm.cu -- cs_multiply (csparse.py:1608-1642) and its inner kernel cs_scatter
+// (csparse.py:1961-1989): C = A*B, column by column (Gustavson), as a two-phase
+// SpGEMM:
+//
+//   k_ub        per column j of B: ub[j] = sum_k nnz(A(:,k)) over k in B(:,j)
+//               (the number of multiply-adds; also the size bound used for binning)
+//   k_bin       columns -> work lists by size class (no host round trip per class)
+//   k_sym_*     symbolic: cnt[j] = |union of the patterns A(:,k)|  -- structural,
+//               explicit and cancelled zeros count, exactly like cs_scatter's mark test
+//   excl_scan   Cp = cumsum(cnt) (scan.cu); replaces the reference's realloc doubling
+//   k_num_*     numeric: hash-accumulate x[i] += B(k,j)*A(i,k), emit (Ci, Cx)
+//
+// The reference's dense workspaces w[m] (marks) and x[m] (accumulator) become a
+// per-warp hash table in shared memory (row -> discovery position) plus dense
+// per-position arrays; columns too large for shared memory use the reference's
+// own dense w[m]/x[m] scheme in global memory, one workspace per resident CTA.
+//
+// Order and rounding: a warp walks B(:,j) in storage order and each A(:,k) in
+// storage order (32 entries per step, lane = storage offset), products are
+// rounded before they are added, first touch assigns.  New rows are ranked by
+// ballot/popc, so C's columns come out in the reference's DISCOVERY ORDER and the
+// sums are formed in the reference's order: p, i and x are bit-identical to
+// cs_multiply, not merely equal after a sort.  (A with duplicate entries inside a
+// column makes two lanes hit one row in a step; that case is serialised in lane
+// order, see CANON.)
+#include "common.cuh"
+
+namespace csb {
+
+constexpr int EMPTY = -1;
+
+__device__ __forceinline__ unsigned hash_row(int i, int logh)
+{
+    return ((unsigned)i * 0x9E3779B1u) >> (32 - logh);
+}
+
+// ---- sizes and bins ------------------------------------------------------------
+__global__ void k_ub(int nB, const csi *__restrict__ Bp, const csi *__restrict__ Bi,
+                     const csi *__restrict__ Ap, int *__restrict__ ub, unsigned long long *flops)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    long long s = 0;
+    if (j < nB) {
+        for (int p = Bp[j]; p < Bp[j + 1]; p++) {
+            const int k = Bi[p];
+            s += Ap[k + 1] - Ap[k];
+        }
+        ub[j] = (int)min(s, (long long)INT_MAX);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(flops, (unsigned long long)s);
+}
+
+// size[j] -> class by thresholds t0 < t1 < t2: 0 -> skipped, (0,t0] -> list 0,
+// (t0,t1] -> list 1, (t1,t2] -> list 2, > t2 -> list 3
+__global__ void k_bin(int n, const int *__restrict__ size, int cap, int t0, int t1, int t2,
+                      int *__restrict__ lists, int *__restrict__ counts)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int s = min(size[j], cap);
+    if (s <= 0) return;
+    const int b = s <= t0 ? 0 : s <= t1 ? 1 : s <= t2 ? 2 : 3;
+    lists[(size_t)b * n + atomicAdd(&counts[b], 1)] = j;
+}
+
+// ---- symbolic, one warp per column, hash set in shared memory ---------------------
+template <int LOGH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_sym_warp(const int *__restrict__ list, int ncols,
+           const csi *__restrict__ Ap, const csi *__restrict__ Ai,
+           const csi *__restrict__ Bp, const csi *__restrict__ Bi, int *__restrict__ cnt_out)
+{
+    constexpr int H = 1 << LOGH;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *tab = reinterpret_cast<int *>(sm_raw) + wid * H;
+    const int nwarps = gridDim.x * WARPS;
+    for (int idx = blockIdx.x * WARPS + wid; idx < ncols; idx += nwarps) {
+        const int j = list[idx];
+        for (int s = lane; s < H; s += 32) tab[s] = EMPTY;
+        __syncwarp();
+        int mine = 0;
+        const int pb_end = Bp[j + 1];
+        for (int pb0 = Bp[j]; pb0 < pb_end; pb0 += 32) {
+            const int my_pb = pb0 + lane;
+            int my_ab = 0, my_ae = 0;
+            if (my_pb < pb_end) {
+                const int k = Bi[my_pb];
+                my_ab = Ap[k];
+                my_ae = Ap[k + 1];
+            }
+            const int nb = min(32, pb_end - pb0);
+            for (int s = 0; s < nb; s++) {
+                const int ab = __shfl_sync(0xffffffffu, my_ab, s);
+                const int ae = __shfl_sync(0xffffffffu, my_ae, s);
+                for (int pa = ab + lane; pa < ae; pa += 32) {
+                    const int i = Ai[pa];
+                    unsigned h = hash_row(i, LOGH);
+                    while (true) {
+                        const int old = atomicCAS(&tab[h], EMPTY, i);
+                        if (old == EMPTY) { mine++; break; }
+                        if (old == i) break;
+                        h = (h + 1) & (H - 1);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0) cnt_out[j] = mine;
+        __syncwarp();
+    }
+}
+
+// ---- symbolic, one CTA per column, dense marks in global memory --------------------
+// marks[ws][m] plays the reference's w[] (csparse.py:1624): zero-initialised once,
+// never cleared; the mark of a column is a per-workspace counter + 1.
+__global__ void __launch_bounds__(256)
+k_sym_dense(const int *__restrict__ list, int ncols, int m,
+            const csi *__restrict__ Ap, const csi *__restrict__ Ai,
+            const csi *__restrict__ Bp, const csi *__restrict__ Bi,
+            int *marks, int *__restrict__ cnt_out)
+{
+    __shared__ int s_cnt;
+    int *w = marks + (size_t)blockIdx.x * m;
+    int mark = 0;
+    for (int idx = blockIdx.x; idx < ncols; idx += gridDim.x) {
+        const int j = list[idx];
+        mark++;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        int mine = 0;
+        for (int pb = Bp[j]; pb < Bp[j + 1]; pb++) {
+            const int k = Bi[pb];
+            for (int pa = Ap[k] + threadIdx.x; pa < Ap[k + 1]; pa += blockDim.x)
+                if (atomicMax(&w[Ai[pa]], mark) < mark) mine++;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+        __syncthreads();
+        if (threadIdx.x == 0) cnt_out[j] = s_cnt;
+        __syncthreads();
+    }
+}
+
+// ---- numeric, one warp per column ---------------------------------------------------
+// Shared memory per warp: keys[H] (row or EMPTY), poss[H] (discovery position of
+// that row), rowlist[CAP], vals[CAP].  CANON: every column of A has distinct rows.
+template <int LOGH, int CAP, int WARPS, bool VALUES, bool CANON>
+__global__ void __launch_bounds__(WARPS * 32)
+k_num_warp(const int *__restrict__ list, int ncols,
+           const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+           const csi *__restrict__ Bp, const csi *__restrict__ Bi, const double *__restrict__ Bx,
+           const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+{
+    constexpr int H = 1 << LOGH;
+    constexpr int PER_WARP = 2 * H * 4 + CAP * 4 + CAP * 8;      // bytes
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *base = sm_raw + (size_t)wid * PER_WARP;
+    double *vals = reinterpret_cast<double *>(base);                       // CAP doubles first (alignment)
+    int *keys = reinterpret_cast<int *>(base + CAP * 8);
+    int *poss = keys + H;
+    int *rowlist = poss + H;
+    const unsigned lt = lanemask_lt();
+    const int nwarps = gridDim.x * WARPS;
+
+    for (int idx = blockIdx.x * WARPS + wid; idx < ncols; idx += nwarps) {
+        const int j = list[idx];
+        for (int s = lane; s < H; s += 32) keys[s] = EMPTY;
+        __syncwarp();
+        int cnt = 0;                                   // warp-uniform: rows discovered so far
+        const int pb_end = Bp[j + 1];
+        for (int pb0 = Bp[j]; pb0 < pb_end; pb0 += 32) {
+            const int my_pb = pb0 + lane;
+            int my_ab = 0, my_ae = 0;
+            double my_beta = 1.0;                      // pattern-only B: coefficient 1 (csparse.py:1636)
+            if (my_pb < pb_end) {
+                const int k = Bi[my_pb];
+                my_ab = Ap[k];
+                my_ae = Ap[k + 1];
+                if (VALUES) my_beta = Bx[my_pb];
+            }
+            const int nb = min(32, pb_end - pb0);
+            for (int s = 0; s < nb; s++) {
+                const int ab = __shfl_sync(0xffffffffu, my_ab, s);
+                const int ae = __shfl_sync(0xffffffffu, my_ae, s);
+                const double beta = __shfl_sync(0xffffffffu, my_beta, s);
+                for (int pa0 = ab; pa0 < ae; pa0 += 32) {          // warp-uniform trip count
+                    const int pa = pa0 + lane;
+                    const bool active = pa < ae;
+                    int i = 0;
+                    double prod = 0.0;
+                    if (active) {
+                        i = Ai[pa];
+                        if (VALUES) prod = __dmul_rn(beta, Ax[pa]);
+                    }
+                    bool leader = active;              // lane that performs the insert for its row
+                    int lead_lane = lane;
+                    if (!CANON) {
+                        const unsigned act = __ballot_sync(0xffffffffu, active);
+                        if (active) {
+                            const unsigned peers = __match_any_sync(act, i);
+                            lead_lane = __ffs(peers) - 1;
+                            leader = lead_lane == lane;
+                        }
+                    }
+                    int slot = 0;
+                    bool isnew = false;
+                    if (leader) {
+                        unsigned h = hash_row(i, LOGH);
+                        while (true) {
+                            const int old = atomicCAS(&keys[h], EMPTY, i);
+                            if (old == EMPTY) { isnew = true; break; }
+                            if (old == i) break;
+                            h = (h + 1) & (H - 1);
+                        }
+                        slot = (int)h;
+                    }
+                    const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
+                    if (isnew) {
+                        const int pos = cnt + __popc(newmask & lt);
+                        poss[slot] = pos;
+                        rowlist[pos] = i;
+                        if (VALUES) vals[pos] = prod;              // first touch assigns (csparse.py:1986)
+                    }
+                    cnt += __popc(newmask);
+                    __syncwarp();
+                    if (VALUES) {
+                        if (CANON) {
+                            if (active && !isnew) {
+                                const int pos = poss[slot];
+                                vals[pos] = __dadd_rn(vals[pos], prod);   // (csparse.py:1988)
+                            }
+                        } else {
+                            slot = __shfl_sync(0xffffffffu, slot, lead_lane);
+                            unsigned pend = __ballot_sync(0xffffffffu, active && !isnew);
+                            while (pend) {                          // storage (= lane) order
+                                const int l = __ffs(pend) - 1;
+                                if (lane == l) {
+                                    const int pos = poss[slot];
+                                    vals[pos] = __dadd_rn(vals[pos], prod);
+                                }
+                                pend &= pend - 1;
+                                __syncwarp();
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        const int out = Cp[j];
+        for (int t = lane; t < cnt; t += 32) {
+            Ci[out + t] = rowlist[t];
+            if (VALUES) Cx[out + t] = vals[t];
+        }
+        __syncwarp();
+    }
+}
+
+// ---- numeric, one CTA per column, dense workspaces in global memory -----------------
+// The reference's algorithm verbatim per column: marks w[m], accumulator x[m]
+// (csparse.py:1624-1626), discovery order by a block-wide rank of the new rows.
+template <bool VALUES, bool CANON>
+__global__ void __launch_bounds__(256)
+k_num_dense(const int *__restrict__ list, int ncols, int m,
+            const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+            const csi *__restrict__ Bp, const csi *__restrict__ Bi, const double *__restrict__ Bx,
+            const csi *__restrict__ Cp, csi *Ci, double *Cx, int *marks, double *acc)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_cnt;
+    int *w = marks + (size_t)blockIdx.x * m;
+    double *x = VALUES ? acc + (size_t)blockIdx.x * m : nullptr;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+    int mark = 0;
+    for (int idx = blockIdx.x; idx < ncols; idx += gridDim.x) {
+        const int j = list[idx];
+        mark++;
+        const int out = Cp[j];
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        for (int pb = Bp[j]; pb < Bp[j + 1]; pb++) {
+            const int k = Bi[pb];
+            const double beta = VALUES ? Bx[pb] : 1.0;
+            const int ab = Ap[k], ae = Ap[k + 1];
+            for (int pa0 = ab; pa0 < ae; pa0 += 256) {
+                const int pa = pa0 + threadIdx.x;
+                const bool active = pa < ae;
+                int i = 0;
+                double prod = 0.0;
+                bool isnew = false;
+                if (active) {
+                    i = Ai[pa];
+                    if (VALUES) prod = __dmul_rn(beta, Ax[pa]);
+                    if (CANON) { isnew = w[i] < mark; if (isnew) w[i] = mark; }
+                    else       { isnew = atomicMax(&w[i], mark) < mark; }
+                }
+                const unsigned nm = __ballot_sync(0xffffffffu, isnew);
+                if (lane == 0) s_warp[wid] = __popc(nm);
+                __syncthreads();
+                int before = s_cnt;
+                for (int u = 0; u < wid; u++) before += s_warp[u];
+                if (isnew) {
+                    Ci[out + before + __popc(nm & lt)] = i;
+                    if (VALUES) x[i] = CANON ? prod : 0.0;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int tot = 0;
+                    for (int u = 0; u < 8; u++) tot += s_warp[u];
+                    s_cnt += tot;
+                }
+                if (VALUES && active) {
+                    if (CANON) { if (!isnew) x[i] = __dadd_rn(x[i], prod); }
+                    else       atomicAdd(&x[i], prod);
+                }
+                __syncthreads();
+            }
+        }
+        if (VALUES) {
+            const int cnt = s_cnt;
+            for (int t = threadIdx.x; t < cnt; t += 256) Cx[out + t] = x[Ci[out + t]];   // csparse.py:1637-1639
+        }
+        __syncthreads();
+    }
+}
+
+// ---- "does every column have strictly increasing rows?" -------------------------------
+__global__ void k_canon(const csi *__restrict__ Ap, const csi *__restrict__ Ai, int n, int nnz, int *bad)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (p >= nnz) return;
+    if (Ai[p - 1] >= Ai[p]) {
+        const int j = upper_row(Ap, 0, n, p);      // column holding entry p
+        if (Ap[j] != p) *bad = 1;                  // descent strictly inside a column
+    }
+}
+
+__global__ void k_col_sizes(int n, const csi *__restrict__ Cp, int *__restrict__ sz)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) sz[j] = Cp[j + 1] - Cp[j];
+}
+
+int mat_is_canonical(csb200_mat *A, int *out)
+{
+    if (A->canon < 0) {
+        if (A->nnz < 2) { A->canon = 1; }
+        else {
+            DevBuf<int> bad;
+            CSB_TRY(bad.alloc(1));
+            CSB_CUDA(cudaMemsetAsync(bad.ptr, 0, sizeof(int), stream()));
+            k_canon<<<ceil_div(A->nnz, 256), 256, 0, stream()>>>(A->p, A->i, A->n, (int)A->nnz, bad.ptr);
+            CSB_LAUNCHED();
+            int h = 0;
+            CSB_CUDA(cudaMemcpyAsync(&h, bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+            CSB_CUDA(cudaStreamSynchronize(stream()));
+            A->canon = h ? 0 : 1;
+        }
+    }
+    *out = A->canon;
+    return CSB200_OK;
+}
+
+// ---- host side ---------------------------------------------------------------------------
+template <int LOGH, int WARPS>
+static int run_sym_warp(const int *list, int ncols, const csb200_mat *A, const csb200_mat *B, int *cnt)
+{
+    if (ncols == 0) return CSB200_OK;
+    const size_t smem = (size_t)WARPS * (1 << LOGH) * sizeof(int);
+    auto kern = k_sym_warp<LOGH, WARPS>;
+    CSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * 16);
+    kern<<<grid, WARPS * 32, smem, stream()>>>(list, ncols, A->p, A->i, B->p, B->i, cnt);
+    CSB_LAUNCHED();
+    return CSB200_OK;
+}
+
+template <int LOGH, int CAP, int WARPS>
+static int run_num_warp(const int *list, int ncols, const csb200_mat *A, const csb200_mat *B,
+                        csb200_mat *C, bool values, bool canon)
+{
+    if (ncols == 0) return CSB200_OK;
+    const size_t smem = (size_t)WARPS * (2 * (1 << LOGH) * 4 + CAP * 12);
+    const int grid = (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * 16);
+#define NUM_LAUNCH(V, K)                                                                          \
+    do {                                                                                          \
+        auto kern = k_num_warp<LOGH, CAP, WARPS, V, K>;                                           \
+        CSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, WARPS * 32, smem, stream()>>>(list, ncols, A->p, A->i, A->x, B->p, B->i, B->x, \
+                                                   C->p, C->i, C->x);                             \
+    } while (0)
+    if (values) { if (canon) NUM_LAUNCH(true, true); else NUM_LAUNCH(true, false); }
+    else        { if (canon) NUM_LAUNCH(false, true); else NUM_LAUNCH(false, false); }
+#undef NUM_LAUNCH
+    CSB_LAUNCHED();
+    return CSB200_OK;
+}
+
+int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
+{
+    const csi m = A->m, n = B->n;
+    const bool values = A->x != nullptr && B->x != nullptr;      // csparse.py:1625
+    cudaStream_t s = stream();
+
+    csb200_mat *C = new csb200_mat();
+    C->m = m; C->n = n; C->device = A->device;
+    auto fail = [&](int st) { csb200_mat_free(C); return st; };
+    int st = dev_alloc(&C->p, (size_t)n + 1);
+    if (st != CSB200_OK) return fail(st);
+
+    int canon = 1;
+    if ((st = mat_is_canonical(A, &canon)) != CSB200_OK) return fail(st);
+
+    DevBuf<int> ub, cnt, lists, counts, marks, marks_num;
+    DevBuf<double> acc;
+    DevBuf<unsigned long long> flops;
+    DevBuf<long long> total;
+    const size_t ncap = (size_t)(n > 0 ? n : 1);
+    if ((st = ub.alloc(ncap)) || (st = cnt.alloc(ncap)) || (st = lists.alloc(4 * ncap)) ||
+        (st = counts.alloc(8)) || (st = flops.alloc(1)) || (st = total.alloc(1)))
+        return fail(st);
+#define MM_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+        set_error(CSB200_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); return fail(CSB200_ERR_CUDA); } } while (0)
+#define MM_LAUNCHED() do { g_launches.fetch_add(1, std::memory_order_relaxed); MM_CUDA(cudaGetLastError()); } while (0)
+#define MM_TRY(expr) do { int s_ = (expr); if (s_ != CSB200_OK) return fail(s_); } while (0)
+    MM_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * sizeof(int), s));
+    MM_CUDA(cudaMemsetAsync(flops.ptr, 0, sizeof(unsigned long long), s));
+    MM_CUDA(cudaMemsetAsync(cnt.ptr, 0, ncap * sizeof(int), s));
+
+    int h_counts[8] = {0};
+    unsigned long long h_flops = 0;
+    constexpr int DENSE_CTAS = 64;
+    if (n > 0) {
+        k_ub<<<ceil_div(n, 256), 256, 0, s>>>(n, B->p, B->i, A->p, ub.ptr, flops.ptr);
+        MM_LAUNCHED();
+        // symbolic classes by min(ub, m): <=256 | <=1024 | <=8192 | dense
+        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, m, 256, 1024, 8192, lists.ptr, counts.ptr);
+        MM_LAUNCHED();
+        MM_CUDA(cudaMemcpyAsync(h_counts, counts.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MM_CUDA(cudaMemcpyAsync(&h_flops, flops.ptr, sizeof(h_flops), cudaMemcpyDeviceToHost, s));
+        MM_CUDA(cudaStreamSynchronize(s));
+        tls().last_flops = (int64_t)h_flops;
+        MM_TRY((run_sym_warp<9, 8>(lists.ptr, h_counts[0], A, B, cnt.ptr)));
+        MM_TRY((run_sym_warp<11, 8>(lists.ptr + ncap, h_counts[1], A, B, cnt.ptr)));
+        MM_TRY((run_sym_warp<14, 2>(lists.ptr + 2 * ncap, h_counts[2], A, B, cnt.ptr)));
+        if (h_counts[3] > 0) {
+            const int ctas = min(DENSE_CTAS, h_counts[3]);
+            MM_TRY(marks.alloc((size_t)ctas * m));
+            MM_CUDA(cudaMemsetAsync(marks.ptr, 0, (size_t)ctas * m * sizeof(int), s));
+            k_sym_dense<<<ctas, 256, 0, s>>>(lists.ptr + 3 * ncap, h_counts[3], m, A->p, A->i, B->p, B->i,
+                                              marks.ptr, cnt.ptr);
+            MM_LAUNCHED();
+        }
+    } else {
+        tls().last_flops = 0;
+    }
+    // Cp = cumsum(cnt); nnz(C)
+    MM_TRY(launch_excl_scan(C->p, cnt.ptr, n, total.ptr, nullptr));
+    // cnt now holds Cp[0..n-1]; the class of a column for the numeric phase is
+    // decided by its exact size Cp[j+1]-Cp[j], recomputed into ub.
+    long long h_total = 0;
+    MM_CUDA(cudaMemcpyAsync(&h_total, total.ptr, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    MM_CUDA(cudaStreamSynchronize(s));
+    if (h_total > 0x7fffffffLL) {
+        set_error(CSB200_ERR_OVERFLOW, "cs_multiply: nnz(C) = %lld does not fit int32", h_total);
+        return fail(CSB200_ERR_OVERFLOW);
+    }
+    C->nnz = h_total;
+    const size_t cap = (size_t)(h_total > 0 ? h_total : 1);
+    MM_TRY(dev_alloc(&C->i, cap));
+    if (values) MM_TRY(dev_alloc(&C->x, cap));
+    if (h_total > 0) {
+        // exact sizes: ub[j] = Cp[j+1] - Cp[j]
+        k_col_sizes<<<ceil_div(n, 256), 256, 0, s>>>(n, C->p, ub.ptr);
+        MM_LAUNCHED();
+        MM_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * sizeof(int), s));
+        // numeric classes by exact column size: <=128 | <=1024 | (unused) | dense
+        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, INT_MAX, 128, 1024, 1024, lists.ptr, counts.ptr);
+        MM_LAUNCHED();
+        MM_CUDA(cudaMemcpyAsync(h_counts, counts.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MM_CUDA(cudaStreamSynchronize(s));
+        MM_TRY((run_num_warp<8, 128, 8>(lists.ptr, h_counts[0], A, B, C, values, canon != 0)));
+        MM_TRY((run_num_warp<11, 1024, 4>(lists.ptr + ncap, h_counts[1], A, B, C, values, canon != 0)));
+        if (h_counts[3] > 0) {
+            const int ctas = min(DENSE_CTAS, h_counts[3]);
+            MM_TRY(marks_num.alloc((size_t)ctas * m));
+            MM_CUDA(cudaMemsetAsync(marks_num.ptr, 0, (size_t)ctas * m * sizeof(int), s));
+            if (values) MM_TRY(acc.alloc((size_t)ctas * m));
+            const int *lst = lists.ptr + 3 * ncap;
+#define DENSE_LAUNCH(V, K) k_num_dense<V, K><<<ctas, 256, 0, s>>>(lst, h_counts[3], m, A->p, A->i, A->x, \
+                                B->p, B->i, B->x, C->p, C->i, C->x, marks_num.ptr, acc.ptr)
+            if (values) { if (canon) DENSE_LAUNCH(true, true); else DENSE_LAUNCH(true, false); }
+            else        { if (canon) DENSE_LAUNCH(false, true); else DENSE_LAUNCH(false, false); }
+#undef DENSE_LAUNCH
+            MM_LAUNCHED();
+        }
+    }
+#undef MM_CUDA
+#undef MM_LAUNCHED
+#undef MM_TRY
+    *out = C;
+    return CSB200_OK;
+}
+
+}  // namespace csb

@@ -1,0 +1,123 @@
+/*
+ * csparse_b200.h -- C ABI of libcsparse_b200.so
+ *
+ * B200-native (sm_100a) replacement for the data-parallel hot path of
+ * rwl/CSparse.py: cs_cumsum, cs_transpose, cs_gaxpy, cs_multiply.  The
+ * reference is pure Python and has no FFI layer: its boundary is
+ * the module namespace.  These entry points are what a ctypes binding of that
+ * namespace binds; each cites the reference function it
+ * replaces as csparse.py:line.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, int32 indices (csi), IEEE binary64 values.
+ *   - every function returns a csb200_status; CSB200_ERR_ARG corresponds to
+ *     the reference's sentinel returns (None / False / -1).
+ *   - "host" entry points take caller-owned host buffers and do the H2D/D2H
+ *     copies themselves; "_dev" entry points take device pointers and are
+ *     asynchronous on the current stream (csb200_set_stream).
+ *   - csb200_mat is an opaque, immutable, device-resident CSC matrix
+ *     (the reference's `cs` object with nz == -1, csparse.py:37-54).
+ *   - no CPU fallback: without a CUDA device every compute call fails with
+ *     CSB200_ERR_CUDA.
+ */
+#ifndef CSPARSE_B200_H
+#define CSPARSE_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CSB200_API __attribute__((visibility("default")))
+#else
+#define CSB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t csi;
+typedef struct csb200_mat csb200_mat;
+
+typedef enum {
+    CSB200_OK = 0,
+    CSB200_ERR_ARG = 1,       /* bad argument: reference returns None / False / -1 */
+    CSB200_ERR_CUDA = 2,      /* CUDA runtime / driver failure (no device, OOM, ...) */
+    CSB200_ERR_OVERFLOW = 3,  /* a count does not fit int32 */
+    CSB200_ERR_INDEX = 4,     /* row index outside [0, m) or p not monotone */
+    CSB200_ERR_NOMEM = 5
+} csb200_status;
+
+/* ---- library state ------------------------------------------------------ */
+CSB200_API int csb200_version(void);
+CSB200_API const char *csb200_last_error(void);              /* thread-local message of the last failure */
+CSB200_API int csb200_device_count(int *count);
+CSB200_API int csb200_set_device(int device);                /* cudaSetDevice for the calling thread */
+CSB200_API int csb200_set_stream(void *cuda_stream);         /* stream used by this thread's calls; NULL = legacy default */
+CSB200_API int csb200_synchronize(void);                     /* cudaStreamSynchronize on that stream */
+CSB200_API int csb200_sm_count(int *count);
+/* number of kernels this library launched since load (all threads); bench.py's gpu_launches */
+CSB200_API int64_t csb200_launch_count(void);
+
+/* ---- cs_cumsum (csparse.py:767-784) ------------------------------------- */
+/* p[0..n] = exclusive prefix sum of c[0..n-1]; c[0..n-1] <- p[0..n-1];
+ * *total = sum(c) as int64.  Only p[0..n] and c[0..n-1] are touched.
+ * Single-pass decoupled look-back scan. */
+CSB200_API int csb200_cumsum(csi *p, csi *c, csi n, int64_t *total);          /* host buffers */
+CSB200_API int csb200_cumsum_dev(csi *d_p, csi *d_c, csi n, int64_t *total);  /* device buffers; synchronises to return total */
+
+/* ---- matrix handles (the cs object, csparse.py:37-54) -------------------- */
+/* nnz is p[n]; i/x may be longer than nnz (tails ignored, as in the reference).
+ * x == NULL => pattern-only matrix (A.x is None).  validate != 0 checks that p
+ * is monotone from 0 and every row index is in [0, m). */
+CSB200_API int csb200_mat_upload(csi m, csi n, const csi *p, const csi *i, const double *x,
+                      int validate, csb200_mat **out);
+/* copy device arrays (d_p has n+1 entries) into a new handle */
+CSB200_API int csb200_mat_from_dev(csi m, csi n, const csi *d_p, const csi *d_i, const double *d_x,
+                        csb200_mat **out);
+CSB200_API int csb200_mat_dims(const csb200_mat *A, csi *m, csi *n, int64_t *nnz, int *has_values);
+CSB200_API int csb200_mat_download(const csb200_mat *A, csi *p, csi *i, double *x);   /* p: n+1, i/x: nnz */
+CSB200_API int csb200_mat_dev_ptrs(const csb200_mat *A, csi **d_p, csi **d_i, double **d_x);
+/* columns [j0, j1) as a new matrix (used to shard B / the CSR view across GPUs) */
+CSB200_API int csb200_mat_col_slice(const csb200_mat *A, csi j0, csi j1, csb200_mat **out);
+CSB200_API int csb200_mat_free(csb200_mat *A);
+
+/* ---- cs_transpose (csparse.py:2292-2315) --------------------------------- */
+/* C = A' as CSC (= CSR view of A): stable counting sort by row index.  Result
+ * p, i, x are bit-identical to the reference's.  C has values iff values != 0
+ * and A has values. */
+CSB200_API int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C);
+/* one-shot form on host buffers: Cp has m+1 slots, Ci/Cx nnz slots (Cx may be NULL) */
+CSB200_API int csb200_transpose_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
+                          csi *Cp, csi *Ci, double *Cx);
+
+/* ---- cs_gaxpy (csparse.py:1199-1213) -------------------------------------- */
+/* y[0..m) += A * x[0..n).  Row-parallel, atomic-free SpMV over the CSR view of
+ * A, which is built once per handle by csb200_transpose and cached. */
+CSB200_API int csb200_gaxpy(csb200_mat *A, const double *x, double *y);           /* host x, y */
+CSB200_API int csb200_gaxpy_dev(csb200_mat *A, const double *d_x, double *d_y);   /* device x, y; async */
+/* y[0..AT.n) += AT' * x[0..AT.m): the same kernel applied to an explicit CSR
+ * view (AT is the CSC of A').  Used by the row-block sharded multi-GPU path. */
+CSB200_API int csb200_gaxpy_t_dev(csb200_mat *AT, const double *d_x, double *d_y);
+/* one-shot form, everything on the host (matrix upload + CSR build + SpMV) */
+CSB200_API int csb200_gaxpy_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
+                      const double *x, double *y);
+/* build (and cache) the CSR view now instead of on first use */
+CSB200_API int csb200_gaxpy_prepare(csb200_mat *A);
+/* which kernel the cached plan uses: 1 = row-stream, 2 = merge-path */
+CSB200_API int csb200_gaxpy_plan(csb200_mat *A, int *kind);
+/* force a plan (0 = automatic); for tests and benchmarks */
+CSB200_API int csb200_gaxpy_force_plan(csb200_mat *A, int kind);
+
+/* ---- cs_multiply (csparse.py:1608-1642, cs_scatter :1961-1989) ------------ */
+/* C = A*B: symbolic per-column count (shared-memory hash sets, dense spill for
+ * large columns), exclusive scan, numeric fill.  Structural zeros are kept.
+ * Columns of C come out in the reference's discovery order.  C has values iff
+ * both A and B have. */
+CSB200_API int csb200_multiply(const csb200_mat *A, const csb200_mat *B, csb200_mat **C);
+/* number of multiply-adds of the last csb200_multiply on this thread */
+CSB200_API int64_t csb200_multiply_last_flops(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSPARSE_B200_H */

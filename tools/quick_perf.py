@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Development probe (not the contract bench): device-resident timings of the four
+kernels on the BASELINE configs, CUDA events, printed as JSON lines."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import csparse_cuda as cc
+from csparse_cuda import synth
+
+PEAK = 6456.5
+
+
+def timeit(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def report(name, nbytes, med, best, **kw):
+    gbs = nbytes / (med * 1e-3) / 1e9
+    print(json.dumps({"what": name, "ms_median": round(med, 4), "ms_best": round(best, 4),
+                      "GBs": round(gbs, 1), "frac_of_measured_peak": round(gbs / PEAK, 3), **kw}), flush=True)
+
+
+def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
+    nnz = len(i)
+    t0 = time.time()
+    dA = cc.from_arrays(m, n, p, i, x)
+    print(json.dumps({"what": tag + " upload", "s": round(time.time() - t0, 2), "nnz": nnz}), flush=True)
+    holder = {}
+
+    def tr():
+        holder["c"] = cc.cs_transpose(dA, True)
+    med, best = timeit(tr, 2, 5)
+    report(tag + " cs_transpose", synth.transpose_bytes(m, n, nnz), med, best)
+    holder.clear()
+    xv = torch.randn(n, dtype=torch.float64, device="cuda")
+    yv = torch.randn(m, dtype=torch.float64, device="cuda")
+    for plan in plans:
+        dA.force_gaxpy_plan(plan)
+        dA.prepare_gaxpy()
+        med, best = timeit(lambda: dA.gaxpy_dev(xv.data_ptr(), yv.data_ptr()), 3, 20)
+        report(f"{tag} cs_gaxpy[{dA.gaxpy_plan()}]", synth.gaxpy_bytes(m, n, nnz), med, best,
+               gflops=round(2 * nnz / (med * 1e-3) / 1e9, 1))
+    if do_mul:
+        def mul():
+            holder["c"] = cc.cs_multiply(dA, dA)
+        med, best = timeit(mul, 1, 3)
+        C = holder["c"]
+        report(tag + " cs_multiply A*A", synth.multiply_bytes(nnz, nnz, C.nnz, n, n), med, best,
+               nnzC=C.nnz, nnzC_per_s=round(C.nnz / (med * 1e-3), 1), madds=cc.last_multiply_flops())
+    dA.free()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lap", type=int, default=4096)
+    ap.add_argument("--st", type=int, default=128)
+    ap.add_argument("--rmat", type=int, default=20)
+    a = ap.parse_args()
+    torch.cuda.init()
+    cc.set_stream(torch.cuda.current_stream().cuda_stream)
+    n = 1 << 24
+    c = torch.randint(0, 9, (n,), dtype=torch.int32, device="cuda")
+    pp = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    import ctypes as C
+    from csparse_cuda import _lib
+    tot = C.c_int64()
+    med, best = timeit(lambda: _lib.lib().csb200_cumsum_dev(C.c_void_p(pp.data_ptr()), C.c_void_p(c.data_ptr()), n, C.byref(tot)), 2, 10)
+    report("cs_cumsum n=2^24 (incl. D2H of total)", synth.cumsum_bytes(n), med, best)
+    if a.lap:
+        run_matrix(f"lap2d {a.lap}", *synth.lap2d(a.lap), do_mul=a.lap <= 2048, plans=("stream", "merge"))
+    if a.st:
+        run_matrix(f"st27 {a.st}", *synth.st27(a.st), do_mul=True, plans=("stream",))
+    if a.rmat:
+        run_matrix(f"rmat {a.rmat}", *synth.rmat(a.rmat, 16), do_mul=False, plans=("merge", "stream"))
