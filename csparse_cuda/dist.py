@@ -1,0 +1,281 @@
+"""Multi-GPU sharding of the two paths that shard, one process per GPU,
+``torch.distributed`` for the plumbing (NCCL over NVLink/NVSwitch on the B200 box,
+gloo in the CPU tests).
+
+cs_gaxpy     rows are independent: each rank owns a contiguous block of rows of the
+             CSR view (balanced by nnz) and the matching slices of x and y.  Per
+             step the rank fetches the x entries its block references --
+             * halo mode  (banded matrices): only from the two neighbouring ranks,
+               a few KB each way, as batched P2P isend/irecv;
+             * gather mode (general matrices): an all-gather of x --
+             then runs the local row-block SpMV.  y needs no reduction.
+cs_multiply  columns of C are independent: each rank owns a block of columns of B
+             (balanced by multiply-adds), A is replicated, every rank runs
+             symbolic + scan + numeric on its block; the only communication is the
+             final gather of the per-block results.
+cs_transpose / cs_cumsum do not shard ("replicas only").
+
+The partitioning and exchange logic is device-agnostic; the local kernels are
+injected (``local_spmv``) so that the world_size-2 gloo tests exercise exactly the
+code the NCCL path runs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+
+# ---- partitioning (pure numpy) --------------------------------------------------
+
+def balanced_bounds(weights_prefix: np.ndarray, parts: int) -> np.ndarray:
+    """Split items 0..n-1 into `parts` contiguous blocks of nearly equal weight.
+
+    ``weights_prefix`` is the inclusive-exclusive prefix array of length n+1
+    (e.g. a row-pointer array).  Returns ``bounds`` of length parts+1 with
+    bounds[0] = 0, bounds[parts] = n, non-decreasing.
+    """
+    n = len(weights_prefix) - 1
+    total = int(weights_prefix[n])
+    targets = (np.arange(1, parts, dtype=np.float64) * total / parts)
+    inner = np.searchsorted(weights_prefix, targets, side="left").astype(np.int64)
+    inner = np.clip(inner, 0, n)
+    b = np.concatenate(([0], inner, [n])).astype(np.int64)
+    return np.maximum.accumulate(b)
+
+
+def even_bounds(n: int, parts: int) -> np.ndarray:
+    return (np.arange(parts + 1, dtype=np.int64) * n) // parts
+
+
+@dataclass
+class RowBlock:
+    """Rows [r0, r1) of a CSR view, with the column window it references."""
+    r0: int
+    r1: int
+    rowptr: np.ndarray      # int32, r1-r0+1, rebased to 0
+    col: np.ndarray         # int32 GLOBAL column ids
+    val: np.ndarray         # float64
+    cmin: int
+    cmax: int               # inclusive; cmin > cmax when the block is empty
+
+
+def csr_row_block(rowptr: np.ndarray, col: np.ndarray, val: np.ndarray, r0: int, r1: int) -> RowBlock:
+    b, e = int(rowptr[r0]), int(rowptr[r1])
+    c = np.ascontiguousarray(col[b:e], dtype=np.int32)
+    rp = (rowptr[r0:r1 + 1].astype(np.int64) - b).astype(np.int32)
+    cmin, cmax = (int(c.min()), int(c.max())) if e > b else (0, -1)
+    return RowBlock(r0, r1, rp, c, np.ascontiguousarray(val[b:e], dtype=np.float64), cmin, cmax)
+
+
+@dataclass
+class ExchangePlan:
+    mode: str               # "halo" | "gather"
+    x_bounds: np.ndarray    # ownership of x: rank g owns [x_bounds[g], x_bounds[g+1])
+    win_lo: int             # local x window = global columns [win_lo, win_hi)
+    win_hi: int
+    lo_need: List[int]      # per rank: entries needed from the rank below
+    hi_need: List[int]      # per rank: entries needed from the rank above
+
+
+def plan_exchange(rank: int, world: int, x_bounds: np.ndarray, windows: Sequence[Sequence[int]],
+                  n_global: int) -> ExchangePlan:
+    """``windows[g] = (cmin, cmax)`` of every rank (all-gathered).  Halo mode needs every
+    rank's window to stay inside its own slice of x plus its two neighbours' slices."""
+    lo_need, hi_need, halo_ok = [], [], True
+    for g in range(world):
+        c0, c1 = int(x_bounds[g]), int(x_bounds[g + 1])
+        cmin, cmax = windows[g]
+        lo = max(0, c0 - cmin) if cmax >= cmin else 0
+        hi = max(0, cmax - (c1 - 1)) if cmax >= cmin else 0
+        lo_room = c0 - int(x_bounds[g - 1]) if g > 0 else 0
+        hi_room = int(x_bounds[g + 2]) - c1 if g + 1 < world else 0
+        if lo > lo_room or hi > hi_room:
+            halo_ok = False
+        lo_need.append(lo)
+        hi_need.append(hi)
+    if world == 1:
+        return ExchangePlan("halo", x_bounds, 0, n_global, [0], [0])
+    if not halo_ok:
+        return ExchangePlan("gather", x_bounds, 0, n_global, lo_need, hi_need)
+    c0, c1 = int(x_bounds[rank]), int(x_bounds[rank + 1])
+    return ExchangePlan("halo", x_bounds, c0 - lo_need[rank], c1 + hi_need[rank], lo_need, hi_need)
+
+
+class ShardedGaxpy:
+    """y_local += A[r0:r1, :] * x for this rank's row block; x and y are distributed.
+
+    Parameters
+    ----------
+    block : RowBlock            this rank's rows of the CSR view (global column ids)
+    m_global, n_global : int    shape of A
+    row_bounds : array(G+1)     row ownership (y follows it)
+    x_bounds : array(G+1)       ownership of x (defaults to row_bounds when A is square)
+    make_local : callable(rowptr, col_local, val, ncols_local) -> handle
+    local_spmv : callable(handle, x_window_tensor, y_local_tensor) -> None   (y += ...)
+    device : torch device of the vectors
+    """
+
+    def __init__(self, block: RowBlock, m_global: int, n_global: int, row_bounds, x_bounds=None,
+                 make_local: Callable = None, local_spmv: Callable = None, device="cpu", group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.block, self.device = block, device
+        self.m_global, self.n_global = m_global, n_global
+        self.row_bounds = np.asarray(row_bounds, dtype=np.int64)
+        if x_bounds is None:
+            x_bounds = self.row_bounds if m_global == n_global else even_bounds(n_global, self.world)
+        self.x_bounds = np.asarray(x_bounds, dtype=np.int64)
+        # every rank learns every rank's column window
+        mine = torch.tensor([block.cmin, block.cmax], dtype=torch.int64)
+        if self.world > 1:
+            allw = [torch.zeros(2, dtype=torch.int64) for _ in range(self.world)]
+            if dist.get_backend(group) == "nccl":
+                allw_d = [w.to(device) for w in allw]
+                dist.all_gather(allw_d, mine.to(device), group=group)
+                allw = [w.cpu() for w in allw_d]
+            else:
+                dist.all_gather(allw, mine, group=group)
+            windows = [(int(w[0]), int(w[1])) for w in allw]
+        else:
+            windows = [(block.cmin, block.cmax)]
+        self.plan = plan_exchange(self.rank, self.world, self.x_bounds, windows, n_global)
+        pl = self.plan
+        self.c0, self.c1 = int(self.x_bounds[self.rank]), int(self.x_bounds[self.rank + 1])
+        self.x_window = torch.zeros(pl.win_hi - pl.win_lo, dtype=torch.float64, device=device)
+        self.own = slice(self.c0 - pl.win_lo, self.c1 - pl.win_lo)       # my slice inside the window
+        col_local = (block.col.astype(np.int64) - pl.win_lo).astype(np.int32)
+        self.handle = make_local(block.rowptr, col_local, block.val, pl.win_hi - pl.win_lo)
+        self.local_spmv = local_spmv
+        self.exchanged_bytes = 0
+
+    # -- the per-step exchange of x --------------------------------------------------
+    def exchange(self, x_own):
+        """Fill the local x window from the distributed x (each rank passes its own slice)."""
+        torch, dist, pl = self.torch, self.dist, self.plan
+        xw = self.x_window
+        if self.world == 1:
+            xw[self.own] = x_own
+            return xw
+        if pl.mode == "gather":
+            sizes = [int(pl.x_bounds[g + 1] - pl.x_bounds[g]) for g in range(self.world)]
+            if len(set(sizes)) == 1:
+                dist.all_gather_into_tensor(xw, x_own.contiguous(), group=self.group)
+            else:
+                views = [xw[int(pl.x_bounds[g]):int(pl.x_bounds[g + 1])] for g in range(self.world)]
+                dist.all_gather(views, x_own.contiguous(), group=self.group)
+            self.exchanged_bytes = 8 * (self.n_global - sizes[self.rank])
+            return xw
+        xw[self.own] = x_own
+        r, ops, nbytes = self.rank, [], 0
+        own = xw[self.own]
+        if r > 0:
+            give = pl.hi_need[r - 1]           # the rank below needs the head of my slice
+            if give:
+                ops.append(dist.P2POp(dist.isend, own[:give].contiguous(), r - 1, group=self.group))
+            if pl.lo_need[r]:
+                ops.append(dist.P2POp(dist.irecv, xw[: pl.lo_need[r]], r - 1, group=self.group))
+                nbytes += 8 * pl.lo_need[r]
+        if r + 1 < self.world:
+            give = pl.lo_need[r + 1]           # the rank above needs the tail of my slice
+            if give:
+                ops.append(dist.P2POp(dist.isend, own[own.numel() - give:].contiguous(), r + 1, group=self.group))
+            if pl.hi_need[r]:
+                ops.append(dist.P2POp(dist.irecv, xw[xw.numel() - pl.hi_need[r]:], r + 1, group=self.group))
+                nbytes += 8 * pl.hi_need[r]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        self.exchanged_bytes = nbytes
+        return xw
+
+    def step(self, x_own, y_own):
+        """One distributed cs_gaxpy: exchange x, then y_own += A_block * x_window."""
+        xw = self.exchange(x_own)
+        self.local_spmv(self.handle, xw, y_own)
+        return y_own
+
+
+# ---- CUDA bindings for the local kernels -----------------------------------------------
+
+def cuda_make_local(rowptr, col_local, val, ncols_local):
+    """Upload a row block as the CSC of its transpose (= CSR view), ready for gaxpy_t_dev."""
+    import csparse_cuda as cc
+    h = cc.from_arrays(ncols_local, len(rowptr) - 1, rowptr, col_local, val, validate=True)
+    return h
+
+
+def cuda_local_spmv(handle, x_window, y_own):
+    handle.gaxpy_t_dev(x_window.data_ptr(), y_own.data_ptr())
+
+
+# ---- column-sharded cs_multiply ---------------------------------------------------------
+
+def multiply_column_bounds(Ap: np.ndarray, Bp: np.ndarray, Bi: np.ndarray, parts: int) -> np.ndarray:
+    """Column blocks of B with nearly equal multiply-add counts
+    (flops[j] = sum over k in B(:,j) of nnz(A(:,k)))."""
+    lens = np.diff(Ap).astype(np.int64)
+    per_entry = lens[Bi[: int(Bp[-1])]]
+    pref = np.zeros(len(per_entry) + 1, dtype=np.int64)
+    np.cumsum(per_entry, out=pref[1:])
+    col_prefix = pref[Bp.astype(np.int64)]          # flops before column j
+    return balanced_bounds(col_prefix, parts)
+
+
+def sharded_multiply(dA, dB, bounds, rank: int, gather: Optional[str] = "all", group=None, device="cuda"):
+    """C(:, J_rank) = A * B(:, J_rank) on this rank; then the final gather.
+
+    Returns (local DeviceMatrix, gathered) where gathered is None, or a tuple of torch
+    tensors (Cp, Ci, Cx) holding the whole product (on every rank for gather="all").
+    """
+    import torch
+    import torch.distributed as dist
+    import csparse_cuda as cc
+    j0, j1 = int(bounds[rank]), int(bounds[rank + 1])
+    dBl = dB.col_slice(j0, j1)
+    dCl = cc.cs_multiply(dA, dBl)
+    dBl.free()
+    if gather is None:
+        return dCl, None
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    p_ptr, i_ptr, x_ptr = dCl.device_pointers()
+    # wrap the result's device arrays as torch tensors without copying
+    cp = _as_tensor(p_ptr, dCl.n + 1, torch.int32, device)
+    ci = _as_tensor(i_ptr, max(dCl.nnz, 1), torch.int32, device)[: dCl.nnz]
+    cx = _as_tensor(x_ptr, max(dCl.nnz, 1), torch.float64, device)[: dCl.nnz] if dCl.has_values else None
+    if world == 1:
+        return dCl, (cp.clone(), ci.clone(), None if cx is None else cx.clone())
+    nnz_all = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(nnz_all, torch.tensor([dCl.nnz], dtype=torch.int64, device=device), group=group)
+    nnz_all = [int(t.item()) for t in nnz_all]
+    offs = np.concatenate(([0], np.cumsum(nnz_all)))
+    n_total = int(bounds[-1])
+    Cp = torch.empty(n_total + 1, dtype=torch.int32, device=device)
+    Ci = torch.empty(int(offs[-1]), dtype=torch.int32, device=device)
+    Cx = torch.empty(int(offs[-1]), dtype=torch.float64, device=device) if cx is not None else None
+    p_views = [Cp[int(bounds[g]):int(bounds[g + 1])] for g in range(world)]
+    dist.all_gather(p_views, (cp[:-1] + int(offs[rank])).contiguous(), group=group)
+    Cp[n_total] = int(offs[-1])
+    dist.all_gather([Ci[int(offs[g]):int(offs[g + 1])] for g in range(world)], ci.contiguous(), group=group)
+    if Cx is not None:
+        dist.all_gather([Cx[int(offs[g]):int(offs[g + 1])] for g in range(world)], cx.contiguous(), group=group)
+    return dCl, (Cp, Ci, Cx)
+
+
+def _as_tensor(ptr: int, count: int, dtype, device):
+    """Zero-copy torch view of a device buffer owned by libcsparse_b200 (the handle must outlive it)."""
+    import torch
+
+    class _Mem:
+        pass
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    typestr = {torch.int32: "<i4", torch.float64: "<f8", torch.int64: "<i8"}[dtype]
+    holder = _Mem()
+    holder.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
+                                       "version": 2, "strides": None}
+    del itemsize
+    return torch.as_tensor(holder, device=device)

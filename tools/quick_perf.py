@@ -17,7 +17,12 @@ from csparse_cuda import synth
 PEAK = 6456.5
 
 
+ONCE = False
+
+
 def timeit(fn, warm=3, iters=10):
+    if ONCE:
+        warm, iters = 1, 1
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -73,7 +78,9 @@ if __name__ == "__main__":
     ap.add_argument("--lap", type=int, default=4096)
     ap.add_argument("--st", type=int, default=128)
     ap.add_argument("--rmat", type=int, default=20)
+    ap.add_argument("--once", action="store_true", help="one warm-up + one timed call per op (for ncu launch lists)")
     a = ap.parse_args()
+    ONCE = a.once
     torch.cuda.init()
     cc.set_stream(torch.cuda.current_stream().cuda_stream)
     n = 1 << 24
