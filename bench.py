@@ -1,0 +1,531 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract for the csparse_cuda hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--impl reference]
+
+One "step" is one pass of the hot path over one resident input.  The default
+workload is BASELINE.json's headline: cs_gaxpy (y += A*x) on the 2-D 5-point
+Laplacian 4096^2 (n = 16 777 216, nnz = 83 869 696), metric "cs_gaxpy HBM GB/s" =
+algorithmic bytes (12 nnz + 4(n+1) + 8n + 16m) / time.  Other
+workloads: multiply_st27 (cs_multiply A*A, 27-point stencil 128^3, nnz(C)/s),
+transpose_lap2d, gaxpy_rmat (R-MAT 2^scale rows, merge-path kernel).
+
+N > 1 (launched by torchrun, one rank per GPU, NCCL): weak scaling -- every rank
+owns a 4096 x 4096 slab (16.7 M rows) of a 4096 x 4096N grid; per step each rank
+exchanges its x halo with its neighbours and runs the local row-block SpMV.
+
+`--impl reference` times the reference algorithm on the host CPU (the C oracle
+port of csparse.py's loops, single thread -- the reference has no parallelism).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="gaxpy_lap2d",
+                    choices=["gaxpy_lap2d", "multiply_st27", "transpose_lap2d", "gaxpy_rmat"])
+    ap.add_argument("--k", type=int, default=0, help="grid edge (lap2d: 4096, st27: 128) or R-MAT scale (24)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads in the N=1 default run")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host CPU
+# ------------------------------------------------------------------------------------
+
+def cpu_workload(workload: str, k: int):
+    """(callable running ONE pass on the CPU, units per pass, description, unit-of-metric)"""
+    from csparse_cuda import synth
+    from oracle import oracle as orc
+    if workload == "gaxpy_lap2d":
+        m, n, p, i, x = synth.lap2d(k)
+        A = orc.csc(m, n, p, i, x)
+        xv, y = synth.vectors(m, n)
+        return (lambda: orc.cs_gaxpy(A, xv, y)), synth.gaxpy_bytes(m, n, len(i)) / 1e9, \
+            f"full cs_gaxpy pass, lap2d {k}^2 (nnz {len(i)})", "GB/s"
+    if workload == "gaxpy_rmat":
+        m, n, p, i, x = synth.rmat(k, 16)
+        A = orc.csc(m, n, p, i, x)
+        xv, y = synth.vectors(m, n)
+        return (lambda: orc.cs_gaxpy(A, xv, y)), synth.gaxpy_bytes(m, n, len(i)) / 1e9, \
+            f"full cs_gaxpy pass, R-MAT scale {k} (nnz {len(i)})", "GB/s"
+    if workload == "transpose_lap2d":
+        m, n, p, i, x = synth.lap2d(k)
+        A = orc.csc(m, n, p, i, x)
+        return (lambda: orc.cs_transpose(A, True)), synth.transpose_bytes(m, n, len(i)) / 1e9, \
+            f"full cs_transpose pass, lap2d {k}^2", "GB/s"
+    if workload == "multiply_st27":
+        m, n, p, i, x = synth.st27(k)
+        A = orc.csc(m, n, p, i, x)
+        nnzc = (5 * k - 4) ** 3
+        return (lambda: orc.cs_multiply(A, A)), float(nnzc), \
+            f"full cs_multiply A*A pass, st27 {k}^3 (nnz(C) {nnzc})", "nnz(C)/s"
+    raise ValueError(workload)
+
+
+def time_cpu(fn, units, min_seconds=6.0, min_passes=2, max_passes=200):
+    fn()                                   # warm the caches / page in
+    t0, passes = time.perf_counter(), 0
+    while passes < min_passes or (time.perf_counter() - t0 < min_seconds and passes < max_passes):
+        fn()
+        passes += 1
+    dt = time.perf_counter() - t0
+    return units * passes / dt, passes, dt
+
+
+def default_k(workload: str) -> int:
+    return {"gaxpy_lap2d": 4096, "transpose_lap2d": 4096, "multiply_st27": 128, "gaxpy_rmat": 24}[workload]
+
+
+def cpu_sample_k(workload: str, k: int) -> int:
+    """bounded CPU sample of the same family (seconds, not minutes)"""
+    if workload == "multiply_st27":
+        return min(k, 64)          # 128^3 takes ~10 s/pass and 6 GB in C; 64^3 is the same per-column work
+    if workload == "gaxpy_rmat":
+        return min(k, 20)
+    return k
+
+
+def run_reference(a):
+    """--impl reference: the reference algorithm (oracle C port of csparse.py) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    k = a.k or default_k(a.workload)
+    ks = cpu_sample_k(a.workload, k)
+    fn, units, desc, unit = cpu_workload(a.workload, ks)
+    for _ in range(max(a.warmup, 1) if ks < 2048 else 1):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    value = units * a.steps / dt
+    metric = "cs_gaxpy HBM GB/s" if a.workload.startswith("gaxpy") else \
+        ("cs_multiply nnz(C)/s" if a.workload == "multiply_st27" else "cs_transpose HBM GB/s")
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+        "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": a.workload, "k": k, "cpu_sample_k": ks, "sample": desc},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": "port",
+                         "sample": desc + "; oracle/csparse_oracle.c (C restatement of csparse.py loops), 1 thread; "
+                                          "the Python reference itself is single-threaded and cannot travel to the GPU box"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------
+
+def device_timed(torch, dist, world, fn, steps, warmup):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events,
+    max over ranks.  Returns total milliseconds."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; csparse_cuda has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import csparse_cuda as cc
+    from csparse_cuda import synth, dist as csd
+    cc.set_device(local)
+    cc.set_stream(torch.cuda.current_stream().cuda_stream)
+    peak, peak_src = peaks()
+    k = a.k or default_k(a.workload)
+    out = {}
+    sampler = ClockSampler(local)
+
+    if a.workload == "gaxpy_lap2d":
+        out = bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler)
+    elif a.workload == "gaxpy_rmat":
+        out = bench_gaxpy_single(a, torch, cc, synth, "rmat", k, peak, peak_src, sampler)
+    elif a.workload == "transpose_lap2d":
+        out = bench_transpose(a, torch, cc, synth, k, peak, peak_src, sampler)
+    elif a.workload == "multiply_st27":
+        out = bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler)
+
+    if rank == 0:
+        if world == 1 and a.workload == "gaxpy_lap2d" and not a.no_extra:
+            out["extra"] = extras(a, torch, cc, synth, peak)
+        if world == 1 and not a.no_cpu:
+            from oracle import oracle as orc
+            orc.build()
+            ks = cpu_sample_k(a.workload, k)
+            fn, units, desc, unit = cpu_workload(a.workload, ks)
+            v, passes, dt = time_cpu(fn, units)
+            out["cpu_baseline"] = {"value": v, "unit": unit, "cores": 1, "kind": "port",
+                                   "sample": f"{passes} x {desc} in {dt:.1f} s; oracle/csparse_oracle.c, 1 thread "
+                                             f"(host has {os.cpu_count()} logical CPUs; the reference is single-threaded)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def pinned(torch, arr):
+    t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    return t
+
+
+def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler):
+    """Row-block sharded cs_gaxpy on the 5-point Laplacian.  N = 1: the k x k grid.
+    N > 1 weak: a k x (k N) grid, one k x k slab per rank; strong: the k x k grid split by rows."""
+    ky_total = k * world if a.scaling == "weak" else k
+    n_global = k * ky_total
+    bounds = csd.even_bounds(ky_total, world) * k          # split between grid lines
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    # the Laplacian is symmetric: rows r0..r1 of the CSR view == columns r0..r1 of the CSC
+    m_, n_, p, i, x = synth.lap2d_cols(k, ky_total, r0, r1)
+    nnz_local = len(i)
+    nnz_global = 5 * n_global - 2 * k - 2 * ky_total
+    alg_bytes_local = synth.gaxpy_bytes(r1 - r0, r1 - r0, nnz_local)
+    alg_bytes_global = synth.gaxpy_bytes(n_global, n_global, nnz_global)
+
+    x_own = torch.from_numpy(np.random.default_rng(rank).standard_normal(r1 - r0)).cuda()
+    y_own = torch.from_numpy(np.random.default_rng(100 + rank).standard_normal(r1 - r0)).cuda()
+    if world == 1:
+        dA = cc.from_arrays(n_global, n_global, p, i, x)     # CSC; its CSR view is built once and cached
+        dA.prepare_gaxpy()
+        plan = dA.gaxpy_plan()
+        xp, yp = x_own.data_ptr(), y_own.data_ptr()
+        step = lambda: dA.gaxpy_dev(xp, yp)
+        launches_per_step, exch = 1 if plan == "stream" else 2, 0
+        mode = "single"
+    else:
+        blk = csd.RowBlock(r0, r1, p, i, x, int(i.min()), int(i.max()))
+        sh = csd.ShardedGaxpy(blk, n_global, n_global, bounds, make_local=csd.cuda_make_local,
+                              local_spmv=csd.cuda_local_spmv, device="cuda")
+        sh.handle.gaxpy_plan()
+        plan = sh.handle.gaxpy_plan()
+        step = lambda: sh.step(x_own, y_own)
+        step()
+        launches_per_step, exch, mode = 1 if plan == "stream" else 2, sh.exchanged_bytes, sh.plan.mode
+
+    l0 = cc.launch_count()
+    sampler.start()
+    ms = device_timed(torch, dist, world, step, a.steps, a.warmup)
+    clocks = sampler.stop()
+    launches = cc.launch_count() - l0 - launches_per_step * a.warmup
+    value = alg_bytes_global * a.steps / (ms * 1e-3) / 1e9
+
+    # kernel-only roofline of the dominant kernel: the local SpMV launch, timed alone
+    if world == 1:
+        kern = step
+    else:
+        xw = sh.x_window
+        kern = lambda: csd.cuda_local_spmv(sh.handle, xw, y_own)
+    kms = device_timed(torch, dist, 1, kern, a.steps, 2) / a.steps
+    achieved = alg_bytes_local / (kms * 1e-3) / 1e9
+
+    # e2e: the reference-facing call on HOST buffers (pinned), copies inside the timed region.
+    # "cold": csb200_gaxpy_host -- matrix + vectors uploaded every step (what cs_gaxpy(A, x, y)
+    # on a host cs does); "resident": the matrix handle stays in HBM, x/y travel every step.
+    e2e, e2e_res = None, None
+    if world == 1:
+        hp, hi, hx = pinned(torch, p), pinned(torch, i), pinned(torch, x)
+        hxv = pinned(torch, np.random.default_rng(0).standard_normal(n_global))
+        hyv = pinned(torch, np.random.default_rng(1).standard_normal(n_global))
+        cold = lambda: cc.gaxpy_host(n_global, n_global, hp.data_ptr(), hi.data_ptr(), hx.data_ptr(),
+                                     hxv.data_ptr(), hyv.data_ptr())
+        ksteps = max(3, min(a.steps, 10))
+        cold(); cold()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            cold()
+        dt = (time.perf_counter() - t0) / ksteps
+        h2d = hp.numel() * 4 + hi.numel() * 4 + hx.numel() * 8 + 8 * n_global * 2
+        e2e = {"value": alg_bytes_global / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 8 * n_global, "ms_per_step": dt * 1e3, "steps": ksteps,
+               "call": "csb200_gaxpy_host(m,n,Ap,Ai,Ax,x,y): pinned host buffers; uploads the matrix, builds the CSR view, SpMV, downloads y"}
+        import ctypes as C
+        from csparse_cuda import _lib
+        res = lambda: _lib.check(_lib.lib().csb200_gaxpy(dA._h, C.c_void_p(hxv.data_ptr()), C.c_void_p(hyv.data_ptr())))
+        res(); res()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            res()
+        dt = (time.perf_counter() - t0) / a.steps
+        e2e_res = {"value": alg_bytes_global / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 16 * n_global,
+                   "d2h_bytes_per_step": 8 * n_global, "ms_per_step": dt * 1e3,
+                   "call": "csb200_gaxpy(handle, x, y): matrix resident in HBM, pinned host x/y copied every step"}
+    else:
+        # N > 1: per step each rank copies its x slice H2D and its y slice D2H around the sharded step
+        hx_own, hy_own = x_own.cpu().pin_memory(), y_own.cpu().pin_memory()
+
+        def e2e_step():
+            x_own.copy_(hx_own, non_blocking=True)
+            sh.step(x_own, y_own)
+            hy_own.copy_(y_own, non_blocking=True)
+        ems = device_timed(torch, dist, world, e2e_step, a.steps, 2)
+        e2e = {"value": alg_bytes_global * a.steps / (ems * 1e-3) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": 8 * (r1 - r0), "d2h_bytes_per_step": 8 * (r1 - r0), "ms_per_step": ems / a.steps,
+               "call": "per rank: x slice H2D, halo exchange + local csb200_gaxpy_t_dev, y slice D2H (matrix block resident)"}
+
+    res = {
+        "metric": "cs_gaxpy HBM GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cs_gaxpy y+=A*x, 2-D 5-point Laplacian {k}x{ky_total} (n={n_global}, nnz={nnz_global}), "
+                               f"{r1 - r0} rows/GPU, row-block sharded", "kernel": f"k_spmv_{plan}",
+                   "exchange": mode, "exchange_bytes_per_rank_step": exch,
+                   "l2": "inputs (1.0 GB matrix per GPU) exceed the 126 MB L2; no flush needed",
+                   "gflops": 2 * nnz_global * a.steps / (ms * 1e-3) / 1e9},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": f"k_spmv_{plan}", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes_local, "kernel_ms": kms},
+        "e2e": e2e,
+    }
+    if e2e_res:
+        res["e2e_resident"] = e2e_res
+    return res
+
+
+def bench_gaxpy_single(a, torch, cc, synth, family, k, peak, peak_src, sampler):
+    m, n, p, i, x = synth.rmat(k, 16) if family == "rmat" else synth.lap2d(k)
+    nnz = len(i)
+    dA = cc.from_arrays(m, n, p, i, x)
+    dA.prepare_gaxpy()
+    plan = dA.gaxpy_plan()
+    xv = torch.randn(n, dtype=torch.float64, device="cuda")
+    yv = torch.randn(m, dtype=torch.float64, device="cuda")
+    step = lambda: dA.gaxpy_dev(xv.data_ptr(), yv.data_ptr())
+    l0 = cc.launch_count()
+    sampler.start()
+    ms = device_timed(torch, None, 1, step, a.steps, a.warmup)
+    clocks = sampler.stop()
+    per = 1 if plan == "stream" else 2
+    launches = cc.launch_count() - l0 - per * a.warmup
+    b = synth.gaxpy_bytes(m, n, nnz)
+    value = b * a.steps / (ms * 1e-3) / 1e9
+    return {"metric": "cs_gaxpy HBM GB/s", "value": value, "unit": "GB/s", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cs_gaxpy, R-MAT scale {k} ef 16 (n={n}, nnz={nnz})", "kernel": f"k_spmv_{plan}",
+                       "l2": "inputs exceed L2" if b > 2.5e8 else "inputs fit L2 (no flush): launch-bound parity config"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
+                         "traffic": None, "kernel": f"k_spmv_{plan}", "peak_source": peak_src},
+            "e2e": None}
+
+
+def bench_transpose(a, torch, cc, synth, k, peak, peak_src, sampler):
+    m, n, p, i, x = synth.lap2d(k)
+    nnz = len(i)
+    dA = cc.from_arrays(m, n, p, i, x)
+    hold = {}
+
+    def step():
+        hold["c"] = cc.cs_transpose(dA, True)
+    l0 = cc.launch_count()
+    sampler.start()
+    ms = device_timed(torch, None, 1, step, a.steps, a.warmup)
+    clocks = sampler.stop()
+    total_l = cc.launch_count() - l0
+    launches = total_l * a.steps // (a.steps + a.warmup)
+    b = synth.transpose_bytes(m, n, nnz)
+    value = b * a.steps / (ms * 1e-3) / 1e9
+    return {"metric": "cs_transpose HBM GB/s", "value": value, "unit": "GB/s", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cs_transpose(values=True), lap2d {k}^2 (nnz={nnz})", "l2": "inputs exceed L2"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
+                         "traffic": None, "kernel": "whole cs_transpose (hist+scan+scatter+fix)", "peak_source": peak_src},
+            "e2e": None}
+
+
+def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler):
+    """cs_multiply A*A on the 27-point stencil; N > 1: column blocks of B, A replicated, final gather."""
+    m, n, p, i, x = synth.st27(k)
+    nnz = len(i)
+    dA = cc.from_arrays(m, n, p, i, x)
+    bounds = csd.multiply_column_bounds(p, p, i, world)
+    hold = {}
+    if world == 1:
+        def step():
+            hold["c"] = cc.cs_multiply(dA, dA)
+    else:
+        def step():
+            hold["c"] = csd.sharded_multiply(dA, dA, bounds, rank, gather="all", device="cuda")
+    steps, warm = min(a.steps, 10), min(a.warmup, 3) or 1
+    l0 = cc.launch_count()
+    sampler.start()
+    ms = device_timed(torch, dist, world, step, steps, warm)
+    clocks = sampler.stop()
+    launches = (cc.launch_count() - l0) * steps // (steps + warm)
+    nnzc = (5 * k - 4) ** 3
+    got = hold["c"].nnz if world == 1 else int(hold["c"][1][1].numel())
+    assert got == nnzc, (got, nnzc)
+    value = nnzc * steps / (ms * 1e-3)
+    b = synth.multiply_bytes(nnz, nnz, nnzc, n, n)
+    gbs = b * steps / (ms * 1e-3) / 1e9
+    return {"metric": "cs_multiply nnz(C)/s", "value": value, "unit": "nnz(C)/s", "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cs_multiply A*A, 27-point stencil {k}^3 (n={n}, nnz={nnz}, nnz(C)={nnzc}), "
+                                   f"column blocks of B, A replicated", "l2": "inputs + output exceed L2",
+                       "gflops": 2 * cc.last_multiply_flops() * world * steps / (ms * 1e-3) / 1e9 if world == 1 else None},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "traffic": None, "kernel": "whole cs_multiply (ub+bin+symbolic+scan+numeric)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b},
+            "e2e": None}
+
+
+def extras(a, torch, cc, synth, peak):
+    """Secondary device-resident numbers reported beside the headline at N = 1."""
+    ex = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, warm, iters):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    try:
+        m, n, p, i, x = synth.lap2d(4096)
+        dA = cc.from_arrays(m, n, p, i, x)
+        hold = {}
+        ms = timed(lambda: hold.__setitem__("c", cc.cs_transpose(dA, True)), 2, 5)
+        b = synth.transpose_bytes(m, n, len(i))
+        ex["cs_transpose lap2d 4096^2"] = {"ms": ms, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak}
+        hold.clear(); dA.free()
+        m, n, p, i, x = synth.st27(128)
+        dA = cc.from_arrays(m, n, p, i, x)
+        ms = timed(lambda: hold.__setitem__("c", cc.cs_multiply(dA, dA)), 1, 3)
+        nnzc = hold["c"].nnz
+        b = synth.multiply_bytes(len(i), len(i), nnzc, n, n)
+        ex["cs_multiply st27 128^3 A*A"] = {"ms": ms, "nnz(C)/s": nnzc / ms * 1e3, "GB/s": b / ms / 1e6,
+                                            "frac_of_peak": b / ms / 1e6 / peak, "nnzC": nnzc,
+                                            "GFLOP/s": 2 * cc.last_multiply_flops() / ms / 1e6}
+        hold.clear()
+        ms = timed(lambda: hold.__setitem__("c", cc.cs_transpose(dA, True)), 2, 5)
+        b = synth.transpose_bytes(m, n, len(i))
+        ex["cs_transpose st27 128^3"] = {"ms": ms, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak}
+        hold.clear(); dA.free()
+    except Exception as e:  # secondary numbers never sink the headline
+        ex["error"] = repr(e)
+    return ex
+
+
+if __name__ == "__main__":
+    main()

@@ -58,11 +58,24 @@ __global__ void k_bin(int n, const int *__restrict__ size, int cap, int t0, int 
                       int *__restrict__ lists, int *__restrict__ counts)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const int s = min(size[j], cap);
-    if (s <= 0) return;
-    const int b = s <= t0 ? 0 : s <= t1 ? 1 : s <= t2 ? 2 : 3;
-    lists[(size_t)b * n + atomicAdd(&counts[b], 1)] = j;
+    int b = -1;
+    if (j < n) {
+        const int s = min(size[j], cap);
+        if (s > 0) b = s <= t0 ? 0 : s <= t1 ? 1 : s <= t2 ? 2 : 3;
+    }
+    // one atomic per warp and class instead of one per column
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned mask = __ballot_sync(0xffffffffu, b == c);
+        if (mask) {
+            int base = 0;
+            const int leader = __ffs(mask) - 1;
+            if ((threadIdx.x & 31) == leader) base = atomicAdd(&counts[c], __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (b == c) lists[(size_t)c * n + base + __popc(mask & lt)] = j;
+        }
+    }
 }
 
 // ---- symbolic, one warp per column, hash set in shared memory ---------------------

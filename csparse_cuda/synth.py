@@ -13,21 +13,29 @@ from __future__ import annotations
 import numpy as np
 
 
-def lap2d(k: int):
-    """A = I (x) L1 + L1 (x) I with L1 = tridiag(-1, 2, -1); index = ix + k*iy."""
-    n = k * k
-    j = np.arange(n, dtype=np.int64)
-    ix = j % k
-    iy = j // k
-    rows = np.stack([j - k, j - 1, j, j + 1, j + k], axis=1)
-    valid = np.stack([iy > 0, ix > 0, np.ones(n, bool), ix < k - 1, iy < k - 1], axis=1)
-    vals = np.broadcast_to(np.array([-1.0, -1.0, 4.0, -1.0, -1.0]), (n, 5))
-    p = np.zeros(n + 1, dtype=np.int64)
+def lap2d_cols(kx: int, ky: int, j0: int, j1: int):
+    """Columns [j0, j1) of the 5-point Laplacian on a kx x ky grid (index = ix + kx*iy),
+    with GLOBAL row indices.  The matrix is symmetric, so these are also rows [j0, j1)
+    of its CSR view.  Returns (m, j1-j0, p, i, x)."""
+    n = kx * ky
+    j = np.arange(j0, j1, dtype=np.int64)
+    ix = j % kx
+    iy = j // kx
+    rows = np.stack([j - kx, j - 1, j, j + 1, j + kx], axis=1)
+    valid = np.stack([iy > 0, ix > 0, np.ones(len(j), bool), ix < kx - 1, iy < ky - 1], axis=1)
+    vals = np.broadcast_to(np.array([-1.0, -1.0, 4.0, -1.0, -1.0]), (len(j), 5))
+    p = np.zeros(len(j) + 1, dtype=np.int64)
     np.cumsum(valid.sum(axis=1), out=p[1:])
     i = rows[valid].astype(np.int32)
     x = np.ascontiguousarray(vals[valid], dtype=np.float64)
+    return n, len(j), p.astype(np.int32), i, x
+
+
+def lap2d(k: int):
+    """A = I (x) L1 + L1 (x) I with L1 = tridiag(-1, 2, -1); index = ix + k*iy."""
+    m, n, p, i, x = lap2d_cols(k, k, 0, k * k)
     assert p[-1] == 5 * n - 4 * k
-    return n, n, p.astype(np.int32), i, x
+    return m, n, p, i, x
 
 
 def st27(k: int, seed: int = 0):
