@@ -172,10 +172,10 @@ class DeviceMatrix(object):
     def gaxpy_plan(self) -> str:
         k = C.c_int()
         _lib.check(_lib.lib().csb200_gaxpy_plan(self._h, C.byref(k)), "gaxpy_plan")
-        return {1: "stream", 2: "merge"}.get(k.value, "none")
+        return {1: "stream", 2: "merge", 3: "stream_ld"}.get(k.value, "none")
 
     def force_gaxpy_plan(self, kind: Optional[str]):
-        code = {None: 0, "auto": 0, "stream": 1, "merge": 2}[kind]
+        code = {None: 0, "auto": 0, "stream": 1, "merge": 2, "stream_ld": 3}[kind]
         _lib.check(_lib.lib().csb200_gaxpy_force_plan(self._h, code))
 
 

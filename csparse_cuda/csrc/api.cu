@@ -88,8 +88,8 @@ static int mat_alloc(csi m, csi n, long long nnz, bool has_x, csb200_mat **out)
     if (!A) return set_error(CSB200_ERR_NOMEM, "out of host memory");
     A->m = m; A->n = n; A->nnz = nnz;
     cudaGetDevice(&A->device);
-    const size_t cap = (size_t)(nnz > 0 ? nnz : 1);
-    int st = dev_alloc(&A->p, (size_t)n + 1);
+    const size_t cap = (size_t)(nnz > 0 ? nnz : 1) + MAT_PAD;
+    int st = dev_alloc(&A->p, (size_t)n + 1 + MAT_PAD);
     if (st == CSB200_OK) st = dev_alloc(&A->i, cap);
     if (st == CSB200_OK && has_x) st = dev_alloc(&A->x, cap);
     if (st != CSB200_OK) { csb200_mat_free(A); return st; }
@@ -376,7 +376,7 @@ int csb200_gaxpy_plan(csb200_mat *A, int *kind)
 
 int csb200_gaxpy_force_plan(csb200_mat *A, int kind)
 {
-    if (!A || kind < 0 || kind > 2) return set_error(CSB200_ERR_ARG, "bad plan kind");
+    if (!A || kind < 0 || kind > 3) return set_error(CSB200_ERR_ARG, "bad plan kind");
     A->forced_plan = kind;
     if (A->csr) A->csr->forced_plan = kind;
     return CSB200_OK;

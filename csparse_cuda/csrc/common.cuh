@@ -79,6 +79,10 @@ struct DevBuf {
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Every p / i / x array of a handle is over-allocated by MAT_PAD elements so that
+// 16-byte-granular bulk (TMA) copies may read a few elements past the logical end.
+constexpr size_t MAT_PAD = 8;
+
 // ---- kernels exported between translation units ----------------------------
 // scan.cu : p[0..n] = exclusive scan(c), c[i] <- p[i]; d_total (int64) and
 //           d_max (max element, may be null) are device scalars.

@@ -425,7 +425,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
     csb200_mat *C = new csb200_mat();
     C->m = m; C->n = n; C->device = A->device;
     auto fail = [&](int st) { csb200_mat_free(C); return st; };
-    int st = dev_alloc(&C->p, (size_t)n + 1);
+    int st = dev_alloc(&C->p, (size_t)n + 1 + MAT_PAD);
     if (st != CSB200_OK) return fail(st);
 
     int canon = 1;
@@ -486,7 +486,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
         return fail(CSB200_ERR_OVERFLOW);
     }
     C->nnz = h_total;
-    const size_t cap = (size_t)(h_total > 0 ? h_total : 1);
+    const size_t cap = (size_t)(h_total > 0 ? h_total : 1) + MAT_PAD;
     MM_TRY(dev_alloc(&C->i, cap));
     if (values) MM_TRY(dev_alloc(&C->x, cap));
     if (h_total > 0) {

@@ -19,7 +19,7 @@
 #include "common.cuh"
 
 struct SpmvPlan {
-    int kind = 0;            // 1 stream, 2 merge
+    int kind = 0;            // 1 stream (TMA-staged), 2 merge, 3 stream (plain loads)
     int rows_per_cta = 0;    // stream
     int merge_ctas = 0;      // merge
     int *merge_part = nullptr;      // a-coordinate (row) at the start diagonal of each CTA, merge_ctas+1
@@ -101,6 +101,157 @@ k_spmv_stream(int m, const csi *__restrict__ rowptr, const csi *__restrict__ col
             for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, o));
             if (lane == 0 && e > b) y[r0 + row] = __dadd_rn(y[r0 + row], s);
         }
+    }
+}
+
+// ---- TMA-staged persistent row-stream kernel ------------------------------------------
+// One CTA per SM slot, looping over row blocks.  A producer warp stages each block's
+// rowptr / col / val slices into a ring of shared-memory stages with 1-D bulk copies
+// (cp.async.bulk, completion on an mbarrier); 16 consumer warps turn a landed stage
+// into products (x gathered through L1/L2), then one thread per row adds its products
+// in storage order.  The copy engine keeps several stages in flight per SM, so HBM
+// never waits for the dependent x gather or the per-row reduction.
+constexpr int TS_CONSUMERS = 512;               // consumer threads == max rows per block
+constexpr int TS_THREADS = TS_CONSUMERS + 32;   // + producer warp
+constexpr int TS_TILE = 2816;                   // nonzeros staged per block
+constexpr int TS_STAGES = 3;
+constexpr int TS_RP = TS_CONSUMERS + 4;         // staged row pointers (multiple of 4)
+constexpr int TS_STAGE_BYTES = TS_TILE * 12 + TS_RP * 4;
+constexpr int TS_SMEM = TS_STAGES * TS_STAGE_BYTES + 64;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 2)
+k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi *__restrict__ col,
+           const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TS_STAGES * TS_STAGE_BYTES);
+    const int tid = threadIdx.x;
+    const int niter = (nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < TS_STAGES; s++) {
+            mbar_init(smem_u32(&bars[s]), 1);                           // full: producer's expect_tx arrival
+            mbar_init(smem_u32(&bars[TS_STAGES + s]), TS_CONSUMERS / 32); // empty: one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= TS_CONSUMERS) {
+        // ---------------- producer warp: lane 0 issues the bulk copies ----------------
+        if (tid == TS_CONSUMERS) {
+            for (int it = 0; it < niter; it++) {
+                const int stage = it % TS_STAGES;
+                if (it >= TS_STAGES) mbar_wait(smem_u32(&bars[TS_STAGES + stage]), ((it / TS_STAGES) - 1) & 1);
+                const int blk = blockIdx.x + it * gridDim.x;
+                const int r0 = blk * R;
+                const int nrows = min(R, m - r0);
+                const int start = rowptr[r0], end = rowptr[r0 + nrows];
+                const int a0 = start & ~3;
+                const int len = ((end + 3) & ~3) - a0;
+                const unsigned rp_bytes = (unsigned)(((nrows + 1 + 3) & ~3) * 4);
+                const bool staged = len <= TS_TILE;
+                unsigned char *st = smem + stage * TS_STAGE_BYTES;
+                const unsigned full = smem_u32(&bars[stage]);
+                mbar_expect_tx(full, rp_bytes + (staged ? (unsigned)len * 12u : 0u));
+                bulk_g2s(smem_u32(st + TS_TILE * 12), rowptr + r0, rp_bytes, full);
+                if (staged && len > 0) {
+                    bulk_g2s(smem_u32(st), val + a0, (unsigned)len * 8u, full);
+                    bulk_g2s(smem_u32(st + TS_TILE * 8), col + a0, (unsigned)len * 4u, full);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int lane = tid & 31;
+    for (int it = 0; it < niter; it++) {
+        const int stage = it % TS_STAGES;
+        const int blk = blockIdx.x + it * gridDim.x;
+        const int r0 = blk * R;
+        const int nrows = min(R, m - r0);
+        double yv = 0.0;
+        if (tid < nrows) yv = y[r0 + tid];                   // issued early; used after the products
+        unsigned char *st = smem + stage * TS_STAGE_BYTES;
+        double *sval = reinterpret_cast<double *>(st);
+        const int *scol = reinterpret_cast<const int *>(st + TS_TILE * 8);
+        const int *srp = reinterpret_cast<const int *>(st + TS_TILE * 12);
+        mbar_wait(smem_u32(&bars[stage]), (it / TS_STAGES) & 1);
+        const int start = srp[0], end = srp[nrows];
+        const int a0 = start & ~3;
+        const int len = ((end + 3) & ~3) - a0;
+        if (len <= TS_TILE) {
+            for (int k = tid * 4; k < len; k += TS_CONSUMERS * 4) {
+                const int4 c = *reinterpret_cast<const int4 *>(scol + k);
+                const double2 v0 = *reinterpret_cast<const double2 *>(sval + k);
+                const double2 v1 = *reinterpret_cast<const double2 *>(sval + k + 2);
+                const int g = a0 + k;                         // global index of the first of four entries
+                if (g >= start && g + 3 < end) {
+                    const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+                    double2 o0, o1;
+                    o0.x = __dmul_rn(v0.x, x0); o0.y = __dmul_rn(v0.y, x1);
+                    o1.x = __dmul_rn(v1.x, x2); o1.y = __dmul_rn(v1.y, x3);
+                    *reinterpret_cast<double2 *>(sval + k) = o0;
+                    *reinterpret_cast<double2 *>(sval + k + 2) = o1;
+                } else {                                      // ragged ends: entries of neighbouring blocks / padding
+                    if (g >= start && g < end) sval[k] = __dmul_rn(v0.x, __ldg(x + c.x));
+                    if (g + 1 >= start && g + 1 < end) sval[k + 1] = __dmul_rn(v0.y, __ldg(x + c.y));
+                    if (g + 2 >= start && g + 2 < end) sval[k + 2] = __dmul_rn(v1.x, __ldg(x + c.z));
+                    if (g + 3 >= start && g + 3 < end) sval[k + 3] = __dmul_rn(v1.y, __ldg(x + c.w));
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TS_CONSUMERS) : "memory");
+            if (tid < nrows) {
+                const int b = srp[tid] - a0, e = srp[tid + 1] - a0;
+                if (e > b) {
+                    double s = yv;
+                    for (int k = b; k < e; k++) s = __dadd_rn(s, sval[k]);
+                    y[r0 + tid] = s;
+                }
+            }
+        } else {
+            // block too large for a stage: one warp per row straight from global memory
+            for (int row = tid >> 5; row < nrows; row += TS_CONSUMERS / 32) {
+                const int b = srp[row], e = srp[row + 1];
+                double s = 0.0;
+                for (int k = b + lane; k < e; k += 32) s = __dadd_rn(s, __dmul_rn(val[k], __ldg(x + col[k])));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, o));
+                if (lane == 0 && e > b) y[r0 + row] = __dadd_rn(y[r0 + row], s);
+            }
+        }
+        // the stage is about to be overwritten through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[TS_STAGES + stage]));
     }
 }
 
@@ -246,6 +397,13 @@ int spmv_build_plan(csb200_mat *AT)
     if (AT->forced_plan) kind = AT->forced_plan;
     pl->kind = kind;
     if (kind == 1) {
+        // rows per block: a multiple of 4 (16-byte aligned rowptr slices), sized so that an
+        // average block fills ~85 % of a stage
+        int R = (int)(0.85 * TS_TILE / (avg > 1.0 ? avg : 1.0));
+        R = R > TS_CONSUMERS ? TS_CONSUMERS : R;
+        R &= ~3;
+        pl->rows_per_cta = R < 4 ? 4 : R;
+    } else if (kind == 3) {
         int R = (int)(0.8 * SP_TILE / (avg > 1.0 ? avg : 1.0));
         pl->rows_per_cta = R < 1 ? 1 : (R > SP_THREADS ? SP_THREADS : R);
     } else {
@@ -274,6 +432,19 @@ int spmv_run(csb200_mat *AT, const double *d_x, double *d_y)
     if (m == 0 || AT->nnz == 0) return CSB200_OK;
     SpmvPlan *pl = AT->plan;
     if (pl->kind == 1) {
+        const int R = pl->rows_per_cta;
+        const int nblocks = ceil_div(m, R);
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            CSB_CUDA(cudaGetDevice(&dev));
+            CSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        }
+        const int grid = min(nblocks, 2 * sms);      // two resident CTAs per SM
+        k_spmv_tma<<<grid, TS_THREADS, TS_SMEM, stream()>>>(m, nblocks, R, AT->p, AT->i, AT->x, d_x, d_y);
+        CSB_LAUNCHED();
+    } else if (pl->kind == 3) {
         const int R = pl->rows_per_cta;
         k_spmv_stream<<<ceil_div(m, R), SP_THREADS, 0, stream()>>>(m, AT->p, AT->i, AT->x, d_x, d_y, R);
         CSB_LAUNCHED();

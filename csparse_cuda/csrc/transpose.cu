@@ -266,11 +266,11 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     const csi m = A->m, n = A->n;
     const long long nnz = A->nnz;
     const bool has_x = values && A->x != nullptr;
-    const size_t cap = (size_t)(nnz > 0 ? nnz : 1);
+    const size_t cap = (size_t)(nnz > 0 ? nnz : 1) + MAT_PAD;
 
     csb200_mat *C = new csb200_mat();
     C->m = n; C->n = m; C->nnz = nnz; C->device = A->device;
-    int st = dev_alloc(&C->p, (size_t)m + 1);
+    int st = dev_alloc(&C->p, (size_t)m + 1 + MAT_PAD);
     if (st == CSB200_OK) st = dev_alloc(&C->i, cap);
     if (st == CSB200_OK && has_x) st = dev_alloc(&C->x, cap);
     auto fail = [&](int s) { csb200_mat_free(C); return s; };

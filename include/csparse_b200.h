@@ -103,7 +103,8 @@ CSB200_API int csb200_gaxpy_host(csi m, csi n, const csi *Ap, const csi *Ai, con
                       const double *x, double *y);
 /* build (and cache) the CSR view now instead of on first use */
 CSB200_API int csb200_gaxpy_prepare(csb200_mat *A);
-/* which kernel the cached plan uses: 1 = row-stream, 2 = merge-path */
+/* which kernel the cached plan uses: 1 = row-stream (TMA-staged), 2 = merge-path,
+ * 3 = row-stream with plain loads (kept for A/B measurements) */
 CSB200_API int csb200_gaxpy_plan(csb200_mat *A, int *kind);
 /* force a plan (0 = automatic); for tests and benchmarks */
 CSB200_API int csb200_gaxpy_force_plan(csb200_mat *A, int kind);

@@ -92,8 +92,8 @@ if __name__ == "__main__":
     med, best = timeit(lambda: _lib.lib().csb200_cumsum_dev(C.c_void_p(pp.data_ptr()), C.c_void_p(c.data_ptr()), n, C.byref(tot)), 2, 10)
     report("cs_cumsum n=2^24 (incl. D2H of total)", synth.cumsum_bytes(n), med, best)
     if a.lap:
-        run_matrix(f"lap2d {a.lap}", *synth.lap2d(a.lap), do_mul=a.lap <= 2048, plans=("stream", "merge"))
+        run_matrix(f"lap2d {a.lap}", *synth.lap2d(a.lap), do_mul=a.lap <= 2048, plans=("stream", "stream_ld", "merge"))
     if a.st:
-        run_matrix(f"st27 {a.st}", *synth.st27(a.st), do_mul=True, plans=("stream",))
+        run_matrix(f"st27 {a.st}", *synth.st27(a.st), do_mul=True, plans=("stream", "stream_ld"))
     if a.rmat:
         run_matrix(f"rmat {a.rmat}", *synth.rmat(a.rmat, 16), do_mul=False, plans=("merge", "stream"))
