@@ -41,6 +41,9 @@ def balanced_bounds(weights_prefix: np.ndarray, parts: int) -> np.ndarray:
     targets = (np.arange(1, parts, dtype=np.float64) * total / parts)
     inner = np.searchsorted(weights_prefix, targets, side="left").astype(np.int64)
     inner = np.clip(inner, 0, n)
+    lower = np.clip(inner - 1, 0, n)                      # the cut just before may be closer
+    closer = np.abs(weights_prefix[lower] - targets) < np.abs(weights_prefix[inner] - targets)
+    inner = np.where(closer, lower, inner)
     b = np.concatenate(([0], inner, [n])).astype(np.int64)
     return np.maximum.accumulate(b)
 
@@ -80,7 +83,7 @@ class ExchangePlan:
 
 
 def plan_exchange(rank: int, world: int, x_bounds: np.ndarray, windows: Sequence[Sequence[int]],
-                  n_global: int) -> ExchangePlan:
+                  n_global: int, force_gather: bool = False) -> ExchangePlan:
     """``windows[g] = (cmin, cmax)`` of every rank (all-gathered).  Halo mode needs every
     rank's window to stay inside its own slice of x plus its two neighbours' slices."""
     lo_need, hi_need, halo_ok = [], [], True
@@ -97,7 +100,7 @@ def plan_exchange(rank: int, world: int, x_bounds: np.ndarray, windows: Sequence
         hi_need.append(hi)
     if world == 1:
         return ExchangePlan("halo", x_bounds, 0, n_global, [0], [0])
-    if not halo_ok:
+    if not halo_ok or force_gather:
         return ExchangePlan("gather", x_bounds, 0, n_global, lo_need, hi_need)
     c0, c1 = int(x_bounds[rank]), int(x_bounds[rank + 1])
     return ExchangePlan("halo", x_bounds, c0 - lo_need[rank], c1 + hi_need[rank], lo_need, hi_need)
@@ -118,7 +121,8 @@ class ShardedGaxpy:
     """
 
     def __init__(self, block: RowBlock, m_global: int, n_global: int, row_bounds, x_bounds=None,
-                 make_local: Callable = None, local_spmv: Callable = None, device="cpu", group=None):
+                 make_local: Callable = None, local_spmv: Callable = None, device="cpu", group=None,
+                 force_gather: bool = False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
@@ -143,7 +147,7 @@ class ShardedGaxpy:
             windows = [(int(w[0]), int(w[1])) for w in allw]
         else:
             windows = [(block.cmin, block.cmax)]
-        self.plan = plan_exchange(self.rank, self.world, self.x_bounds, windows, n_global)
+        self.plan = plan_exchange(self.rank, self.world, self.x_bounds, windows, n_global, force_gather)
         pl = self.plan
         self.c0, self.c1 = int(self.x_bounds[self.rank]), int(self.x_bounds[self.rank + 1])
         self.x_window = torch.zeros(pl.win_hi - pl.win_lo, dtype=torch.float64, device=device)
@@ -166,8 +170,15 @@ class ShardedGaxpy:
             if len(set(sizes)) == 1:
                 dist.all_gather_into_tensor(xw, x_own.contiguous(), group=self.group)
             else:
-                views = [xw[int(pl.x_bounds[g]):int(pl.x_bounds[g + 1])] for g in range(self.world)]
-                dist.all_gather(views, x_own.contiguous(), group=self.group)
+                # uneven ownership: gather equal-sized padded slices, then place them
+                mx = max(sizes)
+                if getattr(self, "_pad", None) is None:
+                    self._pad = torch.zeros(self.world * mx, dtype=torch.float64, device=self.device)
+                    self._mine = torch.zeros(mx, dtype=torch.float64, device=self.device)
+                self._mine[: sizes[self.rank]] = x_own
+                dist.all_gather_into_tensor(self._pad, self._mine, group=self.group)
+                for g in range(self.world):
+                    xw[int(pl.x_bounds[g]):int(pl.x_bounds[g + 1])] = self._pad[g * mx: g * mx + sizes[g]]
             self.exchanged_bytes = 8 * (self.n_global - sizes[self.rank])
             return xw
         xw[self.own] = x_own

@@ -1,0 +1,92 @@
+"""Full-size BASELINE configs on the GPU: compared with the C oracle where it finishes
+in seconds, and through size-independent properties otherwise."""
+import numpy as np
+import pytest
+
+import csparse_cuda as cc
+from csparse_cuda import synth
+from oracle import oracle as orc
+from tests.golden_util import normwise
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.asarray(a, np.float64).view(np.int64)
+
+
+def test_c3_lap2d_4096_transpose_and_gaxpy():
+    """Config C3: n = 16 777 216, nnz = 83 869 696."""
+    m, n, p, i, x = synth.lap2d(4096)
+    assert len(i) == 83869696
+    A = orc.csc(m, n, p, i, x)
+    dA = cc.from_arrays(m, n, p, i, x)
+    dT = cc.cs_transpose(dA, True)
+    tp, ti, tx = dT.arrays()
+    R = orc.cs_transpose(A, True)
+    assert np.array_equal(tp, R.p) and np.array_equal(ti, R.i) and np.array_equal(bits(tx), bits(R.x))
+    del R
+    # symmetric matrix: A' == A bit for bit; and transposing twice is the identity
+    assert np.array_equal(tp, p) and np.array_equal(ti, i) and np.array_equal(bits(tx), bits(x))
+    xv, y0 = synth.vectors(m, n)
+    yref = y0.copy()
+    orc.cs_gaxpy(A, xv, yref)
+    for plan in ("stream", "merge"):
+        dA.force_gaxpy_plan(plan)
+        y = y0.copy()
+        assert cc.cs_gaxpy(dA, xv, y)
+        assert normwise(y, yref) <= 1e-12
+        if plan == "stream":
+            assert np.array_equal(bits(y), bits(yref))        # every block fits a stage: bit-exact
+    # linearity: A(2x) accumulates exactly twice A x on top of y0 = 0
+    z1, z2 = np.zeros(m), np.zeros(m)
+    cc.cs_gaxpy(dA, xv, z1)
+    cc.cs_gaxpy(dA, 2.0 * xv, z2)
+    assert np.array_equal(bits(2.0 * z1), bits(z2))
+
+
+def test_c4_st27_multiply():
+    """Config C4 family: full oracle comparison at 64^3, structural properties at 128^3."""
+    m, n, p, i, x = synth.st27(64)
+    A = orc.csc(m, n, p, i, x)
+    R = orc.cs_multiply(A, A)
+    dA = cc.from_arrays(m, n, p, i, x)
+    cp, ci, cx = cc.cs_multiply(dA, dA).arrays()
+    assert R.nnz == (5 * 64 - 4) ** 3
+    assert np.array_equal(cp, R.p) and np.array_equal(ci, R.i[:R.nnz])      # discovery order
+    assert np.array_equal(bits(cx), bits(R.x[:R.nnz]))
+    del R, cp, ci, cx
+    dA.free()
+    m, n, p, i, x = synth.st27(128)
+    dA = cc.from_arrays(m, n, p, i, x)
+    dC = cc.cs_multiply(dA, dA)
+    assert dC.nnz == 634 ** 3 == 254840104
+    assert cc.last_multiply_flops() == 1142 ** 3 == 1489355288
+    # C v == A (A v) within rounding (a checksum of checksums), v > 0 so no cancellation
+    v = np.random.default_rng(5).uniform(0.5, 1.5, n)
+    t = np.zeros(m); cc.cs_gaxpy(dA, v, t)
+    u = np.zeros(m); cc.cs_gaxpy(dA, t, u)
+    w = np.zeros(m); cc.cs_gaxpy(dC, v, w)
+    assert normwise(w, u) <= 1e-12
+    # transpose of C has the same column counts (A*A is structurally symmetric)
+    tp = cc.cs_transpose(dC, False).arrays()[0]
+    assert np.array_equal(tp, dC.arrays()[0])
+
+
+def test_c5_rmat20_transpose_and_gaxpy():
+    """Config C5 family at scale 20 (16 M nnz, rows up to ~40 k entries): merge-path plan."""
+    m, n, p, i, x = synth.rmat(20, 16)
+    A = orc.csc(m, n, p, i, x)
+    dA = cc.from_arrays(m, n, p, i, x)
+    tp, ti, tx = cc.cs_transpose(dA, True).arrays()
+    R = orc.cs_transpose(A, True)
+    assert np.array_equal(tp, R.p) and np.array_equal(ti, R.i) and np.array_equal(bits(tx), bits(R.x))
+    xv, y0 = synth.vectors(m, n)
+    yref = y0.copy()
+    orc.cs_gaxpy(A, xv, yref)
+    y = y0.copy()
+    assert cc.cs_gaxpy(dA, xv, y)
+    assert dA.gaxpy_plan() == "merge"
+    assert normwise(y, yref) <= 1e-12
+    untouched = np.diff(R.p) == 0                 # empty rows keep y bit for bit
+    assert np.array_equal(bits(y[untouched]), bits(y0[untouched]))

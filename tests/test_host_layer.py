@@ -1,0 +1,116 @@
+"""CPU-only checks of the host layer and the C-ABI boundary: the library loads and
+exports every symbol include/csparse_b200.h declares, argument-shape errors map to
+the reference's sentinels without touching a GPU, and the product package never
+reaches into oracle/."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+import csparse_cuda as cc
+from csparse_cuda import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "csparse_b200.h")).read()
+    return sorted(set(re.findall(r"CSB200_API\s+[\w\s\*]+?\b(csb200_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_functions()
+    assert len(names) >= 25
+    L = _lib.lib()
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/csparse_b200.h but not exported"
+    assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header out of sync"
+    assert L.csb200_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_header_cites_the_reference_for_each_entry_point():
+    src = open(os.path.join(ROOT, "include", "csparse_b200.h")).read()
+    for ref in ("csparse.py:767-784", "csparse.py:2292-2315", "csparse.py:1199-1213", "csparse.py:1608-1642",
+                "csparse.py:37-54"):
+        assert ref in src
+
+
+def test_cs_object_and_predicates():
+    A = cc.cs()
+    assert (A.nzmax, A.m, A.n, A.p, A.i, A.x, A.nz) == (0, 0, 0, [], [], [], 0)
+    assert cc.CS_TRIPLET(A) and not cc.CS_CSC(A)
+    A.nz = -1
+    assert cc.CS_CSC(A) and not cc.CS_TRIPLET(A)
+    assert not cc.CS_CSC(None) and not cc.CS_TRIPLET(None)
+
+
+def test_sentinels_need_no_gpu():
+    """Argument-shape errors return None / False / -1 like the reference
+    (csparse.py:777, :1207-1208, :1616-1619, :2299-2300) before any device work."""
+    T = cc.cs(); T.nz = 2; T.m = T.n = 2
+    assert cc.cs_transpose(T, True) is None and cc.cs_transpose(None, False) is None
+    assert cc.cs_multiply(T, T) is None and cc.cs_multiply(None, None) is None
+    assert cc.cs_gaxpy(T, [1.0], [1.0]) is False and cc.cs_gaxpy(None, [1.0], [1.0]) is False
+    A = cc.cs(); A.nz = -1; A.m, A.n = 2, 3; A.p, A.i, A.x = [0, 0, 0, 0], [0], [0.0]
+    assert cc.cs_gaxpy(A, None, [0.0, 0.0]) is False and cc.cs_gaxpy(A, [0.0] * 3, None) is False
+    assert cc.cs_multiply(A, A) is None                       # A.n != B.m
+    assert cc.cs_cumsum(None, [1], 1) == -1 and cc.cs_cumsum([0, 0], None, 1) == -1
+    P = cc.cs(); P.nz = -1; P.m = P.n = 1; P.p, P.i, P.x = [0, 1], [0], None
+    with pytest.raises(TypeError):
+        cc.cs_gaxpy(P, [1.0], [1.0])
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    A = cc.cs(); A.nz = -1; A.m = A.n = 2; A.nzmax = 2
+    A.p, A.i, A.x = [0, 1, 2], [0, 1], [1.0, 2.0]
+    for call in (lambda: cc.cs_transpose(A, True), lambda: cc.cs_multiply(A, A),
+                 lambda: cc.cs_gaxpy(A, [1.0, 1.0], [0.0, 0.0]), lambda: cc.cs_cumsum([0, 0, 0], [1, 2], 2)):
+        with pytest.raises(cc.CSparseCudaError):
+            call()
+
+
+def test_product_never_imports_the_oracle():
+    for path in glob.glob(os.path.join(ROOT, "csparse_cuda", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h")):
+            text = open(path, errors="replace").read()
+            assert "oracle" not in text.lower(), f"{path} mentions the oracle"
+
+
+def test_marshalling():
+    assert cc._i32([1, 2, 3, 4], 3).tolist() == [1, 2, 3] and cc._i32([1, 2, 3], 3).dtype == np.int32
+    a = np.arange(5, dtype=np.int32)
+    assert cc._i32(a, 5) is a or np.shares_memory(cc._i32(a, 5), a)          # zero-copy for int32 numpy
+    assert cc._f64([1, 2.5], 2).tolist() == [1.0, 2.5]                       # ints are promoted
+    import array
+    assert cc._i32(array.array("i", [4, 5, 6]), 2).tolist() == [4, 5]
+    with pytest.raises(OverflowError):
+        cc._i32([2 ** 31], 1)
+
+
+def test_synthetic_generators():
+    m, n, p, i, x = synth.lap2d(16)
+    assert m == n == 256 and p[-1] == len(i) == 5 * 256 - 4 * 16
+    assert np.all(np.diff(i.astype(np.int64))[np.diff(np.repeat(np.arange(n), np.diff(p))) == 0] > 0)
+    d = np.zeros((m, n)); d[i, np.repeat(np.arange(n), np.diff(p))] = x
+    assert np.array_equal(d, d.T) and np.all(np.diag(d) == 4.0) and np.all(d.sum(1) >= 0)
+    # column slabs of a rectangular grid tile the whole matrix
+    full = synth.lap2d_cols(8, 24, 0, 192)
+    parts = [synth.lap2d_cols(8, 24, a, b) for a, b in ((0, 64), (64, 128), (128, 192))]
+    assert np.array_equal(np.concatenate([q[3] for q in parts]), full[3])
+    assert sum(len(q[3]) for q in parts) == 5 * 192 - 2 * 8 - 2 * 24
+    m, n, p, i, x = synth.st27(5)
+    assert p[-1] == len(i) == (3 * 5 - 2) ** 3 and x.min() >= 0.5 and x.max() <= 1.5
+    m, n, p, i, x = synth.rmat(8, 4)
+    cols = np.repeat(np.arange(n), np.diff(p))
+    key = cols.astype(np.int64) * m + i
+    assert np.all(np.diff(key) > 0)                      # canonical: sorted, no duplicates
+    assert synth.gaxpy_bytes(16777216, 16777216, 83869696) == 1476198404
+    assert synth.transpose_bytes(16777216, 16777216, 83869696) == 2147090440
+    assert synth.multiply_bytes(55742968, 55742968, 254840104, 2097152, 2097152) == 4421078316
