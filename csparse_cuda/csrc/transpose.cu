@@ -1,48 +1,48 @@
-// transpose.cu -- cs_transpose (csparse.py:2292-2315): C = A' as a counting sort
-// by row index.  The reference is a sequential stable scatter; the result must be
-// bit-identical (p, i and x), so the order inside every output column has to be
-// the source order.
+// transpose.cu -- cs_transpose (csparse.py:2292-2315): C = A' as a counting sort by
+// row index.  The reference is a sequential stable scatter (histogram :2305-2306,
+// cs_cumsum :2307, scatter :2308-2314); the result must be bit-identical (p, i, x),
+// so the order inside every output column has to be the source order.
 //
-// Kernels (all HBM-bound integer / byte movement, no tensor cores):
-//   k_hist        row histogram           w[Ai[p]]++               (:2305-2306)
-//   excl_scan     Cp = cumsum(w), w = Cp  (scan.cu)                (:2307)
-//   k_tile_cols   column of the first entry of every 4096-entry tile
-//   k_scatter     q = w[Ai[p]]++ ; Ci[q] = j ; Cx[q] = Ax[p]       (:2308-2314)
-//   k_fix_*       restore source order inside each output column
+// Per-entry global atomics and 4/8-byte scattered stores cost one L2 transaction
+// each and capped a direct scatter at 13 % of the HBM roofline on B200 (measured,
+// profiles/r1_probe_launches.csv).  This version moves the data in two coalesced
+// hops instead -- a two-level (bucket, row) counting sort:
 //
-// The scatter hands out slots with atomics, so entries of one output column may
-// land permuted.  Entries of an output column come from distinct source columns
-// (or are duplicates of one (i,j) pair), hence source order == ascending j with
-// ties in storage order: the fix kernels check every output column, sort the few
-// that are out of order by j, and re-read tied groups from the source column.
-// Correctness never depends on how the atomics were ordered; only speed does.
+//   k_bucket_hist   rows are grouped into buckets of RB consecutive rows; count
+//                   entries per bucket (warp-aggregated: ~4 atomics per 32 entries)
+//   excl_scan       bucket offsets (scan.cu) -- also the bucket fill cursors
+//   k_tile_cols     column of the first entry of every 4096-entry tile
+//   k_partition     stream (Ai, Ax), attach the column id, append {row, col, val}
+//                   to the entry's bucket (one warp-aggregated atomic per bucket and
+//                   warp; 16-byte stores in contiguous runs)
+//   k_bucket_sort   one CTA per bucket: count rows in shared memory (this IS the
+//                   reference's histogram + cs_cumsum, restricted to RB rows),
+//                   scatter the bucket into a shared-memory staging area, put every
+//                   row into source order, write Cp / Ci / Cx fully coalesced
+//   k_bucket_big    buckets larger than the staging area (power-law rows): the same
+//                   steps with the staging area in global memory
+//
+// Source order: entries of one output column come from distinct source columns (or
+// are duplicates of one (i,j) pair), so source order == ascending j with ties in
+// storage order.  Buckets are filled in whatever order the atomics land; each row
+// is then sorted by j, and tied groups are re-read from the source column in
+// storage order.  Correctness never depends on how atomics were ordered.
 #include "common.cuh"
 
 namespace csb {
 
 constexpr int TR_THREADS = 256;
-constexpr int TR_TILE = 4096;                 // entries per scatter CTA
+constexpr int TR_TILE = 4096;                 // entries per partition CTA
 constexpr int TR_SMEM_COLS = 6144;            // column pointers staged per tile
+constexpr int BK_THREADS = 512;
+constexpr int BK_EPT = 12;                    // entries per thread
+constexpr int BK_CAP = BK_THREADS * BK_EPT;   // 6144 entries staged per bucket
+constexpr int BK_RB_MAX = 2048;               // rows per bucket (power of two)
+constexpr int BK_SMEM = BK_CAP * 12 + 2 * (BK_RB_MAX + 1) * 4 + 64;
 constexpr int FIX_SHORT = 32;                 // rows up to this length: one thread
-constexpr int FIX_MID = 1024;                 // up to this: one warp; longer: one CTA
 
-// ---- histogram ---------------------------------------------------------------
-__global__ void __launch_bounds__(TR_THREADS)
-k_hist(const csi *__restrict__ Ai, long long nnz, int *__restrict__ w)
-{
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; p < nnz; p += stride) {
-        if (p + 3 < nnz) {
-            const int4 r = ldg_stream(reinterpret_cast<const int4 *>(Ai + p));
-            atomicAdd(&w[r.x], 1);
-            atomicAdd(&w[r.y], 1);
-            atomicAdd(&w[r.z], 1);
-            atomicAdd(&w[r.w], 1);
-        } else {
-            for (long long q = p; q < nnz; q++) atomicAdd(&w[Ai[q]], 1);
-        }
-    }
-}
+struct __align__(16) Entry { int row; int col; double val; };
+struct __align__(8) EntryP { int row; int col; };
 
 // ---- tile -> first column ------------------------------------------------------
 __global__ void k_tile_cols(const csi *__restrict__ Ap, int n, long long nnz, int ntiles,
@@ -55,15 +55,42 @@ __global__ void k_tile_cols(const csi *__restrict__ Ap, int n, long long nnz, in
     tile_col[t] = upper_row(Ap, 0, n, (int)p0);   // largest j with Ap[j] <= p0
 }
 
-// ---- scatter -------------------------------------------------------------------
+// ---- bucket histogram ------------------------------------------------------------
+__global__ void __launch_bounds__(TR_THREADS)
+k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__restrict__ bcount)
+{
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    // whole warps iterate together so that the match masks are well defined
+    for (long long p0 = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * 4; p0 < nnz; p0 += stride) {
+        const long long p = p0 + lane * 4;
+        int b[4] = {-1, -1, -1, -1};
+        if (p + 3 < nnz) {
+            const int4 r = ldg_stream(reinterpret_cast<const int4 *>(Ai + p));
+            b[0] = r.x >> log_rb; b[1] = r.y >> log_rb; b[2] = r.z >> log_rb; b[3] = r.w >> log_rb;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) if (p + e < nnz) b[e] = Ai[p + e] >> log_rb;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const unsigned peers = __match_any_sync(0xffffffffu, b[e]);
+            if (b[e] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&bcount[b[e]], __popc(peers));
+        }
+    }
+}
+
+// ---- partition into buckets ---------------------------------------------------------
 template <bool VALUES>
 __global__ void __launch_bounds__(TR_THREADS)
-k_scatter(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
-          long long nnz, const int *__restrict__ tile_col, int *__restrict__ w,
-          csi *__restrict__ Ci, double *__restrict__ Cx)
+k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+            long long nnz, const int *__restrict__ tile_col, int log_rb, int *__restrict__ bfill,
+            void *__restrict__ inter_)
 {
     __shared__ int sAp[TR_SMEM_COLS];
     const int t = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
     const long long p_begin = (long long)t * TR_TILE;
     const long long p_end = min(nnz, p_begin + TR_TILE);
     const int j_first = tile_col[t];
@@ -74,10 +101,12 @@ k_scatter(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *
         for (int k = threadIdx.x; k <= ncols; k += TR_THREADS) sAp[k] = Ap[j_first + k];
     __syncthreads();
 
-    for (long long p = p_begin + threadIdx.x * 4; p < p_end; p += TR_THREADS * 4) {
-        int rows[4];
-        double vals[4];
-        const int cnt = (int)min((long long)4, p_end - p);
+    // warps iterate together (uniform trip count) for the match/shuffle below
+    for (long long pw = p_begin + (threadIdx.x & ~31) * 4; pw < p_end; pw += TR_THREADS * 4) {
+        const long long p = pw + lane * 4;
+        int rows[4] = {0, 0, 0, 0}, cols[4] = {0, 0, 0, 0};
+        double vals[4] = {0.0, 0.0, 0.0, 0.0};
+        const int cnt = p < p_end ? (int)min((long long)4, p_end - p) : 0;
         if (cnt == 4) {
             const int4 r = ldg_stream(reinterpret_cast<const int4 *>(Ai + p));
             rows[0] = r.x; rows[1] = r.y; rows[2] = r.z; rows[3] = r.w;
@@ -87,29 +116,51 @@ k_scatter(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *
                 vals[0] = a.x; vals[1] = a.y; vals[2] = b.x; vals[3] = b.y;
             }
         } else {
-            for (int e = 0; e < cnt; e++) {
-                rows[e] = Ai[p + e];
-                if (VALUES) vals[e] = Ax[p + e];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (e < cnt) {
+                    rows[e] = Ai[p + e];
+                    if (VALUES) vals[e] = Ax[p + e];
+                }
             }
         }
-        int j;   // column of entry p: largest j with Ap[j] <= p
-        if (staged) j = upper_row(sAp, 0, ncols - 1, (int)p);
-        else        j = upper_row(Ap, j_first, j_last, (int)p) - j_first;
+        if (cnt > 0) {
+            int j;   // column of entry p: largest j with Ap[j] <= p
+            if (staged) j = upper_row(sAp, 0, ncols - 1, (int)p);
+            else        j = upper_row(Ap, j_first, j_last, (int)p) - j_first;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (e < cnt) {
+                    const int pe = (int)p + e;
+                    if (staged) { while (sAp[j + 1] <= pe) j++; }
+                    else        { while (Ap[j_first + j + 1] <= pe) j++; }
+                    cols[e] = j_first + j;
+                }
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            if (e < cnt) {
-                const int pe = (int)p + e;
-                if (staged) { while (sAp[j + 1] <= pe) j++; }
-                else        { while (Ap[j_first + j + 1] <= pe) j++; }
-                const int q = atomicAdd(&w[rows[e]], 1);
-                Ci[q] = j_first + j;
-                if (VALUES) Cx[q] = vals[e];
+            const int b = e < cnt ? (rows[e] >> log_rb) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (b >= 0 && lane == leader) base = atomicAdd(&bfill[b], __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (b >= 0) {
+                const long long pos = (long long)base + __popc(peers & lt);
+                if (VALUES) {
+                    Entry en; en.row = rows[e]; en.col = cols[e]; en.val = vals[e];
+                    reinterpret_cast<Entry *>(inter_)[pos] = en;
+                } else {
+                    EntryP en; en.row = rows[e]; en.col = cols[e];
+                    reinterpret_cast<EntryP *>(inter_)[pos] = en;
+                }
             }
         }
     }
 }
 
-// ---- order repair ----------------------------------------------------------------
+// ---- order repair helpers ------------------------------------------------------------
 // After sorting an output column by j, runs of equal j are duplicates of one
 // (row r, column j) entry of A; their values must appear in A's storage order.
 __device__ void fix_tied_group(const csi *Ap, const csi *Ai, const double *Ax,
@@ -120,66 +171,40 @@ __device__ void fix_tied_group(const csi *Ap, const csi *Ai, const double *Ax,
         if (Ai[p] == r) cx[k++] = Ax[p];
 }
 
+// one thread: in-place insertion sort of a short row (len <= FIX_SHORT) by column
 template <bool VALUES>
-__global__ void __launch_bounds__(256)
-k_fix_short(int m, const csi *__restrict__ Cp, csi *Ci, double *Cx,
-            const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
-            int *mid_list, int *big_list, int *counts)
+__device__ void thread_fix_row(int r, csi *ci, double *cx, int len,
+                               const csi *Ap, const csi *Ai, const double *Ax)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= m) return;
-    const int b = Cp[r], len = Cp[r + 1] - b;
-    if (len < 2) return;
-    if (len > FIX_SHORT) {
-        if (len <= FIX_MID) mid_list[atomicAdd(&counts[0], 1)] = r;
-        else                big_list[atomicAdd(&counts[1], 1)] = r;
-        return;
-    }
     bool sorted = true;
-    int prev = Ci[b];
-    for (int k = 1; k < len; k++) {
-        const int cur = Ci[b + k];
-        sorted &= cur > prev;
-        prev = cur;
-    }
+    for (int k = 1; k < len; k++) sorted &= ci[k] > ci[k - 1];
     if (sorted) return;
-    // rare: insertion sort of (j, x) pairs by j
-    int key[FIX_SHORT];
-    double val[FIX_SHORT];
-    for (int k = 0; k < len; k++) {
-        key[k] = Ci[b + k];
-        if (VALUES) val[k] = Cx[b + k];
-    }
     for (int a = 1; a < len; a++) {
-        const int kj = key[a];
-        const double kv = VALUES ? val[a] : 0.0;
+        const int kj = ci[a];
+        const double kv = VALUES ? cx[a] : 0.0;
         int c = a - 1;
-        while (c >= 0 && key[c] > kj) {
-            key[c + 1] = key[c];
-            if (VALUES) val[c + 1] = val[c];
+        while (c >= 0 && ci[c] > kj) {
+            ci[c + 1] = ci[c];
+            if (VALUES) cx[c + 1] = cx[c];
             c--;
         }
-        key[c + 1] = kj;
-        if (VALUES) val[c + 1] = kv;
-    }
-    for (int k = 0; k < len; k++) {
-        Ci[b + k] = key[k];
-        if (VALUES) Cx[b + k] = val[k];
+        ci[c + 1] = kj;
+        if (VALUES) cx[c + 1] = kv;
     }
     if (VALUES) {
         for (int k = 0; k + 1 < len;) {
             int g = 1;
-            while (k + g < len && key[k + g] == key[k]) g++;
-            if (g > 1) fix_tied_group(Ap, Ai, Ax, r, key[k], Cx + b + k, g);
+            while (k + g < len && ci[k + g] == ci[k]) g++;
+            if (g > 1) fix_tied_group(Ap, Ai, Ax, r, ci[k], cx + k, g);
             k += g;
         }
     }
 }
 
-// Cooperative in-place sort of one output column by a group of G threads
-// (G = 32: a warp, G = blockDim: a CTA).  Normalised bitonic network: every
-// comparator moves the smaller key to the lower index, so virtual +inf padding
-// above `len` never moves and any length works.
+// Cooperative in-place sort of one row by a group of G threads (G = 32: a warp,
+// otherwise the whole CTA).  Normalised bitonic network: every comparator moves the
+// smaller key to the lower index, so virtual +inf padding above `len` never moves
+// and any length works.  Works on shared or global memory.
 template <int G, bool VALUES>
 __device__ void group_sort_row(csi *ci, double *cx, int len, int tid)
 {
@@ -188,10 +213,8 @@ __device__ void group_sort_row(csi *ci, double *cx, int len, int tid)
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (P >> 1); t += G) {
-                // t-th comparator of this stage
                 const int lo = ((t / j) * (j << 1)) + (t % j);
                 const int hi = (j == (k >> 1)) ? (lo ^ (k - 1)) : (lo + j);
-                // for the mirror stage lo^(k-1) > lo always holds (lo's bit j is 0)
                 if (hi < len) {
                     const int a = ci[lo], b = ci[hi];
                     if (a > b) {
@@ -206,13 +229,9 @@ __device__ void group_sort_row(csi *ci, double *cx, int len, int tid)
 }
 
 template <int G, bool VALUES>
-__device__ void group_fix_row(int r, const csi *Cp, csi *Ci, double *Cx,
+__device__ void group_fix_row(int r, csi *ci, double *cx, int len,
                               const csi *Ap, const csi *Ai, const double *Ax, int tid, int *flag)
 {
-    const int b = Cp[r], len = Cp[r + 1] - b;
-    csi *ci = Ci + b;
-    double *cx = VALUES ? Cx + b : nullptr;
-    // cooperative order check
     bool bad = false;
     for (int t = tid; t + 1 < len; t += G) bad |= ci[t] >= ci[t + 1];
     if (G == 32) {
@@ -235,29 +254,174 @@ __device__ void group_fix_row(int r, const csi *Cp, csi *Ci, double *Cx,
                 fix_tied_group(Ap, Ai, Ax, r, ci[t], cx + t, g);
             }
         }
+        if (G == 32) __syncwarp(); else __syncthreads();
     }
 }
 
-template <bool VALUES>
-__global__ void __launch_bounds__(128)
-k_fix_mid(const int *list, const int *counts, const csi *Cp, csi *Ci, double *Cx,
-          const csi *Ap, const csi *Ai, const double *Ax)
+// exclusive scan of cnt[0..n) (n <= BK_RB_MAX) into start[0..n], by the whole CTA
+__device__ void block_scan_rows(const int *cnt, int *start, int n, int *warp_tot)
 {
-    const int nrows = counts[0];
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < nrows; k += warps)
-        group_fix_row<32, VALUES>(list[k], Cp, Ci, Cx, Ap, Ai, Ax, threadIdx.x & 31, nullptr);
+    constexpr int PER = BK_RB_MAX / BK_THREADS;      // 4 consecutive rows per thread
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int v[PER], s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int idx = tid * PER + k; v[k] = idx < n ? cnt[idx] : 0; s += v[k]; }
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const int w = lane < BK_THREADS / 32 ? warp_tot[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        if (lane < BK_THREADS / 32) warp_tot[lane] = winc - w;
+    }
+    __syncthreads();
+    int e = warp_tot[wid] + inc - s;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int idx = tid * PER + k; if (idx <= n) start[idx] = e; e += v[k]; }
+    __syncthreads();
 }
 
+// ---- one CTA per bucket, staging in shared memory ---------------------------------------
 template <bool VALUES>
-__global__ void __launch_bounds__(512)
-k_fix_big(const int *list, const int *counts, const csi *Cp, csi *Ci, double *Cx,
-          const csi *Ap, const csi *Ai, const double *Ax)
+__global__ void __launch_bounds__(BK_THREADS, 2)
+k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
+              const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+              csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
 {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *sval = reinterpret_cast<double *>(smem);
+    int *scol = reinterpret_cast<int *>(smem + BK_CAP * 8);
+    int *rowcnt = scol + BK_CAP;
+    int *rowstart = rowcnt + BK_RB_MAX + 1;
+    int *warp_tot = rowstart + BK_RB_MAX + 1;          // 16 ints
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int rb = 1 << log_rb;
+    const int R0 = b << log_rb;
+    const int nrows = min(rb, m - R0);
+    const int base = bstart[b];
+    const int nb = bstart[b + 1] - base;
+    if (nb > BK_CAP) return;                           // k_bucket_big's job
+
+    for (int k = tid; k <= rb; k += BK_THREADS) rowcnt[k] = 0;
+    __syncthreads();
+    const Entry *inter = reinterpret_cast<const Entry *>(inter_) + base;
+    const EntryP *interp = reinterpret_cast<const EntryP *>(inter_) + base;
+    int rank[BK_EPT];
+#pragma unroll
+    for (int k = 0; k < BK_EPT; k++) {
+        const int e = tid + k * BK_THREADS;
+        rank[k] = 0;
+        if (e < nb) {
+            const int row = VALUES ? inter[e].row : interp[e].row;
+            rank[k] = atomicAdd(&rowcnt[row - R0], 1);
+        }
+    }
+    __syncthreads();
+    block_scan_rows(rowcnt, rowstart, nrows, warp_tot);
+#pragma unroll
+    for (int k = 0; k < BK_EPT; k++) {
+        const int e = tid + k * BK_THREADS;
+        if (e < nb) {
+            if (VALUES) {
+                const Entry en = inter[e];
+                const int pos = rowstart[en.row - R0] + rank[k];
+                scol[pos] = en.col;
+                sval[pos] = en.val;
+            } else {
+                const EntryP en = interp[e];
+                scol[rowstart[en.row - R0] + rank[k]] = en.col;
+            }
+        }
+    }
+    __syncthreads();
+    // source order inside every row: short rows by one thread, long rows by a warp
+    bool any_long = false;
+    for (int rl = tid; rl < nrows; rl += BK_THREADS) {
+        const int s = rowstart[rl], len = rowstart[rl + 1] - s;
+        if (len > FIX_SHORT) any_long = true;
+        else if (len > 1) thread_fix_row<VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax);
+    }
+    if (__syncthreads_or(any_long)) {
+        for (int rl = tid >> 5; rl < nrows; rl += BK_THREADS / 32) {
+            const int s = rowstart[rl], len = rowstart[rl + 1] - s;
+            if (len > FIX_SHORT)
+                group_fix_row<32, VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax, tid & 31, nullptr);
+        }
+        __syncthreads();
+    }
+    // coalesced output: this bucket owns C's columns R0..R0+nrows and the slots [base, base+nb)
+    for (int rl = tid; rl < nrows; rl += BK_THREADS) Cp[R0 + rl] = base + rowstart[rl];
+    if (b == nbuckets - 1 && tid == 0) Cp[m] = base + nb;
+    for (int t = tid; t < nb; t += BK_THREADS) {
+        Ci[base + t] = scol[t];
+        if (VALUES) Cx[base + t] = sval[t];
+    }
+}
+
+// ---- buckets that do not fit shared memory: staging in global memory ---------------------
+template <bool VALUES>
+__global__ void __launch_bounds__(BK_THREADS)
+k_bucket_big(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
+             const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+             csi *Cp, csi *Ci, double *Cx)
+{
+    __shared__ int rowcnt[BK_RB_MAX + 1];
+    __shared__ int rowstart[BK_RB_MAX + 1];
+    __shared__ int warp_tot[BK_THREADS / 32];
     __shared__ int flag;
-    const int nrows = counts[1];
-    for (int k = blockIdx.x; k < nrows; k += gridDim.x)
-        group_fix_row<512, VALUES>(list[k], Cp, Ci, Cx, Ap, Ai, Ax, threadIdx.x, &flag);
+    const int tid = threadIdx.x;
+    const int rb = 1 << log_rb;
+    for (int b = blockIdx.x; b < nbuckets; b += gridDim.x) {
+        const int base = bstart[b];
+        const int nb = bstart[b + 1] - base;
+        if (nb <= BK_CAP) continue;
+        const int R0 = b << log_rb;
+        const int nrows = min(rb, m - R0);
+        const Entry *inter = reinterpret_cast<const Entry *>(inter_) + base;
+        const EntryP *interp = reinterpret_cast<const EntryP *>(inter_) + base;
+        for (int k = tid; k <= rb; k += BK_THREADS) rowcnt[k] = 0;
+        __syncthreads();
+        for (int e = tid; e < nb; e += BK_THREADS)
+            atomicAdd(&rowcnt[(VALUES ? inter[e].row : interp[e].row) - R0], 1);
+        __syncthreads();
+        block_scan_rows(rowcnt, rowstart, nrows, warp_tot);
+        for (int rl = tid; rl < nrows; rl += BK_THREADS) Cp[R0 + rl] = base + rowstart[rl];
+        if (b == nbuckets - 1 && tid == 0) Cp[m] = base + nb;
+        for (int k = tid; k <= rb; k += BK_THREADS) rowcnt[k] = 0;      // reused as fill cursors
+        __syncthreads();
+        for (int e = tid; e < nb; e += BK_THREADS) {
+            int row, col;
+            double val = 0.0;
+            if (VALUES) { const Entry en = inter[e]; row = en.row; col = en.col; val = en.val; }
+            else        { const EntryP en = interp[e]; row = en.row; col = en.col; }
+            const int pos = base + rowstart[row - R0] + atomicAdd(&rowcnt[row - R0], 1);
+            Ci[pos] = col;
+            if (VALUES) Cx[pos] = val;
+        }
+        __syncthreads();
+        // rows: one thread (short), one warp (medium), the whole CTA (long)
+        for (int rl = tid; rl < nrows; rl += BK_THREADS) {
+            const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
+            if (len > 1 && len <= FIX_SHORT) thread_fix_row<VALUES>(R0 + rl, Ci + s, Cx + s, len, Ap, Ai, Ax);
+        }
+        for (int rl = tid >> 5; rl < nrows; rl += BK_THREADS / 32) {
+            const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
+            if (len > FIX_SHORT && len <= 2048)
+                group_fix_row<32, VALUES>(R0 + rl, Ci + s, Cx + s, len, Ap, Ai, Ax, tid & 31, nullptr);
+        }
+        __syncthreads();
+        for (int rl = 0; rl < nrows; rl++) {
+            const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
+            if (len > 2048)
+                group_fix_row<BK_THREADS, VALUES>(R0 + rl, Ci + s, Cx + s, len, Ap, Ai, Ax, tid, &flag);
+        }
+        __syncthreads();
+    }
 }
 
 // ---- host side -------------------------------------------------------------------
@@ -275,58 +439,55 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     if (st == CSB200_OK && has_x) st = dev_alloc(&C->x, cap);
     auto fail = [&](int s) { csb200_mat_free(C); return s; };
     if (st != CSB200_OK) return fail(st);
-
-    DevBuf<int> w, tile_col, lists, counts;
-    DevBuf<long long> total;
-    if ((st = w.alloc((size_t)(m > 0 ? m : 1))) != CSB200_OK) return fail(st);
-    if ((st = total.alloc(1)) != CSB200_OK) return fail(st);
     cudaStream_t s = stream();
 #define TR_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
         set_error(CSB200_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); return fail(CSB200_ERR_CUDA); } } while (0)
 #define TR_LAUNCHED() do { g_launches.fetch_add(1, std::memory_order_relaxed); TR_CUDA(cudaGetLastError()); } while (0)
-    TR_CUDA(cudaMemsetAsync(w.ptr, 0, (size_t)(m > 0 ? m : 1) * sizeof(int), s));
-    if (nnz == 0) {   // cs_spalloc leaves one zero slot (csparse.py:2401)
+    if (nnz == 0 || m == 0) {   // cs_spalloc leaves one zero slot (csparse.py:2401); Cp is all zero
+        TR_CUDA(cudaMemsetAsync(C->p, 0, ((size_t)m + 1) * sizeof(csi), s));
         TR_CUDA(cudaMemsetAsync(C->i, 0, sizeof(csi), s));
         if (has_x) TR_CUDA(cudaMemsetAsync(C->x, 0, sizeof(double), s));
+        *out = C;
+        return CSB200_OK;
     }
-    if (nnz > 0) {
-        const int blocks = (int)min((long long)ceil_div(nnz, TR_THREADS * 4 * 4), (long long)148 * 64);
-        k_hist<<<blocks, TR_THREADS, 0, s>>>(A->i, nnz, w.ptr);
-        TR_LAUNCHED();
-    }
-    if ((st = launch_excl_scan(C->p, w.ptr, m, total.ptr, nullptr)) != CSB200_OK) return fail(st);
-    if (nnz > 0) {
-        const int ntiles = ceil_div(nnz, TR_TILE);
-        if ((st = tile_col.alloc((size_t)ntiles + 1)) != CSB200_OK) return fail(st);
-        k_tile_cols<<<ceil_div(ntiles + 1, 256), 256, 0, s>>>(A->p, n, nnz, ntiles, tile_col.ptr);
-        TR_LAUNCHED();
-        if (has_x)
-            k_scatter<true><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, w.ptr, C->i, C->x);
-        else
-            k_scatter<false><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, nnz, tile_col.ptr, w.ptr, C->i, nullptr);
-        TR_LAUNCHED();
 
-        // order repair
-        const size_t maxlong = (size_t)(nnz / (FIX_SHORT + 1)) + 1;   // rows longer than FIX_SHORT
-        if ((st = lists.alloc(2 * maxlong)) != CSB200_OK) return fail(st);
-        if ((st = counts.alloc(2)) != CSB200_OK) return fail(st);
-        TR_CUDA(cudaMemsetAsync(counts.ptr, 0, 2 * sizeof(int), s));
-        int *mid = lists.ptr, *big = lists.ptr + maxlong;
-        if (has_x) k_fix_short<true><<<ceil_div(m, 256), 256, 0, s>>>(m, C->p, C->i, C->x, A->p, A->i, A->x, mid, big, counts.ptr);
-        else       k_fix_short<false><<<ceil_div(m, 256), 256, 0, s>>>(m, C->p, C->i, nullptr, A->p, A->i, nullptr, mid, big, counts.ptr);
+    // rows per bucket: the largest power of two whose average bucket fills <= 85 % of the staging area
+    const double avg = (double)nnz / m;
+    int log_rb = 3;
+    while (log_rb < 11 && (double)(2 << log_rb) * avg <= 0.85 * BK_CAP) log_rb++;
+    const int nbuckets = (int)(((long long)m + (1 << log_rb) - 1) >> log_rb);
+    const int ntiles = ceil_div(nnz, TR_TILE);
+
+    DevBuf<int> bstart, bfill, tile_col;
+    DevBuf<long long> total;
+    DevBuf<unsigned char> inter;
+    if ((st = bstart.alloc((size_t)nbuckets + 1)) || (st = bfill.alloc((size_t)nbuckets + 1)) ||
+        (st = tile_col.alloc((size_t)ntiles + 1)) || (st = total.alloc(1)) ||
+        (st = inter.alloc((size_t)nnz * (has_x ? sizeof(Entry) : sizeof(EntryP)))))
+        return fail(st);
+    TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 1) * sizeof(int), s));
+    {
+        const int blocks = (int)min((long long)ceil_div(nnz, TR_THREADS * 4 * 2), (long long)148 * 32);
+        k_bucket_hist<<<blocks, TR_THREADS, 0, s>>>(A->i, nnz, log_rb, bfill.ptr);
         TR_LAUNCHED();
-        if (nnz > FIX_SHORT) {
-            const int g_mid = (int)min((long long)148 * 16, (long long)ceil_div((long long)maxlong, 4));
-            if (has_x) k_fix_mid<true><<<g_mid, 128, 0, s>>>(mid, counts.ptr, C->p, C->i, C->x, A->p, A->i, A->x);
-            else       k_fix_mid<false><<<g_mid, 128, 0, s>>>(mid, counts.ptr, C->p, C->i, nullptr, A->p, A->i, nullptr);
-            TR_LAUNCHED();
-        }
-        if (nnz > FIX_MID) {
-            const int g_big = 148 * 4;
-            if (has_x) k_fix_big<true><<<g_big, 512, 0, s>>>(big, counts.ptr, C->p, C->i, C->x, A->p, A->i, A->x);
-            else       k_fix_big<false><<<g_big, 512, 0, s>>>(big, counts.ptr, C->p, C->i, nullptr, A->p, A->i, nullptr);
-            TR_LAUNCHED();
-        }
+    }
+    // bstart = exclusive scan of the counts; bfill <- bstart (the fill cursors)
+    if ((st = launch_excl_scan(bstart.ptr, bfill.ptr, nbuckets, total.ptr, nullptr)) != CSB200_OK) return fail(st);
+    k_tile_cols<<<ceil_div(ntiles + 1, 256), 256, 0, s>>>(A->p, n, nnz, ntiles, tile_col.ptr);
+    TR_LAUNCHED();
+    if (has_x) k_partition<true><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
+    else       k_partition<false><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
+    TR_LAUNCHED();
+    TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+    TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+    if (has_x) k_bucket_sort<true><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+    else       k_bucket_sort<false><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+    TR_LAUNCHED();
+    if (nnz > BK_CAP) {
+        const int grid = min(nbuckets, 148 * 4);
+        if (has_x) k_bucket_big<true><<<grid, BK_THREADS, 0, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+        else       k_bucket_big<false><<<grid, BK_THREADS, 0, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+        TR_LAUNCHED();
     }
 #undef TR_CUDA
 #undef TR_LAUNCHED
