@@ -132,7 +132,7 @@ def cpu_workload(workload: str, k: int):
     if workload == "multiply_st27":
         m, n, p, i, x = synth.st27(k)
         A = orc.csc(m, n, p, i, x)
-        nnzc = (5 * k - 4) ** 3
+        nnzc = (5 * k - 6) ** 3
         return (lambda: orc.cs_multiply(A, A)), float(nnzc), \
             f"full cs_multiply A*A pass, st27 {k}^3 (nnz(C) {nnzc})", "nnz(C)/s"
     raise ValueError(workload)
@@ -465,7 +465,7 @@ def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_sr
     ms = device_timed(torch, dist, world, step, steps, warm)
     clocks = sampler.stop()
     launches = (cc.launch_count() - l0) * steps // (steps + warm)
-    nnzc = (5 * k - 4) ** 3
+    nnzc = (5 * k - 6) ** 3
     got = hold["c"].nnz if world == 1 else int(hold["c"][1][1].numel())
     assert got == nnzc, (got, nnzc)
     value = nnzc * steps / (ms * 1e-3)

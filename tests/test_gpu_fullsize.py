@@ -52,7 +52,7 @@ def test_c4_st27_multiply():
     R = orc.cs_multiply(A, A)
     dA = cc.from_arrays(m, n, p, i, x)
     cp, ci, cx = cc.cs_multiply(dA, dA).arrays()
-    assert R.nnz == (5 * 64 - 4) ** 3
+    assert R.nnz == (5 * 64 - 6) ** 3
     assert np.array_equal(cp, R.p) and np.array_equal(ci, R.i[:R.nnz])      # discovery order
     assert np.array_equal(bits(cx), bits(R.x[:R.nnz]))
     del R, cp, ci, cx

@@ -43,8 +43,15 @@ def report(name, nbytes, med, best, **kw):
                       "GBs": round(gbs, 1), "frac_of_measured_peak": round(gbs / PEAK, 3), **kw}), flush=True)
 
 
+ONLY = None
+
+
 def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
     nnz = len(i)
+    if ONLY == "transpose":
+        do_mul, plans = False, ()
+    if ONLY == "multiply":
+        plans = ()
     t0 = time.time()
     dA = cc.from_arrays(m, n, p, i, x)
     print(json.dumps({"what": tag + " upload", "s": round(time.time() - t0, 2), "nnz": nnz}), flush=True)
@@ -52,8 +59,9 @@ def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
 
     def tr():
         holder["c"] = cc.cs_transpose(dA, True)
-    med, best = timeit(tr, 2, 5)
-    report(tag + " cs_transpose", synth.transpose_bytes(m, n, nnz), med, best)
+    if ONLY != "multiply":
+        med, best = timeit(tr, 2, 5)
+        report(tag + " cs_transpose", synth.transpose_bytes(m, n, nnz), med, best)
     holder.clear()
     xv = torch.randn(n, dtype=torch.float64, device="cuda")
     yv = torch.randn(m, dtype=torch.float64, device="cuda")
@@ -78,9 +86,11 @@ if __name__ == "__main__":
     ap.add_argument("--lap", type=int, default=4096)
     ap.add_argument("--st", type=int, default=128)
     ap.add_argument("--rmat", type=int, default=20)
+    ap.add_argument("--only", default=None, choices=[None, "transpose", "multiply"])
     ap.add_argument("--once", action="store_true", help="one warm-up + one timed call per op (for ncu launch lists)")
     a = ap.parse_args()
     ONCE = a.once
+    ONLY = a.only
     torch.cuda.init()
     cc.set_stream(torch.cuda.current_stream().cuda_stream)
     n = 1 << 24
