@@ -32,14 +32,18 @@
 namespace csb {
 
 constexpr int TR_THREADS = 256;
-constexpr int TR_TILE = 4096;                 // entries per partition CTA
-constexpr int TR_SMEM_COLS = 6144;            // column pointers staged per tile
-constexpr int BK_THREADS = 512;
+constexpr int TR_TILE = 4096;                 // entries per histogram CTA
+constexpr int PT_EPT = 8;                     // entries per thread in the partition kernel
+constexpr int PT_TILE = TR_THREADS * PT_EPT;  // 2048 entries per partition CTA
+constexpr int PT_SMEM_COLS = 3072;            // column pointers staged per partition tile
+constexpr int HIST_WIN = 2048;                // bucket window counted in shared memory
+constexpr int BK_THREADS = 256;
 constexpr int BK_EPT = 12;                    // entries per thread
-constexpr int BK_CAP = BK_THREADS * BK_EPT;   // 6144 entries staged per bucket
-constexpr int BK_RB_MAX = 2048;               // rows per bucket (power of two)
+constexpr int BK_CAP = BK_THREADS * BK_EPT;   // 3072 entries staged per bucket
+constexpr int BK_RB_MAX = 1024;               // rows per bucket (power of two)
 constexpr int BK_SMEM = BK_CAP * 12 + 2 * (BK_RB_MAX + 1) * 4 + 64;
 constexpr int FIX_SHORT = 32;                 // rows up to this length: one thread
+constexpr int BIG_WROW = BK_CAP / (BK_THREADS / 32);   // 384: longest row a warp stages in its slice
 
 struct __align__(16) Entry { int row; int col; double val; };
 struct __align__(8) EntryP { int row; int col; };
@@ -51,110 +55,171 @@ __global__ void k_tile_cols(const csi *__restrict__ Ap, int n, long long nnz, in
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntiles) return;
     if (t == ntiles) { tile_col[t] = n - 1; return; }
-    const long long p0 = (long long)t * TR_TILE;
+    const long long p0 = (long long)t * PT_TILE;
     tile_col[t] = upper_row(Ap, 0, n, (int)p0);   // largest j with Ap[j] <= p0
 }
 
+// block-wide min / max of a per-thread value (256 threads)
+__device__ __forceinline__ void block_minmax(int lo, int hi, int *s_red, int &bmin, int &bmax)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_red[wid] = lo; s_red[8 + wid] = hi; }
+    __syncthreads();
+    bmin = s_red[0]; bmax = s_red[8];
+#pragma unroll
+    for (int w = 1; w < TR_THREADS / 32; w++) { bmin = min(bmin, s_red[w]); bmax = max(bmax, s_red[8 + w]); }
+    __syncthreads();
+}
+
 // ---- bucket histogram ------------------------------------------------------------
+// A tile of consecutive entries touches a narrow window of buckets for banded
+// matrices: count in a shared-memory window and flush one global atomic per
+// (tile, bucket).  Tiles whose window does not fit fall back to one global atomic
+// per entry (random matrices: the atomics are spread, which L2 handles well).
 __global__ void __launch_bounds__(TR_THREADS)
 k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__restrict__ bcount)
 {
-    const int lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * blockDim.x * 4;
-    // whole warps iterate together so that the match masks are well defined
-    for (long long p0 = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * 4; p0 < nnz; p0 += stride) {
-        const long long p = p0 + lane * 4;
-        int b[4] = {-1, -1, -1, -1};
-        if (p + 3 < nnz) {
+    __shared__ int cnt[HIST_WIN];
+    __shared__ int s_red[16];
+    const long long p_begin = (long long)blockIdx.x * TR_TILE;
+    const long long p_end = min(nnz, p_begin + TR_TILE);
+    int b[16];
+    int lo = INT_MAX, hi = -1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {                       // four independent 16-byte loads in flight
+        const long long p = p_begin + (long long)(k * TR_THREADS + threadIdx.x) * 4;
+        if (p + 3 < p_end) {
             const int4 r = ldg_stream(reinterpret_cast<const int4 *>(Ai + p));
-            b[0] = r.x >> log_rb; b[1] = r.y >> log_rb; b[2] = r.z >> log_rb; b[3] = r.w >> log_rb;
+            b[4 * k] = r.x >> log_rb; b[4 * k + 1] = r.y >> log_rb; b[4 * k + 2] = r.z >> log_rb; b[4 * k + 3] = r.w >> log_rb;
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; e++) if (p + e < nnz) b[e] = Ai[p + e] >> log_rb;
+            for (int e = 0; e < 4; e++) b[4 * k + e] = p + e < p_end ? (Ai[p + e] >> log_rb) : -1;
         }
+    }
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const unsigned peers = __match_any_sync(0xffffffffu, b[e]);
-            if (b[e] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&bcount[b[e]], __popc(peers));
-        }
+    for (int k = 0; k < 16; k++) if (b[k] >= 0) { lo = min(lo, b[k]); hi = max(hi, b[k]); }
+    int bmin, bmax;
+    block_minmax(lo, hi, s_red, bmin, bmax);
+    if (bmax < 0) return;
+    const int win = bmax - bmin + 1;
+    if (win <= HIST_WIN) {
+        for (int k = threadIdx.x; k < win; k += TR_THREADS) cnt[k] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (b[k] >= 0) atomicAdd(&cnt[b[k] - bmin], 1);
+        __syncthreads();
+        for (int k = threadIdx.x; k < win; k += TR_THREADS)
+            if (cnt[k]) atomicAdd(&bcount[bmin + k], cnt[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (b[k] >= 0) atomicAdd(&bcount[b[k]], 1);
     }
 }
 
 // ---- partition into buckets ---------------------------------------------------------
+// Tile of PT_TILE consecutive entries, all loaded up front (8 per thread).  Ranks
+// inside the tile come from shared-memory counters over the tile's bucket window;
+// one global atomic per (tile, bucket) reserves the slots, so the global atomics
+// are few and all in flight together.
 template <bool VALUES>
 __global__ void __launch_bounds__(TR_THREADS)
 k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
             long long nnz, const int *__restrict__ tile_col, int log_rb, int *__restrict__ bfill,
             void *__restrict__ inter_)
 {
-    __shared__ int sAp[TR_SMEM_COLS];
+    __shared__ int sAp[PT_SMEM_COLS];
+    __shared__ int cnt[HIST_WIN];
+    __shared__ int s_red[16];
     const int t = blockIdx.x;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = lanemask_lt();
-    const long long p_begin = (long long)t * TR_TILE;
-    const long long p_end = min(nnz, p_begin + TR_TILE);
+    const long long p_begin = (long long)t * PT_TILE;
+    const long long p_end = min(nnz, p_begin + PT_TILE);
     const int j_first = tile_col[t];
     const int j_last = tile_col[t + 1];           // >= column of the last entry of this tile
     const int ncols = j_last - j_first + 1;
-    const bool staged = ncols + 1 <= TR_SMEM_COLS;
+    const bool staged = ncols + 1 <= PT_SMEM_COLS;
     if (staged)
         for (int k = threadIdx.x; k <= ncols; k += TR_THREADS) sAp[k] = Ap[j_first + k];
-    __syncthreads();
 
-    // warps iterate together (uniform trip count) for the match/shuffle below
-    for (long long pw = p_begin + (threadIdx.x & ~31) * 4; pw < p_end; pw += TR_THREADS * 4) {
-        const long long p = pw + lane * 4;
-        int rows[4] = {0, 0, 0, 0}, cols[4] = {0, 0, 0, 0};
-        double vals[4] = {0.0, 0.0, 0.0, 0.0};
-        const int cnt = p < p_end ? (int)min((long long)4, p_end - p) : 0;
-        if (cnt == 4) {
+    int rows[PT_EPT], cols[PT_EPT], rank[PT_EPT];
+    double vals[PT_EPT];
+    int cntk[PT_EPT / 4];
+#pragma unroll
+    for (int k = 0; k < PT_EPT / 4; k++) {
+        const long long p = p_begin + (long long)(k * TR_THREADS + threadIdx.x) * 4;
+        cntk[k] = p < p_end ? (int)min((long long)4, p_end - p) : 0;
+        if (cntk[k] == 4) {
             const int4 r = ldg_stream(reinterpret_cast<const int4 *>(Ai + p));
-            rows[0] = r.x; rows[1] = r.y; rows[2] = r.z; rows[3] = r.w;
+            rows[4 * k] = r.x; rows[4 * k + 1] = r.y; rows[4 * k + 2] = r.z; rows[4 * k + 3] = r.w;
             if (VALUES) {
                 const double2 a = ldg_stream(reinterpret_cast<const double2 *>(Ax + p));
                 const double2 b = ldg_stream(reinterpret_cast<const double2 *>(Ax + p + 2));
-                vals[0] = a.x; vals[1] = a.y; vals[2] = b.x; vals[3] = b.y;
+                vals[4 * k] = a.x; vals[4 * k + 1] = a.y; vals[4 * k + 2] = b.x; vals[4 * k + 3] = b.y;
             }
         } else {
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                if (e < cnt) {
-                    rows[e] = Ai[p + e];
-                    if (VALUES) vals[e] = Ax[p + e];
-                }
+                rows[4 * k + e] = e < cntk[k] ? Ai[p + e] : -1;
+                if (VALUES) vals[4 * k + e] = e < cntk[k] ? Ax[p + e] : 0.0;
             }
         }
-        if (cnt > 0) {
-            int j;   // column of entry p: largest j with Ap[j] <= p
-            if (staged) j = upper_row(sAp, 0, ncols - 1, (int)p);
-            else        j = upper_row(Ap, j_first, j_last, (int)p) - j_first;
+    }
+    int lo = INT_MAX, hi = -1;
+#pragma unroll
+    for (int k = 0; k < PT_EPT; k++)
+        if (k % 4 < cntk[k / 4]) { const int b = rows[k] >> log_rb; lo = min(lo, b); hi = max(hi, b); }
+    int bmin, bmax;
+    block_minmax(lo, hi, s_red, bmin, bmax);      // also orders the sAp staging before its use
+    const int win = bmax - bmin + 1;
+    const bool windowed = win <= HIST_WIN;
+    if (windowed) {
+        for (int k = threadIdx.x; k < win; k += TR_THREADS) cnt[k] = 0;
+        __syncthreads();
+    }
+    // column of every entry + rank inside the tile's share of its bucket
+#pragma unroll
+    for (int k = 0; k < PT_EPT / 4; k++) {
+        if (cntk[k] > 0) {
+            const int p = (int)(p_begin + (long long)(k * TR_THREADS + threadIdx.x) * 4);
+            int j;   // largest j with Ap[j] <= p
+            if (staged) j = upper_row(sAp, 0, ncols - 1, p);
+            else        j = upper_row(Ap, j_first, j_last, p) - j_first;
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                if (e < cnt) {
-                    const int pe = (int)p + e;
+                if (e < cntk[k]) {
+                    const int pe = p + e;
                     if (staged) { while (sAp[j + 1] <= pe) j++; }
                     else        { while (Ap[j_first + j + 1] <= pe) j++; }
-                    cols[e] = j_first + j;
+                    cols[4 * k + e] = j_first + j;
+                    const int b = rows[4 * k + e] >> log_rb;
+                    rank[4 * k + e] = windowed ? atomicAdd(&cnt[b - bmin], 1) : atomicAdd(&bfill[b], 1);
                 }
             }
         }
+    }
+    if (windowed) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < win; k += TR_THREADS) {
+            const int c = cnt[k];
+            if (c) cnt[k] = atomicAdd(&bfill[bmin + k], c);      // cnt becomes the reserved base
+        }
+        __syncthreads();
+    }
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int b = e < cnt ? (rows[e] >> log_rb) : -1;
-            const unsigned peers = __match_any_sync(0xffffffffu, b);
-            const int leader = __ffs(peers) - 1;
-            int base = 0;
-            if (b >= 0 && lane == leader) base = atomicAdd(&bfill[b], __popc(peers));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (b >= 0) {
-                const long long pos = (long long)base + __popc(peers & lt);
-                if (VALUES) {
-                    Entry en; en.row = rows[e]; en.col = cols[e]; en.val = vals[e];
-                    reinterpret_cast<Entry *>(inter_)[pos] = en;
-                } else {
-                    EntryP en; en.row = rows[e]; en.col = cols[e];
-                    reinterpret_cast<EntryP *>(inter_)[pos] = en;
-                }
+    for (int k = 0; k < PT_EPT; k++) {
+        if (k % 4 < cntk[k / 4]) {
+            const int b = rows[k] >> log_rb;
+            const long long pos = (long long)rank[k] + (windowed ? cnt[b - bmin] : 0);
+            if (VALUES) {
+                Entry en; en.row = rows[k]; en.col = cols[k]; en.val = vals[k];
+                reinterpret_cast<Entry *>(inter_)[pos] = en;
+            } else {
+                EntryP en; en.row = rows[k]; en.col = cols[k];
+                reinterpret_cast<EntryP *>(inter_)[pos] = en;
             }
         }
     }
@@ -229,7 +294,7 @@ __device__ void group_sort_row(csi *ci, double *cx, int len, int tid)
 }
 
 template <int G, bool VALUES>
-__device__ void group_fix_row(int r, csi *ci, double *cx, int len,
+__device__ bool group_fix_row(int r, csi *ci, double *cx, int len,
                               const csi *Ap, const csi *Ai, const double *Ax, int tid, int *flag)
 {
     bool bad = false;
@@ -244,7 +309,7 @@ __device__ void group_fix_row(int r, csi *ci, double *cx, int len,
         bad = *flag != 0;
         __syncthreads();
     }
-    if (!bad) return;
+    if (!bad) return false;
     group_sort_row<G, VALUES>(ci, cx, len, tid);
     if (VALUES) {
         for (int t = tid; t + 1 < len; t += G) {
@@ -256,6 +321,7 @@ __device__ void group_fix_row(int r, csi *ci, double *cx, int len,
         }
         if (G == 32) __syncwarp(); else __syncthreads();
     }
+    return true;
 }
 
 // exclusive scan of cnt[0..n) (n <= BK_RB_MAX) into start[0..n], by the whole CTA
@@ -287,7 +353,7 @@ __device__ void block_scan_rows(const int *cnt, int *start, int n, int *warp_tot
 
 // ---- one CTA per bucket, staging in shared memory ---------------------------------------
 template <bool VALUES>
-__global__ void __launch_bounds__(BK_THREADS, 2)
+__global__ void __launch_bounds__(BK_THREADS, 4)
 k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
               const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
               csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
@@ -370,6 +436,7 @@ k_bucket_big(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, co
              const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
              csi *Cp, csi *Ci, double *Cx)
 {
+    extern __shared__ __align__(16) unsigned char stage[];     // BK_CAP * 12 bytes: row staging
     __shared__ int rowcnt[BK_RB_MAX + 1];
     __shared__ int rowstart[BK_RB_MAX + 1];
     __shared__ int warp_tot[BK_THREADS / 32];
@@ -404,21 +471,42 @@ k_bucket_big(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, co
             if (VALUES) Cx[pos] = val;
         }
         __syncthreads();
-        // rows: one thread (short), one warp (medium), the whole CTA (long)
+        // rows: one thread (<= 32, in place), one warp (<= BIG_WROW, staged in the warp's
+        // shared-memory slice), the whole CTA (<= BK_CAP staged in shared memory, longer
+        // rows sorted in place in global memory)
         for (int rl = tid; rl < nrows; rl += BK_THREADS) {
             const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
             if (len > 1 && len <= FIX_SHORT) thread_fix_row<VALUES>(R0 + rl, Ci + s, Cx + s, len, Ap, Ai, Ax);
         }
-        for (int rl = tid >> 5; rl < nrows; rl += BK_THREADS / 32) {
-            const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
-            if (len > FIX_SHORT && len <= 2048)
-                group_fix_row<32, VALUES>(R0 + rl, Ci + s, Cx + s, len, Ap, Ai, Ax, tid & 31, nullptr);
+        {
+            const int lane = tid & 31, wid = tid >> 5;
+            int *wcol = reinterpret_cast<int *>(stage + BK_CAP * 8) + wid * BIG_WROW;
+            double *wval = reinterpret_cast<double *>(stage) + wid * BIG_WROW;
+            for (int rl = wid; rl < nrows; rl += BK_THREADS / 32) {
+                const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
+                if (len <= FIX_SHORT || len > BIG_WROW) continue;
+                for (int t = lane; t < len; t += 32) { wcol[t] = Ci[s + t]; if (VALUES) wval[t] = Cx[s + t]; }
+                __syncwarp();
+                if (group_fix_row<32, VALUES>(R0 + rl, wcol, wval, len, Ap, Ai, Ax, lane, nullptr))
+                    for (int t = lane; t < len; t += 32) { Ci[s + t] = wcol[t]; if (VALUES) Cx[s + t] = wval[t]; }
+                __syncwarp();
+            }
         }
         __syncthreads();
         for (int rl = 0; rl < nrows; rl++) {
             const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
-            if (len > 2048)
+            if (len <= BIG_WROW) continue;
+            if (len <= BK_CAP) {
+                int *ccol = reinterpret_cast<int *>(stage + BK_CAP * 8);
+                double *cval = reinterpret_cast<double *>(stage);
+                for (int t = tid; t < len; t += BK_THREADS) { ccol[t] = Ci[s + t]; if (VALUES) cval[t] = Cx[s + t]; }
+                __syncthreads();
+                if (group_fix_row<BK_THREADS, VALUES>(R0 + rl, ccol, cval, len, Ap, Ai, Ax, tid, &flag))
+                    for (int t = tid; t < len; t += BK_THREADS) { Ci[s + t] = ccol[t]; if (VALUES) Cx[s + t] = cval[t]; }
+                __syncthreads();
+            } else {
                 group_fix_row<BK_THREADS, VALUES>(R0 + rl, Ci + s, Cx + s, len, Ap, Ai, Ax, tid, &flag);
+            }
         }
         __syncthreads();
     }
@@ -454,9 +542,9 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     // rows per bucket: the largest power of two whose average bucket fills <= 85 % of the staging area
     const double avg = (double)nnz / m;
     int log_rb = 3;
-    while (log_rb < 11 && (double)(2 << log_rb) * avg <= 0.85 * BK_CAP) log_rb++;
+    while (log_rb < 10 && (double)(2 << log_rb) * avg <= 0.85 * BK_CAP) log_rb++;
     const int nbuckets = (int)(((long long)m + (1 << log_rb) - 1) >> log_rb);
-    const int ntiles = ceil_div(nnz, TR_TILE);
+    const int ntiles = ceil_div(nnz, PT_TILE);
 
     DevBuf<int> bstart, bfill, tile_col;
     DevBuf<long long> total;
@@ -467,8 +555,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
         return fail(st);
     TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 1) * sizeof(int), s));
     {
-        const int blocks = (int)min((long long)ceil_div(nnz, TR_THREADS * 4 * 2), (long long)148 * 32);
-        k_bucket_hist<<<blocks, TR_THREADS, 0, s>>>(A->i, nnz, log_rb, bfill.ptr);
+        k_bucket_hist<<<ceil_div(nnz, TR_TILE), TR_THREADS, 0, s>>>(A->i, nnz, log_rb, bfill.ptr);
         TR_LAUNCHED();
     }
     // bstart = exclusive scan of the counts; bfill <- bstart (the fill cursors)
@@ -484,9 +571,11 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     else       k_bucket_sort<false><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
     TR_LAUNCHED();
     if (nnz > BK_CAP) {
-        const int grid = min(nbuckets, 148 * 4);
-        if (has_x) k_bucket_big<true><<<grid, BK_THREADS, 0, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-        else       k_bucket_big<false><<<grid, BK_THREADS, 0, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+        const int grid = min(nbuckets, 148 * 2);
+        TR_CUDA(cudaFuncSetAttribute(k_bucket_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
+        TR_CUDA(cudaFuncSetAttribute(k_bucket_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
+        if (has_x) k_bucket_big<true><<<grid, BK_THREADS, BK_CAP * 12, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+        else       k_bucket_big<false><<<grid, BK_THREADS, BK_CAP * 12, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
         TR_LAUNCHED();
     }
 #undef TR_CUDA
