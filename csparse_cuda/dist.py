@@ -153,9 +153,49 @@ class ShardedGaxpy:
         self.x_window = torch.zeros(pl.win_hi - pl.win_lo, dtype=torch.float64, device=device)
         self.own = slice(self.c0 - pl.win_lo, self.c1 - pl.win_lo)       # my slice inside the window
         col_local = (block.col.astype(np.int64) - pl.win_lo).astype(np.int32)
-        self.handle = make_local(block.rowptr, col_local, block.val, pl.win_hi - pl.win_lo)
         self.local_spmv = local_spmv
         self.exchanged_bytes = 0
+        # Rows that read halo entries sit (for banded matrices) at the two ends of the block:
+        # split it into top / interior / bottom so the interior SpMV overlaps the exchange.
+        nrows = block.r1 - block.r0
+        self.split = None
+        if pl.mode == "halo" and self.world > 1 and nrows > 0 and len(col_local):
+            rp = block.rowptr.astype(np.int64)
+            nonempty = rp[1:] > rp[:-1]
+            starts = rp[:-1][nonempty]
+            rmin = np.full(nrows, np.iinfo(np.int64).max)
+            rmax = np.full(nrows, -1, dtype=np.int64)
+            rmin[nonempty] = np.minimum.reduceat(block.col.astype(np.int64), starts)
+            rmax[nonempty] = np.maximum.reduceat(block.col.astype(np.int64), starts)
+            lo_rows = np.flatnonzero(rmin < self.c0)
+            hi_rows = np.flatnonzero(rmax >= self.c1)
+            top = int(lo_rows.max()) + 1 if len(lo_rows) else 0
+            bot = int(hi_rows.min()) if len(hi_rows) else nrows
+            if top < bot and (len(lo_rows) == 0 or lo_rows.max() < bot) and (len(hi_rows) == 0 or hi_rows.min() >= top):
+                self.split = (top, bot)
+        ncl = pl.win_hi - pl.win_lo
+        if self.split:
+            top, bot = self.split
+            rp = block.rowptr
+
+            def sub(a, b):
+                if b <= a:
+                    return None
+                return make_local((rp[a:b + 1] - rp[a]).astype(np.int32), col_local[rp[a]:rp[b]],
+                                  block.val[rp[a]:rp[b]], ncl)
+            self.h_top, self.handle, self.h_bot = sub(0, top), sub(top, bot), sub(bot, nrows)
+        else:
+            self.handle = make_local(block.rowptr, col_local, block.val, ncl)
+
+    def own_view(self):
+        """This rank's slice of x inside the local window.  Writing x here (instead of passing a
+        separate tensor to step) saves a device copy per step."""
+        return self.x_window[self.own]
+
+    def _place(self, x_own):
+        view = self.x_window[self.own]
+        if x_own.data_ptr() != view.data_ptr():
+            view.copy_(x_own)
 
     # -- the per-step exchange of x --------------------------------------------------
     def exchange(self, x_own):
@@ -163,7 +203,7 @@ class ShardedGaxpy:
         torch, dist, pl = self.torch, self.dist, self.plan
         xw = self.x_window
         if self.world == 1:
-            xw[self.own] = x_own
+            self._place(x_own)
             return xw
         if pl.mode == "gather":
             sizes = [int(pl.x_bounds[g + 1] - pl.x_bounds[g]) for g in range(self.world)]
@@ -181,7 +221,14 @@ class ShardedGaxpy:
                     xw[int(pl.x_bounds[g]):int(pl.x_bounds[g + 1])] = self._pad[g * mx: g * mx + sizes[g]]
             self.exchanged_bytes = 8 * (self.n_global - sizes[self.rank])
             return xw
-        xw[self.own] = x_own
+        for w in self._exchange_start(x_own):
+            w.wait()
+        return xw
+
+    def _exchange_start(self, x_own):
+        """Halo mode: place the own slice, post the neighbour sends / receives, return the works."""
+        dist, pl, xw = self.dist, self.plan, self.x_window
+        self._place(x_own)
         r, ops, nbytes = self.rank, [], 0
         own = xw[self.own]
         if r > 0:
@@ -198,14 +245,23 @@ class ShardedGaxpy:
             if pl.hi_need[r]:
                 ops.append(dist.P2POp(dist.irecv, xw[xw.numel() - pl.hi_need[r]:], r + 1, group=self.group))
                 nbytes += 8 * pl.hi_need[r]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
         self.exchanged_bytes = nbytes
-        return xw
+        return dist.batch_isend_irecv(ops) if ops else []
 
     def step(self, x_own, y_own):
-        """One distributed cs_gaxpy: exchange x, then y_own += A_block * x_window."""
+        """One distributed cs_gaxpy: exchange x, then y_own += A_block * x_window.  In halo
+        mode the interior rows run while the halos are in flight."""
+        if self.split:
+            top, bot = self.split
+            works = self._exchange_start(x_own)
+            self.local_spmv(self.handle, self.x_window, y_own[top:bot])
+            for w in works:
+                w.wait()
+            if self.h_top is not None:
+                self.local_spmv(self.h_top, self.x_window, y_own[:top])
+            if self.h_bot is not None:
+                self.local_spmv(self.h_bot, self.x_window, y_own[bot:])
+            return y_own
         xw = self.exchange(x_own)
         self.local_spmv(self.handle, xw, y_own)
         return y_own
@@ -260,20 +316,34 @@ def sharded_multiply(dA, dB, bounds, rank: int, gather: Optional[str] = "all", g
     cx = _as_tensor(x_ptr, max(dCl.nnz, 1), torch.float64, device)[: dCl.nnz] if dCl.has_values else None
     if world == 1:
         return dCl, (cp.clone(), ci.clone(), None if cx is None else cx.clone())
-    nnz_all = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(nnz_all, torch.tensor([dCl.nnz], dtype=torch.int64, device=device), group=group)
-    nnz_all = [int(t.item()) for t in nnz_all]
+    cnt = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(cnt, torch.tensor([dCl.nnz], dtype=torch.int64, device=device), group=group)
+    nnz_all = [int(v) for v in cnt.tolist()]
     offs = np.concatenate(([0], np.cumsum(nnz_all)))
     n_total = int(bounds[-1])
+    widths = [int(bounds[g + 1] - bounds[g]) for g in range(world)]
     Cp = torch.empty(n_total + 1, dtype=torch.int32, device=device)
     Ci = torch.empty(int(offs[-1]), dtype=torch.int32, device=device)
     Cx = torch.empty(int(offs[-1]), dtype=torch.float64, device=device) if cx is not None else None
-    p_views = [Cp[int(bounds[g]):int(bounds[g + 1])] for g in range(world)]
-    dist.all_gather(p_views, (cp[:-1] + int(offs[rank])).contiguous(), group=group)
+
+    def gather_ragged(dst, src, sizes, starts):
+        """all-gather of unequal pieces: equal-sized padded all_gather_into_tensor, then placement"""
+        mx = max(max(sizes), 1)
+        if len(set(sizes)) == 1 and dst.numel() == world * mx:
+            dist.all_gather_into_tensor(dst, src.contiguous(), group=group)
+            return
+        pad = torch.empty(world * mx, dtype=dst.dtype, device=device)
+        mine = torch.empty(mx, dtype=dst.dtype, device=device)
+        mine[: src.numel()] = src
+        dist.all_gather_into_tensor(pad, mine, group=group)
+        for g in range(world):
+            dst[starts[g]: starts[g] + sizes[g]] = pad[g * mx: g * mx + sizes[g]]
+
+    gather_ragged(Cp[:n_total], (cp[:-1] + int(offs[rank])), widths, [int(b) for b in bounds[:-1]])
     Cp[n_total] = int(offs[-1])
-    dist.all_gather([Ci[int(offs[g]):int(offs[g + 1])] for g in range(world)], ci.contiguous(), group=group)
+    gather_ragged(Ci, ci, nnz_all, [int(o) for o in offs[:-1]])
     if Cx is not None:
-        dist.all_gather([Cx[int(offs[g]):int(offs[g + 1])] for g in range(world)], cx.contiguous(), group=group)
+        gather_ragged(Cx, cx, nnz_all, [int(o) for o in offs[:-1]])
     return dCl, (Cp, Ci, Cx)
 
 
