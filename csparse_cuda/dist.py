@@ -293,19 +293,34 @@ def multiply_column_bounds(Ap: np.ndarray, Bp: np.ndarray, Bi: np.ndarray, parts
     return balanced_bounds(col_prefix, parts)
 
 
-def sharded_multiply(dA, dB, bounds, rank: int, gather: Optional[str] = "all", group=None, device="cuda"):
+def sharded_multiply(dA, dB, bounds, rank: int, gather: Optional[str] = "all", group=None, device="cuda",
+                     dB_local=None):
     """C(:, J_rank) = A * B(:, J_rank) on this rank; then the final gather.
 
-    Returns (local DeviceMatrix, gathered) where gathered is None, or a tuple of torch
-    tensors (Cp, Ci, Cx) holding the whole product (on every rank for gather="all").
+    ``dB_local`` may hold the pre-sliced column block B(:, J_rank) (slice once, multiply many
+    times).  Returns (local DeviceMatrix, gathered) where gathered is None, or a tuple of
+    torch tensors (Cp, Ci, Cx) holding the whole product (on every rank for gather="all").
     """
+    import os
+    import time
     import torch
     import torch.distributed as dist
     import csparse_cuda as cc
+    trace = os.environ.get("CSPARSE_DIST_TRACE") == "1"
+    marks = []
+
+    def mark(name):
+        if trace:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+    mark("start")
     j0, j1 = int(bounds[rank]), int(bounds[rank + 1])
-    dBl = dB.col_slice(j0, j1)
+    dBl = dB_local if dB_local is not None else dB.col_slice(j0, j1)
+    mark("col_slice")
     dCl = cc.cs_multiply(dA, dBl)
-    dBl.free()
+    mark("multiply")
+    if dB_local is None:
+        dBl.free()
     if gather is None:
         return dCl, None
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -339,11 +354,18 @@ def sharded_multiply(dA, dB, bounds, rank: int, gather: Optional[str] = "all", g
         for g in range(world):
             dst[starts[g]: starts[g] + sizes[g]] = pad[g * mx: g * mx + sizes[g]]
 
+    mark("alloc")
     gather_ragged(Cp[:n_total], (cp[:-1] + int(offs[rank])), widths, [int(b) for b in bounds[:-1]])
     Cp[n_total] = int(offs[-1])
+    mark("gather p")
     gather_ragged(Ci, ci, nnz_all, [int(o) for o in offs[:-1]])
+    mark("gather i")
     if Cx is not None:
         gather_ragged(Cx, cx, nnz_all, [int(o) for o in offs[:-1]])
+    mark("gather x")
+    if trace and rank == 0:
+        print("sharded_multiply trace (ms):",
+              ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])), flush=True)
     return dCl, (Cp, Ci, Cx)
 
 
