@@ -208,6 +208,18 @@ def from_arrays(m, n, p, i, x=None, validate: bool = True) -> DeviceMatrix:
     return upload(A, validate)
 
 
+def from_device(m, n, p_ptr: int, i_ptr: int, x_ptr: int = 0) -> DeviceMatrix:
+    """New handle from CSC arrays already in device memory (raw addresses, e.g.
+    torch_tensor.data_ptr(); int32 p of n+1 entries, int32 i, float64 x or 0 for
+    pattern-only).  The arrays are copied; contents are trusted (not validated)."""
+    out = C.c_void_p()
+    st = _lib.check(_lib.lib().csb200_mat_from_dev(int(m), int(n), C.c_void_p(p_ptr), C.c_void_p(i_ptr),
+                                                   C.c_void_p(x_ptr or None), C.byref(out)), "from_device")
+    if st == _lib.ERR_ARG:
+        raise ValueError(_lib.last_error())
+    return DeviceMatrix(out.value)
+
+
 def _as_device(A):
     """(DeviceMatrix, temporary?) for a cs or DeviceMatrix operand."""
     if isinstance(A, DeviceMatrix):

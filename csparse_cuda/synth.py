@@ -101,6 +101,42 @@ def rmat(scale: int, ef: int = 16, a=0.57, b=0.19, c=0.19, seed: int = 1):
     return n, n, p.astype(np.int32), i, np.ascontiguousarray(x, dtype=np.float64)
 
 
+def rmat_torch(scale: int, ef: int = 16, a=0.57, b=0.19, c=0.19, seed: int = 1, device="cuda"):
+    """The same R-MAT family generated on the GPU with torch (input generation only;
+    scale 24 takes minutes in numpy).  Returns torch tensors (p int32, i int32, x float64)
+    of the canonical CSC: duplicates summed, columns sorted.  Not bit-identical to rmat()."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n = 1 << scale
+    ne = ef << scale
+    r = torch.zeros(ne, dtype=torch.int64, device=device)
+    col = torch.zeros(ne, dtype=torch.int64, device=device)
+    for lvl in range(scale):
+        u = torch.rand(ne, generator=g, device=device, dtype=torch.float64)
+        r |= (u >= a + b).to(torch.int64) << lvl
+        col |= (((u >= a) & (u < a + b)) | (u >= a + b + c)).to(torch.int64) << lvl
+        del u
+    v = torch.rand(ne, generator=g, device=device, dtype=torch.float64) * 2.0 - 1.0
+    key = col * n + r
+    del r, col
+    key, order = torch.sort(key)
+    v = v[order]
+    del order
+    ukey, counts = torch.unique_consecutive(key, return_counts=True)
+    del key
+    ends = torch.cumsum(counts, 0)
+    cs = torch.cumsum(v, 0)
+    x = cs[ends - 1]
+    x[1:] -= cs[ends[:-1] - 1]          # segment sums (inputs only: rounding of the generator is irrelevant)
+    del cs, v, ends, counts
+    i = (ukey % n).to(torch.int32)
+    cj = ukey // n
+    p = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    p[1:] = torch.cumsum(torch.bincount(cj, minlength=n), 0)
+    return n, n, p.to(torch.int32), i, x.contiguous()
+
+
 def vectors(m: int, n: int):
     """x = default_rng(0).standard_normal(n), y0 = default_rng(1).standard_normal(m)."""
     return (np.random.default_rng(0).standard_normal(n),
