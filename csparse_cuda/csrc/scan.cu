@@ -1,7 +1,7 @@
 // scan.cu -- cs_cumsum (csparse.py:767-784) as a single-pass decoupled look-back
 // exclusive scan.  HBM-bound: reads c once (4 B), writes p and c once (8 B).
 //
-// Tiles of 2048 ints are claimed in launch order through an atomic ticket, so a
+// Tiles of 8192 ints are claimed in launch order through an atomic ticket, so a
 // tile only ever waits on tiles that are already resident (forward progress).
 // Each tile publishes {flag, value} in ONE 64-bit word (flag in the top two
 // bits), so no fence is needed between flag and payload.
@@ -10,8 +10,9 @@
 namespace csb {
 
 constexpr int SCAN_THREADS = 512;
-constexpr int SCAN_ITEMS = 4;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int SCAN_ROUNDS = 4;                       // 16-byte chunks per thread
+constexpr int SCAN_ITEMS = 4 * SCAN_ROUNDS;          // 16 ints per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS; // 8192 ints per tile
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 
 constexpr unsigned long long ST_NONE = 0, ST_AGG = 1, ST_PREFIX = 2;
@@ -32,7 +33,18 @@ __device__ __forceinline__ long long warp_sum(long long v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ long long warp_inclusive(long long v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
 
+// Tile layout: round q (0..3) covers the 16-byte chunks q*512 .. q*512+511 of the tile, thread
+// t owns chunk q*512 + t of every round: all four loads are coalesced and in flight together.
 template <bool VEC>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_excl_scan(csi *__restrict__ p, csi *__restrict__ c, int n,
@@ -40,56 +52,54 @@ k_excl_scan(csi *__restrict__ p, csi *__restrict__ c, int n,
             long long *total, int *maxv)
 {
     __shared__ unsigned s_tile;
-    __shared__ long long s_warp[SCAN_WARPS];
+    __shared__ long long s_part[SCAN_ROUNDS * SCAN_WARPS];   // (round, warp) sums, round-major
     __shared__ long long s_tile_excl;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned tile = s_tile;
-    const long long idx0 = (long long)tile * SCAN_TILE + (long long)tid * SCAN_ITEMS;
+    const long long base = (long long)tile * SCAN_TILE;
 
-    int v[SCAN_ITEMS] = {0, 0, 0, 0};
-    if (VEC && idx0 + 3 < n) {
-        int4 t = *reinterpret_cast<const int4 *>(c + idx0);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
+    int v[SCAN_ROUNDS][4];
+    long long s[SCAN_ROUNDS], inc[SCAN_ROUNDS];
+    int mx = INT_MIN;
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++)
-            if (idx0 + k < n) v[k] = c[idx0 + k];
+    for (int q = 0; q < SCAN_ROUNDS; q++) {
+        const long long idx0 = base + (long long)(q * SCAN_THREADS + tid) * 4;
+        if (VEC && idx0 + 3 < n) {
+            const int4 t = *reinterpret_cast<const int4 *>(c + idx0);
+            v[q][0] = t.x; v[q][1] = t.y; v[q][2] = t.z; v[q][3] = t.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[q][k] = idx0 + k < n ? c[idx0 + k] : 0;
+        }
     }
-    const long long tsum = (long long)v[0] + v[1] + v[2] + v[3];
-
-    if (maxv) {
-        int mx = INT_MIN;
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++)
-            if (idx0 + k < n) mx = max(mx, v[k]);
+    for (int q = 0; q < SCAN_ROUNDS; q++) {
+        const long long idx0 = base + (long long)(q * SCAN_THREADS + tid) * 4;
+        s[q] = (long long)v[q][0] + v[q][1] + v[q][2] + v[q][3];
+        if (maxv) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (idx0 + k < n) mx = max(mx, v[q][k]);
+        }
+        inc[q] = warp_inclusive(s[q], lane);
+        if (lane == 31) s_part[q * SCAN_WARPS + wid] = inc[q];
+    }
+    if (maxv) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (lane == 0 && mx != INT_MIN) atomicMax(maxv, mx);
     }
-
-    // inclusive scan of the per-thread sums inside each warp
-    long long inc = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        long long t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
 
     if (wid == 0) {
-        const long long ws = lane < SCAN_WARPS ? s_warp[lane] : 0;
-        long long winc = ws;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            long long t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        const long long block_sum = __shfl_sync(0xffffffffu, winc, SCAN_WARPS - 1);
-        if (lane < SCAN_WARPS) s_warp[lane] = winc - ws;   // exclusive offset of each warp
+        // 64 partial sums, two per lane, in tile order
+        const long long a = s_part[2 * lane], b = s_part[2 * lane + 1];
+        const long long pinc = warp_inclusive(a + b, lane);
+        const long long block_sum = __shfl_sync(0xffffffffu, pinc, 31);
+        s_part[2 * lane] = pinc - a - b;              // exclusive offsets
+        s_part[2 * lane + 1] = pinc - b;
 
         long long excl = 0;
         if (tile == 0) {
@@ -119,26 +129,31 @@ k_excl_scan(csi *__restrict__ p, csi *__restrict__ c, int n,
     }
     __syncthreads();
 
-    long long e = s_tile_excl + s_warp[wid] + (inc - tsum);
-    if (VEC && idx0 + 3 < n) {
-        int4 o;
-        o.x = (int)e; e += v[0];
-        o.y = (int)e; e += v[1];
-        o.z = (int)e; e += v[2];
-        o.w = (int)e;
-        *reinterpret_cast<int4 *>(p + idx0) = o;
-        *reinterpret_cast<int4 *>(c + idx0) = o;
-    } else {
+    const long long tile_excl = s_tile_excl;
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            const long long idx = idx0 + k;
-            if (idx < n) {
-                p[idx] = (int)e;
-                c[idx] = (int)e;
-                e += v[k];
-            } else if (idx == n) {
-                p[idx] = (int)e;
-                *total = e;
+    for (int q = 0; q < SCAN_ROUNDS; q++) {
+        const long long idx0 = base + (long long)(q * SCAN_THREADS + tid) * 4;
+        long long e = tile_excl + s_part[q * SCAN_WARPS + wid] + (inc[q] - s[q]);
+        if (VEC && idx0 + 3 < n) {
+            int4 o;
+            o.x = (int)e; e += v[q][0];
+            o.y = (int)e; e += v[q][1];
+            o.z = (int)e; e += v[q][2];
+            o.w = (int)e;
+            *reinterpret_cast<int4 *>(p + idx0) = o;
+            *reinterpret_cast<int4 *>(c + idx0) = o;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const long long idx = idx0 + k;
+                if (idx < n) {
+                    p[idx] = (int)e;
+                    c[idx] = (int)e;
+                    e += v[q][k];
+                } else if (idx == n) {
+                    p[idx] = (int)e;
+                    *total = e;
+                }
             }
         }
     }
