@@ -36,7 +36,12 @@ constexpr int TR_TILE = 4096;                 // entries per histogram CTA
 constexpr int PT_EPT = 8;                     // entries per thread in the partition kernel
 constexpr int PT_TILE = TR_THREADS * PT_EPT;  // 2048 entries per partition CTA
 constexpr int PT_SMEM_COLS = 3072;            // column pointers staged per partition tile
-constexpr int HIST_WIN = 2048;                // bucket window counted in shared memory
+constexpr int HIST_WIN = 4096;                // bucket window counted in shared memory
+constexpr int WB_EPT = 16;                    // entries per lane in the warp-per-bucket kernel
+constexpr int WB_CAP = 32 * WB_EPT;           // 512 entries staged per warp
+constexpr int WB_RB_MAX = 128;                // rows per bucket (power of two)
+constexpr int WB_WARPS = 4;                   // warps (independent buckets) per CTA
+constexpr int WB_WARP_BYTES = WB_CAP * 12 + (2 * WB_RB_MAX + 8) * 4;
 constexpr int BK_THREADS = 256;
 constexpr int BK_EPT = 12;                    // entries per thread
 constexpr int BK_CAP = BK_THREADS * BK_EPT;   // 3072 entries staged per bucket
@@ -429,6 +434,97 @@ k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, c
     }
 }
 
+// ---- one WARP per bucket, staging in the warp's slice of shared memory ---------------------
+// Buckets are small (<= WB_CAP entries, <= WB_RB_MAX rows) so that a single warp can count,
+// scan, scatter and order one bucket with __syncwarp only: the warps of an SM run as many
+// independent pipelines and hide each other's global-memory latency.
+template <bool VALUES>
+__global__ void __launch_bounds__(WB_WARPS * 32)
+k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
+                   const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+                   csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *mine = smem + wid * WB_WARP_BYTES;
+    double *sval = reinterpret_cast<double *>(mine);
+    int *scol = reinterpret_cast<int *>(mine + WB_CAP * 8);
+    int *cnt = scol + WB_CAP;                      // WB_RB_MAX
+    int *start = cnt + WB_RB_MAX;                  // WB_RB_MAX + 1
+    const int b = blockIdx.x * WB_WARPS + wid;
+    if (b >= nbuckets) return;
+    const int rb = 1 << log_rb;
+    const int R0 = b << log_rb;
+    const int nrows = min(rb, m - R0);
+    const int base = bstart[b];
+    const int nb = bstart[b + 1] - base;
+    if (nb > WB_CAP) return;                       // k_bucket_big's job
+
+    for (int k = lane; k < WB_RB_MAX; k += 32) cnt[k] = 0;
+    __syncwarp();
+    const Entry *inter = reinterpret_cast<const Entry *>(inter_) + base;
+    const EntryP *interp = reinterpret_cast<const EntryP *>(inter_) + base;
+    int rank[WB_EPT];
+#pragma unroll
+    for (int k = 0; k < WB_EPT; k++) {
+        const int e = lane + k * 32;
+        rank[k] = 0;
+        if (e < nb) rank[k] = atomicAdd(&cnt[(VALUES ? inter[e].row : interp[e].row) - R0], 1);
+    }
+    __syncwarp();
+    {   // exclusive scan of cnt[0..WB_RB_MAX) -> start[0..WB_RB_MAX]; 4 consecutive rows per lane
+        constexpr int PER = WB_RB_MAX / 32;
+        int v[PER], s = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { v[k] = cnt[lane * PER + k]; s += v[k]; }
+        int inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        int e = inc - s;
+#pragma unroll
+        for (int k = 0; k < PER; k++) { start[lane * PER + k] = e; e += v[k]; }
+        if (lane == 31) start[WB_RB_MAX] = e;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < WB_EPT; k++) {
+        const int e = lane + k * 32;
+        if (e < nb) {
+            if (VALUES) {
+                const Entry en = inter[e];
+                const int pos = start[en.row - R0] + rank[k];
+                scol[pos] = en.col;
+                sval[pos] = en.val;
+            } else {
+                const EntryP en = interp[e];
+                scol[start[en.row - R0] + rank[k]] = en.col;
+            }
+        }
+    }
+    __syncwarp();
+    bool any_long = false;
+    for (int rl = lane; rl < nrows; rl += 32) {
+        const int s = start[rl], len = start[rl + 1] - s;
+        if (len > FIX_SHORT) any_long = true;
+        else if (len > 1) thread_fix_row<VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax);
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, any_long)) {
+        for (int rl = 0; rl < nrows; rl++) {
+            const int s = start[rl], len = start[rl + 1] - s;
+            if (len > FIX_SHORT)
+                group_fix_row<32, VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax, lane, nullptr);
+        }
+        __syncwarp();
+    }
+    for (int rl = lane; rl < nrows; rl += 32) Cp[R0 + rl] = base + start[rl];
+    if (b == nbuckets - 1 && lane == 0) Cp[m] = base + nb;
+    for (int t = lane; t < nb; t += 32) {
+        Ci[base + t] = scol[t];
+        if (VALUES) Cx[base + t] = sval[t];
+    }
+}
+
 // ---- buckets that do not fit shared memory: staging in global memory ---------------------
 template <bool VALUES>
 __global__ void __launch_bounds__(BK_THREADS)
@@ -446,7 +542,7 @@ k_bucket_big(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, co
     for (int b = blockIdx.x; b < nbuckets; b += gridDim.x) {
         const int base = bstart[b];
         const int nb = bstart[b + 1] - base;
-        if (nb <= BK_CAP) continue;
+        if (nb <= WB_CAP) continue;
         const int R0 = b << log_rb;
         const int nrows = min(rb, m - R0);
         const Entry *inter = reinterpret_cast<const Entry *>(inter_) + base;
@@ -541,8 +637,8 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
 
     // rows per bucket: the largest power of two whose average bucket fills <= 85 % of the staging area
     const double avg = (double)nnz / m;
-    int log_rb = 3;
-    while (log_rb < 10 && (double)(2 << log_rb) * avg <= 0.85 * BK_CAP) log_rb++;
+    int log_rb = 2;
+    while (log_rb < 7 && (double)(2 << log_rb) * avg <= 0.85 * WB_CAP) log_rb++;
     const int nbuckets = (int)(((long long)m + (1 << log_rb) - 1) >> log_rb);
     const int ntiles = ceil_div(nnz, PT_TILE);
 
@@ -565,12 +661,14 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     if (has_x) k_partition<true><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
     else       k_partition<false><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
     TR_LAUNCHED();
-    TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
-    TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
-    if (has_x) k_bucket_sort<true><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-    else       k_bucket_sort<false><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
-    TR_LAUNCHED();
-    if (nnz > BK_CAP) {
+    {
+        constexpr int smem = WB_WARPS * WB_WARP_BYTES;
+        const int grid = ceil_div(nbuckets, WB_WARPS);
+        if (has_x) k_bucket_sort_warp<true><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+        else       k_bucket_sort_warp<false><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+        TR_LAUNCHED();
+    }
+    if (nnz > WB_CAP) {
         const int grid = min(nbuckets, 148 * 2);
         TR_CUDA(cudaFuncSetAttribute(k_bucket_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
         TR_CUDA(cudaFuncSetAttribute(k_bucket_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
