@@ -37,11 +37,11 @@ constexpr int PT_EPT = 8;                     // entries per thread in the parti
 constexpr int PT_TILE = TR_THREADS * PT_EPT;  // 2048 entries per partition CTA
 constexpr int PT_SMEM_COLS = 3072;            // column pointers staged per partition tile
 constexpr int HIST_WIN = 4096;                // bucket window counted in shared memory
-constexpr int WB_EPT = 16;                    // entries per lane in the warp-per-bucket kernel
-constexpr int WB_CAP = 32 * WB_EPT;           // 512 entries staged per warp
+constexpr int WB_EPT = 12;                    // entries per lane in the warp-per-bucket kernel
+constexpr int WB_CAP = 32 * WB_EPT;           // 384 entries staged per warp
 constexpr int WB_RB_MAX = 128;                // rows per bucket (power of two)
-constexpr int WB_WARPS = 4;                   // warps (independent buckets) per CTA
-constexpr int WB_WARP_BYTES = WB_CAP * 12 + (2 * WB_RB_MAX + 8) * 4;
+constexpr int WB_WARPS = 8;                   // warps (independent bucket pipelines) per CTA
+constexpr int WB_WARP_BYTES = WB_CAP * 4 + (2 * WB_RB_MAX + 8) * 4 + WB_CAP * 2;   // scol, cnt, start, sidx
 constexpr int BK_THREADS = 256;
 constexpr int BK_EPT = 12;                    // entries per thread
 constexpr int BK_CAP = BK_THREADS * BK_EPT;   // 3072 entries staged per bucket
@@ -275,8 +275,8 @@ __device__ void thread_fix_row(int r, csi *ci, double *cx, int len,
 // otherwise the whole CTA).  Normalised bitonic network: every comparator moves the
 // smaller key to the lower index, so virtual +inf padding above `len` never moves
 // and any length works.  Works on shared or global memory.
-template <int G, bool VALUES>
-__device__ void group_sort_row(csi *ci, double *cx, int len, int tid)
+template <int G, bool VALUES, class V = double>
+__device__ void group_sort_row(csi *ci, V *cx, int len, int tid)
 {
     int P = 2;
     while (P < len) P <<= 1;
@@ -289,7 +289,7 @@ __device__ void group_sort_row(csi *ci, double *cx, int len, int tid)
                     const int a = ci[lo], b = ci[hi];
                     if (a > b) {
                         ci[lo] = b; ci[hi] = a;
-                        if (VALUES) { const double xa = cx[lo]; cx[lo] = cx[hi]; cx[hi] = xa; }
+                        if (VALUES) { const V xa = cx[lo]; cx[lo] = cx[hi]; cx[hi] = xa; }
                     }
                 }
             }
@@ -437,98 +437,153 @@ k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, c
 // ---- one WARP per bucket, staging in the warp's slice of shared memory ---------------------
 // Buckets are small (<= WB_CAP entries, <= WB_RB_MAX rows) so that a single warp can count,
 // scan, scatter and order one bucket with __syncwarp only: the warps of an SM run as many
-// independent pipelines and hide each other's global-memory latency.
+// independent pipelines.  Each warp walks its own sequence of buckets and has the row fields
+// of the NEXT bucket in flight while it works on the current one.  Only (column, source slot)
+// pairs are staged; values are gathered from the bucket (L1/L2-resident) on output.
 template <bool VALUES>
-__global__ void __launch_bounds__(WB_WARPS * 32)
+__global__ void __launch_bounds__(WB_WARPS * 32, 4)
 k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
                    const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
-                   csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+                   csi *__restrict__ Cp, csi *Ci, double *Cx)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned char *mine = smem + wid * WB_WARP_BYTES;
-    double *sval = reinterpret_cast<double *>(mine);
-    int *scol = reinterpret_cast<int *>(mine + WB_CAP * 8);
+    int *scol = reinterpret_cast<int *>(mine);
     int *cnt = scol + WB_CAP;                      // WB_RB_MAX
     int *start = cnt + WB_RB_MAX;                  // WB_RB_MAX + 1
-    const int b = blockIdx.x * WB_WARPS + wid;
-    if (b >= nbuckets) return;
+    unsigned short *sidx = reinterpret_cast<unsigned short *>(start + WB_RB_MAX + 8);
+    const int nwarps = gridDim.x * WB_WARPS;
     const int rb = 1 << log_rb;
-    const int R0 = b << log_rb;
-    const int nrows = min(rb, m - R0);
-    const int base = bstart[b];
-    const int nb = bstart[b + 1] - base;
-    if (nb > WB_CAP) return;                       // k_bucket_big's job
+    const Entry *inter = reinterpret_cast<const Entry *>(inter_);
+    const EntryP *interp = reinterpret_cast<const EntryP *>(inter_);
 
-    for (int k = lane; k < WB_RB_MAX; k += 32) cnt[k] = 0;
-    __syncwarp();
-    const Entry *inter = reinterpret_cast<const Entry *>(inter_) + base;
-    const EntryP *interp = reinterpret_cast<const EntryP *>(inter_) + base;
-    int rank[WB_EPT];
+    int b = blockIdx.x * WB_WARPS + wid;
+    if (b >= nbuckets) return;
+    // prologue: bounds and row fields of the first bucket
+    int base = bstart[b], nb = bstart[b + 1] - base;
+    int rows[WB_EPT];
 #pragma unroll
     for (int k = 0; k < WB_EPT; k++) {
         const int e = lane + k * 32;
-        rank[k] = 0;
-        if (e < nb) rank[k] = atomicAdd(&cnt[(VALUES ? inter[e].row : interp[e].row) - R0], 1);
+        rows[k] = (e < nb && nb <= WB_CAP) ? (VALUES ? inter[base + e].row : interp[base + e].row) : 0;
     }
-    __syncwarp();
-    {   // exclusive scan of cnt[0..WB_RB_MAX) -> start[0..WB_RB_MAX]; 4 consecutive rows per lane
-        constexpr int PER = WB_RB_MAX / 32;
-        int v[PER], s = 0;
+    while (b < nbuckets) {
+        const int R0 = b << log_rb;
+        const int nrows = min(rb, m - R0);
+        const int bn = b + nwarps;                 // next bucket of this warp
+        int nbase = 0, nnb = 0;
+        if (bn < nbuckets) { nbase = bstart[bn]; nnb = bstart[bn + 1] - nbase; }
+
+        if (nb <= WB_CAP) {                        // larger buckets are k_bucket_big's job
+            for (int k = lane; k < WB_RB_MAX; k += 32) cnt[k] = 0;
+            __syncwarp();
+            int slot[WB_EPT];                      // (local row << 16) | rank inside the row
 #pragma unroll
-        for (int k = 0; k < PER; k++) { v[k] = cnt[lane * PER + k]; s += v[k]; }
-        int inc = s;
+            for (int k = 0; k < WB_EPT; k++) {
+                const int rl = rows[k] - R0;
+                slot[k] = (rl << 16) | ((lane + k * 32 < nb) ? atomicAdd(&cnt[rl], 1) : 0);
+            }
+            // the next bucket's row fields go in flight now
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        int e = inc - s;
+            for (int k = 0; k < WB_EPT; k++) {
+                const int e = lane + k * 32;
+                rows[k] = (e < nnb && nnb <= WB_CAP) ? (VALUES ? inter[nbase + e].row : interp[nbase + e].row) : 0;
+            }
+            __syncwarp();
+            {   // exclusive scan of cnt[0..WB_RB_MAX) -> start[0..WB_RB_MAX]; 4 consecutive rows per lane
+                constexpr int PER = WB_RB_MAX / 32;
+                int v[PER], sum = 0;
 #pragma unroll
-        for (int k = 0; k < PER; k++) { start[lane * PER + k] = e; e += v[k]; }
-        if (lane == 31) start[WB_RB_MAX] = e;
-    }
-    __syncwarp();
+                for (int k = 0; k < PER; k++) { v[k] = cnt[lane * PER + k]; sum += v[k]; }
+                int inc = sum;
 #pragma unroll
-    for (int k = 0; k < WB_EPT; k++) {
-        const int e = lane + k * 32;
-        if (e < nb) {
-            if (VALUES) {
-                const Entry en = inter[e];
-                const int pos = start[en.row - R0] + rank[k];
-                scol[pos] = en.col;
-                sval[pos] = en.val;
-            } else {
-                const EntryP en = interp[e];
-                scol[start[en.row - R0] + rank[k]] = en.col;
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                int e = inc - sum;
+#pragma unroll
+                for (int k = 0; k < PER; k++) { start[lane * PER + k] = e; e += v[k]; }
+                if (lane == 31) start[WB_RB_MAX] = e;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < WB_EPT; k++) {
+                const int e = lane + k * 32;
+                if (e < nb) {
+                    const int pos = start[slot[k] >> 16] + (slot[k] & 0xffff);
+                    scol[pos] = VALUES ? inter[base + e].col : interp[base + e].col;
+                    sidx[pos] = (unsigned short)e;
+                }
+            }
+            __syncwarp();
+            // source order inside every row: insertion sort of (column, slot) pairs
+            bool any_long = false, any_tie = false;
+            for (int r = lane; r < nrows; r += 32) {
+                const int s0 = start[r], len = start[r + 1] - s0;
+                if (len > FIX_SHORT) { any_long = true; continue; }
+                int *ci = scol + s0;
+                unsigned short *ix = sidx + s0;
+                for (int a = 1; a < len; a++) {
+                    const int kj = ci[a];
+                    const unsigned short kv = ix[a];
+                    int c = a - 1;
+                    while (c >= 0 && ci[c] > kj) { ci[c + 1] = ci[c]; ix[c + 1] = ix[c]; c--; }
+                    ci[c + 1] = kj; ix[c + 1] = kv;
+                    any_tie |= c >= 0 && ci[c] == kj;
+                }
+            }
+            __syncwarp();
+            if (__any_sync(0xffffffffu, any_long)) {
+                for (int r = 0; r < nrows; r++) {
+                    const int s0 = start[r], len = start[r + 1] - s0;
+                    if (len > FIX_SHORT) {
+                        group_sort_row<32, true, unsigned short>(scol + s0, sidx + s0, len, lane);
+                        for (int t = lane; t + 1 < len; t += 32) any_tie |= scol[s0 + t] == scol[s0 + t + 1];
+                    }
+                }
+                __syncwarp();
+            }
+            for (int r = lane; r < nrows; r += 32) Cp[R0 + r] = base + start[r];
+            if (b == nbuckets - 1 && lane == 0) Cp[m] = base + nb;
+            for (int t = lane; t < nb; t += 32) {
+                Ci[base + t] = scol[t];
+                if (VALUES) Cx[base + t] = inter[base + sidx[t]].val;
+            }
+            if (VALUES && __any_sync(0xffffffffu, any_tie)) {
+                // duplicates of one (i,j) pair: their values go out in A's storage order
+                __syncwarp();
+                for (int r = lane; r < nrows; r += 32) {
+                    const int s0 = start[r], len = start[r + 1] - s0;
+                    for (int k = 0; k + 1 < len;) {
+                        int g = 1;
+                        while (k + g < len && scol[s0 + k + g] == scol[s0 + k]) g++;
+                        if (g > 1) fix_tied_group(Ap, Ai, Ax, R0 + r, scol[s0 + k], Cx + base + s0 + k, g);
+                        k += g;
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int k = 0; k < WB_EPT; k++) {
+                const int e = lane + k * 32;
+                rows[k] = (e < nnb && nnb <= WB_CAP) ? (VALUES ? inter[nbase + e].row : interp[nbase + e].row) : 0;
             }
         }
-    }
-    __syncwarp();
-    bool any_long = false;
-    for (int rl = lane; rl < nrows; rl += 32) {
-        const int s = start[rl], len = start[rl + 1] - s;
-        if (len > FIX_SHORT) any_long = true;
-        else if (len > 1) thread_fix_row<VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax);
-    }
-    __syncwarp();
-    if (__any_sync(0xffffffffu, any_long)) {
-        for (int rl = 0; rl < nrows; rl++) {
-            const int s = start[rl], len = start[rl + 1] - s;
-            if (len > FIX_SHORT)
-                group_fix_row<32, VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax, lane, nullptr);
-        }
-        __syncwarp();
-    }
-    for (int rl = lane; rl < nrows; rl += 32) Cp[R0 + rl] = base + start[rl];
-    if (b == nbuckets - 1 && lane == 0) Cp[m] = base + nb;
-    for (int t = lane; t < nb; t += 32) {
-        Ci[base + t] = scol[t];
-        if (VALUES) Cx[base + t] = sval[t];
+        b = bn; base = nbase; nb = nnb;
     }
 }
 
 // ---- buckets that do not fit shared memory: staging in global memory ---------------------
+__global__ void k_find_big(int nbuckets, const int *__restrict__ bstart, int *__restrict__ list, int *__restrict__ count)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbuckets && bstart[b + 1] - bstart[b] > WB_CAP) list[atomicAdd(count, 1)] = b;
+}
+
 template <bool VALUES>
 __global__ void __launch_bounds__(BK_THREADS)
-k_bucket_big(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
+k_bucket_big(int m, int log_rb, int nbuckets, const int *__restrict__ big_list, const int *__restrict__ big_count,
+             const int *__restrict__ bstart, const void *__restrict__ inter_,
              const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
              csi *Cp, csi *Ci, double *Cx)
 {
@@ -539,10 +594,11 @@ k_bucket_big(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, co
     __shared__ int flag;
     const int tid = threadIdx.x;
     const int rb = 1 << log_rb;
-    for (int b = blockIdx.x; b < nbuckets; b += gridDim.x) {
+    const int nbig = *big_count;
+    for (int idx = blockIdx.x; idx < nbig; idx += gridDim.x) {
+        const int b = big_list[idx];
         const int base = bstart[b];
         const int nb = bstart[b + 1] - base;
-        if (nb <= WB_CAP) continue;
         const int R0 = b << log_rb;
         const int nrows = min(rb, m - R0);
         const Entry *inter = reinterpret_cast<const Entry *>(inter_) + base;
@@ -663,17 +719,23 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     TR_LAUNCHED();
     {
         constexpr int smem = WB_WARPS * WB_WARP_BYTES;
-        const int grid = ceil_div(nbuckets, WB_WARPS);
+        const int grid = min(ceil_div(nbuckets, WB_WARPS), 148 * 4);
         if (has_x) k_bucket_sort_warp<true><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
         else       k_bucket_sort_warp<false><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
         TR_LAUNCHED();
     }
     if (nnz > WB_CAP) {
+        DevBuf<int> big_list;
+        if ((st = big_list.alloc((size_t)nbuckets + 1)) != CSB200_OK) return fail(st);
+        int *big_count = big_list.ptr + nbuckets;
+        TR_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int), s));
+        k_find_big<<<ceil_div(nbuckets, 256), 256, 0, s>>>(nbuckets, bstart.ptr, big_list.ptr, big_count);
+        TR_LAUNCHED();
         const int grid = min(nbuckets, 148 * 2);
         TR_CUDA(cudaFuncSetAttribute(k_bucket_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
         TR_CUDA(cudaFuncSetAttribute(k_bucket_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
-        if (has_x) k_bucket_big<true><<<grid, BK_THREADS, BK_CAP * 12, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-        else       k_bucket_big<false><<<grid, BK_THREADS, BK_CAP * 12, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+        if (has_x) k_bucket_big<true><<<grid, BK_THREADS, BK_CAP * 12, s>>>(m, log_rb, nbuckets, big_list.ptr, big_count, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+        else       k_bucket_big<false><<<grid, BK_THREADS, BK_CAP * 12, s>>>(m, log_rb, nbuckets, big_list.ptr, big_count, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
         TR_LAUNCHED();
     }
 #undef TR_CUDA
