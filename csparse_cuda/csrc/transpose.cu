@@ -47,7 +47,8 @@ constexpr int BK_EPT = 12;                    // entries per thread
 constexpr int BK_CAP = BK_THREADS * BK_EPT;   // 3072 entries staged per bucket
 constexpr int BK_RB_MAX = 1024;               // rows per bucket (power of two)
 constexpr int BK_SMEM = BK_CAP * 12 + 2 * (BK_RB_MAX + 1) * 4 + 64;
-constexpr int FIX_SHORT = 32;                 // rows up to this length: one thread
+constexpr int FIX_SHORT = 32;                 // rows up to this length: one thread (global-memory path)
+constexpr int FIX_THREAD = 8;                 // staged rows up to this length: one thread; up to 32: warp rank sort
 constexpr int BIG_WROW = BK_CAP / (BK_THREADS / 32);   // 384: longest row a warp stages in its slice
 
 struct __align__(16) Entry { int row; int col; double val; };
@@ -329,6 +330,41 @@ __device__ bool group_fix_row(int r, csi *ci, double *cx, int len,
     return true;
 }
 
+// One warp sorts a row of 9..32 entries by counting: every lane ranks its own entry
+// against the others (shuffles only), then all entries move at once.  Stable.
+template <bool HAS_V, class V>
+__device__ __forceinline__ bool warp_rank_sort(csi *ci, V *cv, int len, int lane)
+{
+    const int c = lane < len ? ci[lane] : INT_MAX;
+    V v = V();
+    if (HAS_V && lane < len) v = cv[lane];
+    int rank = 0;
+    bool tie = false;
+    for (int u = 0; u < len; u++) {
+        const int cu = __shfl_sync(0xffffffffu, c, u);
+        rank += (cu < c) || (cu == c && u < lane);
+        tie |= cu == c && u != lane;
+    }
+    __syncwarp();
+    if (lane < len) { ci[rank] = c; if (HAS_V) cv[rank] = v; }
+    __syncwarp();
+    return __any_sync(0xffffffffu, tie && lane < len);
+}
+
+// values of tied (duplicate) groups of a sorted row, re-read from A in storage order
+__device__ __forceinline__ void warp_fix_ties(int r, const csi *ci, double *cx, int len,
+                                              const csi *Ap, const csi *Ai, const double *Ax, int lane)
+{
+    for (int t = lane; t + 1 < len; t += 32) {
+        if (ci[t] == ci[t + 1] && (t == 0 || ci[t - 1] != ci[t])) {
+            int g = 2;
+            while (t + g < len && ci[t + g] == ci[t]) g++;
+            fix_tied_group(Ap, Ai, Ax, r, ci[t], cx + t, g);
+        }
+    }
+    __syncwarp();
+}
+
 // exclusive scan of cnt[0..n) (n <= BK_RB_MAX) into start[0..n], by the whole CTA
 __device__ void block_scan_rows(const int *cnt, int *start, int n, int *warp_tot)
 {
@@ -410,18 +446,24 @@ k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, c
         }
     }
     __syncthreads();
-    // source order inside every row: short rows by one thread, long rows by a warp
+    // source order inside every row: <= 8 entries by one thread, <= 32 by a warp's rank sort,
+    // longer rows by a warp's bitonic network
     bool any_long = false;
     for (int rl = tid; rl < nrows; rl += BK_THREADS) {
         const int s = rowstart[rl], len = rowstart[rl + 1] - s;
-        if (len > FIX_SHORT) any_long = true;
+        if (len > FIX_THREAD) any_long = true;
         else if (len > 1) thread_fix_row<VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax);
     }
     if (__syncthreads_or(any_long)) {
+        const int lane = tid & 31;
         for (int rl = tid >> 5; rl < nrows; rl += BK_THREADS / 32) {
             const int s = rowstart[rl], len = rowstart[rl + 1] - s;
-            if (len > FIX_SHORT)
-                group_fix_row<32, VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax, tid & 31, nullptr);
+            if (len > FIX_SHORT) {
+                group_fix_row<32, VALUES>(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax, lane, nullptr);
+            } else if (len > FIX_THREAD) {
+                if (warp_rank_sort<VALUES, double>(scol + s, sval + s, len, lane) && VALUES)
+                    warp_fix_ties(R0 + rl, scol + s, sval + s, len, Ap, Ai, Ax, lane);
+            }
         }
         __syncthreads();
     }
@@ -519,7 +561,7 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
             bool any_long = false, any_tie = false;
             for (int r = lane; r < nrows; r += 32) {
                 const int s0 = start[r], len = start[r + 1] - s0;
-                if (len > FIX_SHORT) { any_long = true; continue; }
+                if (len > FIX_THREAD) { any_long = true; continue; }
                 int *ci = scol + s0;
                 unsigned short *ix = sidx + s0;
                 for (int a = 1; a < len; a++) {
@@ -538,6 +580,8 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
                     if (len > FIX_SHORT) {
                         group_sort_row<32, true, unsigned short>(scol + s0, sidx + s0, len, lane);
                         for (int t = lane; t + 1 < len; t += 32) any_tie |= scol[s0 + t] == scol[s0 + t + 1];
+                    } else if (len > FIX_THREAD) {
+                        any_tie |= warp_rank_sort<true, unsigned short>(scol + s0, sidx + s0, len, lane);
                     }
                 }
                 __syncwarp();
@@ -574,10 +618,11 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
 }
 
 // ---- buckets that do not fit shared memory: staging in global memory ---------------------
-__global__ void k_find_big(int nbuckets, const int *__restrict__ bstart, int *__restrict__ list, int *__restrict__ count)
+__global__ void k_find_big(int nbuckets, const int *__restrict__ bstart, int cap, int *__restrict__ list,
+                           int *__restrict__ count)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nbuckets && bstart[b + 1] - bstart[b] > WB_CAP) list[atomicAdd(count, 1)] = b;
+    if (b < nbuckets && bstart[b + 1] - bstart[b] > cap) list[atomicAdd(count, 1)] = b;
 }
 
 template <bool VALUES>
@@ -693,8 +738,11 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
 
     // rows per bucket: the largest power of two whose average bucket fills <= 85 % of the staging area
     const double avg = (double)nnz / m;
+    // short rows: one warp per small bucket; longer rows: one CTA per larger bucket
+    const bool warp_path = avg <= 8.0;
+    const int bcap = warp_path ? WB_CAP : BK_CAP;
     int log_rb = 2;
-    while (log_rb < 7 && (double)(2 << log_rb) * avg <= 0.85 * WB_CAP) log_rb++;
+    while (log_rb < (warp_path ? 7 : 10) && (double)(2 << log_rb) * avg <= 0.85 * bcap) log_rb++;
     const int nbuckets = (int)(((long long)m + (1 << log_rb) - 1) >> log_rb);
     const int ntiles = ceil_div(nnz, PT_TILE);
 
@@ -717,19 +765,25 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     if (has_x) k_partition<true><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
     else       k_partition<false><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
     TR_LAUNCHED();
-    {
+    if (warp_path) {
         constexpr int smem = WB_WARPS * WB_WARP_BYTES;
         const int grid = min(ceil_div(nbuckets, WB_WARPS), 148 * 4);
         if (has_x) k_bucket_sort_warp<true><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
         else       k_bucket_sort_warp<false><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
         TR_LAUNCHED();
+    } else {
+        TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+        TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+        if (has_x) k_bucket_sort<true><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+        else       k_bucket_sort<false><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+        TR_LAUNCHED();
     }
-    if (nnz > WB_CAP) {
+    if (nnz > bcap) {
         DevBuf<int> big_list;
         if ((st = big_list.alloc((size_t)nbuckets + 1)) != CSB200_OK) return fail(st);
         int *big_count = big_list.ptr + nbuckets;
         TR_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int), s));
-        k_find_big<<<ceil_div(nbuckets, 256), 256, 0, s>>>(nbuckets, bstart.ptr, big_list.ptr, big_count);
+        k_find_big<<<ceil_div(nbuckets, 256), 256, 0, s>>>(nbuckets, bstart.ptr, bcap, big_list.ptr, big_count);
         TR_LAUNCHED();
         const int grid = min(nbuckets, 148 * 2);
         TR_CUDA(cudaFuncSetAttribute(k_bucket_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
