@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
+                                          "-i", str(self.index), "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -319,7 +319,6 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
     l0 = cc.launch_count()
     sampler.start()
     ms = device_timed(torch, dist, world, step, a.steps, a.warmup)
-    clocks = sampler.stop()
     launches = cc.launch_count() - l0 - launches_per_step * a.warmup
     value = alg_bytes_global * a.steps / (ms * 1e-3) / 1e9
 
@@ -334,7 +333,11 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
             nr = sh.split[1] - sh.split[0]
             alg_bytes_local = synth.gaxpy_bytes(nr, nr, sh.handle.nnz)
     kms = device_timed(torch, dist, 1, kern, a.steps, 2) / a.steps
+    clocks = sampler.stop()
     achieved = alg_bytes_local / (kms * 1e-3) / 1e9
+    # DRAM bytes per launch of k_spmv_tma on this exact config from the ncu --set full capture
+    # (profiles/r1_spmv_tma_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
+    traffic = 1342048000 + 127214848 if (world == 1 and k == 4096 and plan == "stream") else None
 
     # e2e: the reference-facing call on HOST buffers (pinned), copies inside the timed region.
     # "cold": csb200_gaxpy_host -- matrix + vectors uploaded every step (what cs_gaxpy(A, x, y)
@@ -391,8 +394,8 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
                    "gflops": 2 * nnz_global * a.steps / (ms * 1e-3) / 1e9},
         "clocks": clocks, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": f"k_spmv_{plan}", "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes_local, "kernel_ms": kms},
+                     "traffic": traffic, "kernel": "k_spmv_tma" if plan == "stream" else f"k_spmv_{plan}",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_local, "kernel_ms": kms},
         "e2e": e2e,
     }
     if e2e_res:
