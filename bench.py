@@ -388,7 +388,7 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"cs_gaxpy y+=A*x, 2-D 5-point Laplacian {k}x{ky_total} (n={n_global}, nnz={nnz_global}), "
-                               f"{r1 - r0} rows/GPU, row-block sharded", "kernel": f"k_spmv_{plan}",
+                               f"{r1 - r0} rows/GPU, row-block sharded", "kernel": "k_spmv_tma" if plan == "stream" else f"k_spmv_{plan}",
                    "exchange": mode, "exchange_bytes_per_rank_step": exch,
                    "l2": "inputs (1.0 GB matrix per GPU) exceed the 126 MB L2; no flush needed",
                    "gflops": 2 * nnz_global * a.steps / (ms * 1e-3) / 1e9},
