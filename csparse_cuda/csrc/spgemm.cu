@@ -78,25 +78,64 @@ __global__ void k_bin(int n, const int *__restrict__ size, int cap, int t0, int 
     }
 }
 
+// ---- warp-private open-addressing insert/lookup without atomics ---------------------
+// One warp owns the table, so a racing plain store + read-back replaces atomicCAS
+// (ATOMS costs ~2 cycles per lane, a conflict-free LDS ~1 cycle per warp): every
+// lane that still looks for row i reads keys[h]; a hit ends its search; lanes that
+// saw EMPTY all store their row, the warp synchronises, and whoever reads its own
+// row back owns the slot -- the losers (distinct rows, same slot) move on.  Rows of
+// the lanes with want == true must be pairwise distinct.  Returns the slot.
+__device__ __forceinline__ int warp_find_or_insert(int *keys, int hmask, int i, bool want,
+                                                   unsigned h, bool &isnew)
+{
+    bool pend = want;
+    isnew = false;
+    while (true) {
+        int k = EMPTY - 1;
+        if (pend) k = keys[h];
+        if (k == i) pend = false;
+        const bool tryins = pend && k == EMPTY;
+        if (__any_sync(0xffffffffu, tryins)) {
+            if (tryins) keys[h] = i;
+            __syncwarp();
+            if (tryins && keys[h] == i) { isnew = true; pend = false; }
+        }
+        if (!__any_sync(0xffffffffu, pend)) break;
+        if (pend) h = (h + 1) & hmask;
+    }
+    return (int)h;
+}
+
 // ---- symbolic, one warp per column, hash set in shared memory ---------------------
-template <int LOGH, int WARPS>
+// Shared memory per warp: keys[H] and slots[CAP] (the slots this column filled, so
+// the table is emptied by undoing cnt entries instead of clearing H).  OPTIMISTIC:
+// the column's bound ub exceeds CAP but its true size usually does not; a column
+// that does outgrow CAP is undone and appended to ovf_list for the next tier.
+template <int LOGH, int CAP, int WARPS, bool OPTIMISTIC, bool CANON>
 __global__ void __launch_bounds__(WARPS * 32)
-k_sym_warp(const int *__restrict__ list, int ncols,
+k_sym_warp(const int *__restrict__ list, const int *__restrict__ ncols_dev, int ncols_host,
            const csi *__restrict__ Ap, const csi *__restrict__ Ai,
-           const csi *__restrict__ Bp, const csi *__restrict__ Bi, int *__restrict__ cnt_out)
+           const csi *__restrict__ Bp, const csi *__restrict__ Bi, int *__restrict__ cnt_out,
+           int *__restrict__ ovf_list, int *ovf_count)
 {
     constexpr int H = 1 << LOGH;
+    static_assert(H >= CAP + 64 && H <= 65536, "table must never fill");
+    constexpr int PER_WARP = H * 4 + CAP * 2;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int *tab = reinterpret_cast<int *>(sm_raw) + wid * H;
+    int *keys = reinterpret_cast<int *>(sm_raw + (size_t)wid * PER_WARP);
+    unsigned short *slots = reinterpret_cast<unsigned short *>(keys + H);
+    const unsigned lt = lanemask_lt();
+    const int ncols = ncols_dev ? *ncols_dev : ncols_host;
     const int nwarps = gridDim.x * WARPS;
+    for (int s = lane; s < H; s += 32) keys[s] = EMPTY;
+    __syncwarp();
     for (int idx = blockIdx.x * WARPS + wid; idx < ncols; idx += nwarps) {
         const int j = list[idx];
-        for (int s = lane; s < H; s += 32) tab[s] = EMPTY;
-        __syncwarp();
-        int mine = 0;
+        int cnt = 0;                                   // warp-uniform
+        bool ovf = false;
         const int pb_end = Bp[j + 1];
-        for (int pb0 = Bp[j]; pb0 < pb_end; pb0 += 32) {
+        for (int pb0 = Bp[j]; pb0 < pb_end && !ovf; pb0 += 32) {
             const int my_pb = pb0 + lane;
             int my_ab = 0, my_ae = 0;
             if (my_pb < pb_end) {
@@ -105,24 +144,41 @@ k_sym_warp(const int *__restrict__ list, int ncols,
                 my_ae = Ap[k + 1];
             }
             const int nb = min(32, pb_end - pb0);
-            for (int s = 0; s < nb; s++) {
+            for (int s = 0; s < nb && !ovf; s++) {
                 const int ab = __shfl_sync(0xffffffffu, my_ab, s);
                 const int ae = __shfl_sync(0xffffffffu, my_ae, s);
-                for (int pa = ab + lane; pa < ae; pa += 32) {
-                    const int i = Ai[pa];
-                    unsigned h = hash_row(i, LOGH);
-                    while (true) {
-                        const int old = atomicCAS(&tab[h], EMPTY, i);
-                        if (old == EMPTY) { mine++; break; }
-                        if (old == i) break;
-                        h = (h + 1) & (H - 1);
+                for (int pa0 = ab; pa0 < ae; pa0 += 32) {
+                    const int pa = pa0 + lane;
+                    const bool active = pa < ae;
+                    const int i = active ? Ai[pa] : 0;
+                    // duplicates inside a column of A: one lane per distinct row inserts
+                    bool leader = active;
+                    if (!CANON) {
+                        const unsigned act = __ballot_sync(0xffffffffu, active);
+                        if (active) leader = (__ffs(__match_any_sync(act, i)) - 1) == lane;
+                    }
+                    bool isnew;
+                    const int slot = warp_find_or_insert(keys, H - 1, i, leader, hash_row(i, LOGH), isnew);
+                    const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
+                    if (newmask) {
+                        const int pos = cnt + __popc(newmask & lt);
+                        if (isnew) {
+                            if (pos < CAP) slots[pos] = (unsigned short)slot;
+                            else keys[slot] = EMPTY;          // beyond the undo list: undo now
+                        }
+                        cnt += __popc(newmask);
+                        __syncwarp();
+                        if (cnt > CAP) { ovf = true; break; }
                     }
                 }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-        if (lane == 0) cnt_out[j] = mine;
+        const int filled = min(cnt, CAP);
+        for (int t = lane; t < filled; t += 32) keys[slots[t]] = EMPTY;
+        if (lane == 0) {
+            if (!ovf) cnt_out[j] = cnt;
+            else if (OPTIMISTIC) ovf_list[atomicAdd(ovf_count, 1)] = j;
+        }
         __syncwarp();
     }
 }
@@ -160,8 +216,9 @@ k_sym_dense(const int *__restrict__ list, int ncols, int m,
 }
 
 // ---- numeric, one warp per column ---------------------------------------------------
-// Shared memory per warp: keys[H] (row or EMPTY), poss[H] (discovery position of
-// that row), rowlist[CAP], vals[CAP].  CANON: every column of A has distinct rows.
+// Shared memory per warp: vals[H] (accumulator of the row held by that slot), keys[H]
+// (row or EMPTY), order[CAP] (slot of the t-th discovered row).  The table is emptied
+// while the column is emitted.  CANON: every column of A has distinct rows.
 template <int LOGH, int CAP, int WARPS, bool VALUES, bool CANON>
 __global__ void __launch_bounds__(WARPS * 32)
 k_num_warp(const int *__restrict__ list, int ncols,
@@ -170,21 +227,21 @@ k_num_warp(const int *__restrict__ list, int ncols,
            const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
 {
     constexpr int H = 1 << LOGH;
-    constexpr int PER_WARP = 2 * H * 4 + CAP * 4 + CAP * 8;      // bytes
+    static_assert(H >= 2 * CAP && H <= 65536, "load factor <= 1/2, slots fit 16 bits");
+    constexpr int PER_WARP = H * 8 + H * 4 + CAP * 2;      // bytes
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned char *base = sm_raw + (size_t)wid * PER_WARP;
-    double *vals = reinterpret_cast<double *>(base);                       // CAP doubles first (alignment)
-    int *keys = reinterpret_cast<int *>(base + CAP * 8);
-    int *poss = keys + H;
-    int *rowlist = poss + H;
+    double *vals = reinterpret_cast<double *>(base);                       // doubles first (alignment)
+    int *keys = reinterpret_cast<int *>(base + H * 8);
+    unsigned short *order = reinterpret_cast<unsigned short *>(keys + H);
     const unsigned lt = lanemask_lt();
     const int nwarps = gridDim.x * WARPS;
 
+    for (int s = lane; s < H; s += 32) keys[s] = EMPTY;
+    __syncwarp();
     for (int idx = blockIdx.x * WARPS + wid; idx < ncols; idx += nwarps) {
         const int j = list[idx];
-        for (int s = lane; s < H; s += 32) keys[s] = EMPTY;
-        __syncwarp();
         int cnt = 0;                                   // warp-uniform: rows discovered so far
         const int pb_end = Bp[j + 1];
         for (int pb0 = Bp[j]; pb0 < pb_end; pb0 += 32) {
@@ -216,47 +273,28 @@ k_num_warp(const int *__restrict__ list, int ncols,
                     if (!CANON) {
                         const unsigned act = __ballot_sync(0xffffffffu, active);
                         if (active) {
-                            const unsigned peers = __match_any_sync(act, i);
-                            lead_lane = __ffs(peers) - 1;
+                            lead_lane = __ffs(__match_any_sync(act, i)) - 1;
                             leader = lead_lane == lane;
                         }
                     }
-                    int slot = 0;
-                    bool isnew = false;
-                    if (leader) {
-                        unsigned h = hash_row(i, LOGH);
-                        while (true) {
-                            const int old = atomicCAS(&keys[h], EMPTY, i);
-                            if (old == EMPTY) { isnew = true; break; }
-                            if (old == i) break;
-                            h = (h + 1) & (H - 1);
-                        }
-                        slot = (int)h;
-                    }
+                    bool isnew;
+                    int slot = warp_find_or_insert(keys, H - 1, i, leader, hash_row(i, LOGH), isnew);
                     const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
                     if (isnew) {
-                        const int pos = cnt + __popc(newmask & lt);
-                        poss[slot] = pos;
-                        rowlist[pos] = i;
-                        if (VALUES) vals[pos] = prod;              // first touch assigns (csparse.py:1986)
+                        order[cnt + __popc(newmask & lt)] = (unsigned short)slot;
+                        if (VALUES) vals[slot] = prod;             // first touch assigns (csparse.py:1986)
                     }
                     cnt += __popc(newmask);
-                    __syncwarp();
                     if (VALUES) {
                         if (CANON) {
-                            if (active && !isnew) {
-                                const int pos = poss[slot];
-                                vals[pos] = __dadd_rn(vals[pos], prod);   // (csparse.py:1988)
-                            }
+                            if (active && !isnew) vals[slot] = __dadd_rn(vals[slot], prod);   // (csparse.py:1988)
                         } else {
+                            __syncwarp();
                             slot = __shfl_sync(0xffffffffu, slot, lead_lane);
                             unsigned pend = __ballot_sync(0xffffffffu, active && !isnew);
                             while (pend) {                          // storage (= lane) order
                                 const int l = __ffs(pend) - 1;
-                                if (lane == l) {
-                                    const int pos = poss[slot];
-                                    vals[pos] = __dadd_rn(vals[pos], prod);
-                                }
+                                if (lane == l) vals[slot] = __dadd_rn(vals[slot], prod);
                                 pend &= pend - 1;
                                 __syncwarp();
                             }
@@ -268,8 +306,10 @@ k_num_warp(const int *__restrict__ list, int ncols,
         }
         const int out = Cp[j];
         for (int t = lane; t < cnt; t += 32) {
-            Ci[out + t] = rowlist[t];
-            if (VALUES) Cx[out + t] = vals[t];
+            const int slot = order[t];
+            Ci[out + t] = keys[slot];
+            if (VALUES) Cx[out + t] = vals[slot];
+            keys[slot] = EMPTY;
         }
         __syncwarp();
     }
@@ -382,15 +422,25 @@ int mat_is_canonical(csb200_mat *A, int *out)
 }
 
 // ---- host side ---------------------------------------------------------------------------
-template <int LOGH, int WARPS>
-static int run_sym_warp(const int *list, int ncols, const csb200_mat *A, const csb200_mat *B, int *cnt)
+// ncols_dev != null: the number of listed columns is read on the device (no host round trip)
+template <int LOGH, int CAP, int WARPS, bool OPTIMISTIC>
+static int run_sym_warp(const int *list, const int *ncols_dev, int ncols, const csb200_mat *A,
+                        const csb200_mat *B, int *cnt, bool canon, int *ovf_list, int *ovf_count)
 {
-    if (ncols == 0) return CSB200_OK;
-    const size_t smem = (size_t)WARPS * (1 << LOGH) * sizeof(int);
-    auto kern = k_sym_warp<LOGH, WARPS>;
-    CSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * 16);
-    kern<<<grid, WARPS * 32, smem, stream()>>>(list, ncols, A->p, A->i, B->p, B->i, cnt);
+    if (!ncols_dev && ncols == 0) return CSB200_OK;
+    const size_t smem = (size_t)WARPS * ((size_t)(1 << LOGH) * 4 + CAP * 2);
+    const int resident = (int)min((size_t)16, (size_t)(220 * 1024) / smem);
+    const int grid = ncols_dev ? 148 * resident
+                               : (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * resident);
+#define SYM_LAUNCH(K)                                                                             \
+    do {                                                                                          \
+        auto kern = k_sym_warp<LOGH, CAP, WARPS, OPTIMISTIC, K>;                                  \
+        CSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, WARPS * 32, smem, stream()>>>(list, ncols_dev, ncols, A->p, A->i, B->p, B->i, cnt, \
+                                                   ovf_list, ovf_count);                          \
+    } while (0)
+    if (canon) SYM_LAUNCH(true); else SYM_LAUNCH(false);
+#undef SYM_LAUNCH
     CSB_LAUNCHED();
     return CSB200_OK;
 }
@@ -400,8 +450,9 @@ static int run_num_warp(const int *list, int ncols, const csb200_mat *A, const c
                         csb200_mat *C, bool values, bool canon)
 {
     if (ncols == 0) return CSB200_OK;
-    const size_t smem = (size_t)WARPS * (2 * (1 << LOGH) * 4 + CAP * 12);
-    const int grid = (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * 16);
+    const size_t smem = (size_t)WARPS * ((size_t)(1 << LOGH) * 12 + CAP * 2);
+    const int resident = (int)min((size_t)16, (size_t)(220 * 1024) / smem);
+    const int grid = (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * resident);
 #define NUM_LAUNCH(V, K)                                                                          \
     do {                                                                                          \
         auto kern = k_num_warp<LOGH, CAP, WARPS, V, K>;                                           \
@@ -453,16 +504,23 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
     if (n > 0) {
         k_ub<<<ceil_div(n, 256), 256, 0, s>>>(n, B->p, B->i, A->p, ub.ptr, flops.ptr);
         MM_LAUNCHED();
-        // symbolic classes by min(ub, m): <=256 | <=1024 | <=8192 | dense
-        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, m, 256, 1024, 8192, lists.ptr, counts.ptr);
+        // symbolic classes by min(ub, m): <=256 (cannot outgrow the small table) |
+        // <=8192 (optimistic: small table first, columns that outgrow it -> list 2) | dense
+        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, m, 256, 8192, 8192, lists.ptr, counts.ptr);
         MM_LAUNCHED();
         MM_CUDA(cudaMemcpyAsync(h_counts, counts.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
         MM_CUDA(cudaMemcpyAsync(&h_flops, flops.ptr, sizeof(h_flops), cudaMemcpyDeviceToHost, s));
         MM_CUDA(cudaStreamSynchronize(s));
         tls().last_flops = (int64_t)h_flops;
-        MM_TRY((run_sym_warp<9, 8>(lists.ptr, h_counts[0], A, B, cnt.ptr)));
-        MM_TRY((run_sym_warp<11, 8>(lists.ptr + ncap, h_counts[1], A, B, cnt.ptr)));
-        MM_TRY((run_sym_warp<14, 2>(lists.ptr + 2 * ncap, h_counts[2], A, B, cnt.ptr)));
+        int *ovf_list = lists.ptr + 2 * ncap, *ovf_count = counts.ptr + 2;
+        MM_TRY((run_sym_warp<9, 256, 8, false>(lists.ptr, nullptr, h_counts[0], A, B, cnt.ptr, canon != 0,
+                                               nullptr, nullptr)));
+        if (h_counts[1] > 0) {
+            MM_TRY((run_sym_warp<9, 256, 8, true>(lists.ptr + ncap, nullptr, h_counts[1], A, B, cnt.ptr,
+                                                  canon != 0, ovf_list, ovf_count)));
+            MM_TRY((run_sym_warp<14, 8192, 2, false>(ovf_list, ovf_count, 0, A, B, cnt.ptr, canon != 0,
+                                                     nullptr, nullptr)));
+        }
         if (h_counts[3] > 0) {
             const int ctas = min(DENSE_CTAS, h_counts[3]);
             MM_TRY(marks.alloc((size_t)ctas * m));
@@ -494,13 +552,14 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
         k_col_sizes<<<ceil_div(n, 256), 256, 0, s>>>(n, C->p, ub.ptr);
         MM_LAUNCHED();
         MM_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * sizeof(int), s));
-        // numeric classes by exact column size: <=128 | <=1024 | (unused) | dense
-        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, INT_MAX, 128, 1024, 1024, lists.ptr, counts.ptr);
+        // numeric classes by exact column size: <=128 | <=512 | <=2048 | dense
+        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, INT_MAX, 128, 512, 2048, lists.ptr, counts.ptr);
         MM_LAUNCHED();
         MM_CUDA(cudaMemcpyAsync(h_counts, counts.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
         MM_CUDA(cudaStreamSynchronize(s));
         MM_TRY((run_num_warp<8, 128, 8>(lists.ptr, h_counts[0], A, B, C, values, canon != 0)));
-        MM_TRY((run_num_warp<11, 1024, 4>(lists.ptr + ncap, h_counts[1], A, B, C, values, canon != 0)));
+        MM_TRY((run_num_warp<10, 512, 8>(lists.ptr + ncap, h_counts[1], A, B, C, values, canon != 0)));
+        MM_TRY((run_num_warp<12, 2048, 4>(lists.ptr + 2 * ncap, h_counts[2], A, B, C, values, canon != 0)));
         if (h_counts[3] > 0) {
             const int ctas = min(DENSE_CTAS, h_counts[3]);
             MM_TRY(marks_num.alloc((size_t)ctas * m));

@@ -28,6 +28,7 @@
 // is then sorted by j, and tied groups are re-read from the source column in
 // storage order.  Correctness never depends on how atomics were ordered.
 #include "common.cuh"
+#include <type_traits>
 
 namespace csb {
 
@@ -49,7 +50,6 @@ constexpr int BK_RB_MAX = 1024;               // rows per bucket (power of two)
 constexpr int BK_SMEM = BK_CAP * 12 + 2 * (BK_RB_MAX + 1) * 4 + 64;
 constexpr int FIX_SHORT = 32;                 // rows up to this length: one thread (global-memory path)
 constexpr int FIX_THREAD = 8;                 // staged rows up to this length: one thread; up to 32: warp rank sort
-constexpr int BIG_WROW = BK_CAP / (BK_THREADS / 32);   // 384: longest row a warp stages in its slice
 
 struct __align__(16) Entry { int row; int col; double val; };
 struct __align__(8) EntryP { int row; int col; };
@@ -617,92 +617,171 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
     }
 }
 
-// ---- buckets that do not fit shared memory: staging in global memory ---------------------
+// ---- buckets that do not fit shared memory (power-law rows) ---------------------------------
+// One CTA sorts the whole bucket by the composite key (local row, source column) with a
+// stable LSD radix sort in global memory: an odd number of passes ping-pongs between the
+// bucket's slice of the partition buffer and a scratch slice, the last pass writes Ci / Cx.
+// Cost is linear in the bucket size whatever the row lengths are (one row may hold the
+// whole bucket).  Each warp owns a contiguous segment of the bucket and a private cursor
+// per digit, so ranks need no atomics: __match_any groups the lanes of a step by digit.
 __global__ void k_find_big(int nbuckets, const int *__restrict__ bstart, int cap, int *__restrict__ list,
-                           int *__restrict__ count)
+                           int *__restrict__ soff, int *__restrict__ count_total)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nbuckets && bstart[b + 1] - bstart[b] > cap) list[atomicAdd(count, 1)] = b;
+    if (b < nbuckets) {
+        const int nb = bstart[b + 1] - bstart[b];
+        if (nb > cap) {
+            const int k = atomicAdd(&count_total[0], 1);
+            list[k] = b;
+            soff[k] = atomicAdd(&count_total[1], nb);     // offset of this bucket's scratch slice
+        }
+    }
 }
 
+constexpr int BIG_THREADS = 1024;
+constexpr int BIG_WARPS = BIG_THREADS / 32;
+constexpr int BIG_UNROLL = 4;                  // 32-entry steps whose loads are in flight together
+constexpr int BIG_MAX_WIDTH = 9;               // 512 digits x 32 warps x 4 B = 64 KB of cursors
+
 template <bool VALUES>
-__global__ void __launch_bounds__(BK_THREADS)
-k_bucket_big(int m, int log_rb, int nbuckets, const int *__restrict__ big_list, const int *__restrict__ big_count,
-             const int *__restrict__ bstart, const void *__restrict__ inter_,
+__global__ void __launch_bounds__(BIG_THREADS)
+k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasses,
+             const int *__restrict__ big_list, const int *__restrict__ big_soff, int nbig,
+             const int *__restrict__ bstart, void *inter_, void *scratch_,
              const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
              csi *Cp, csi *Ci, double *Cx)
 {
-    extern __shared__ __align__(16) unsigned char stage[];     // BK_CAP * 12 bytes: row staging
+    using E = typename std::conditional<VALUES, Entry, EntryP>::type;
+    extern __shared__ __align__(16) int cursors[];             // [digit][warp]
     __shared__ int rowcnt[BK_RB_MAX + 1];
     __shared__ int rowstart[BK_RB_MAX + 1];
-    __shared__ int warp_tot[BK_THREADS / 32];
-    __shared__ int flag;
-    const int tid = threadIdx.x;
+    __shared__ int warp_tot[BIG_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt = lanemask_lt();
     const int rb = 1 << log_rb;
-    const int nbig = *big_count;
+    const int nbins = 1 << width;
+    // exclusive scan of one value per thread over the CTA
+    auto block_excl = [&](int v) {
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        __syncthreads();
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        int before = inc - v;
+        for (int w = 0; w < wid; w++) before += warp_tot[w];
+        return before;
+    };
     for (int idx = blockIdx.x; idx < nbig; idx += gridDim.x) {
         const int b = big_list[idx];
         const int base = bstart[b];
         const int nb = bstart[b + 1] - base;
         const int R0 = b << log_rb;
         const int nrows = min(rb, m - R0);
-        const Entry *inter = reinterpret_cast<const Entry *>(inter_) + base;
-        const EntryP *interp = reinterpret_cast<const EntryP *>(inter_) + base;
-        for (int k = tid; k <= rb; k += BK_THREADS) rowcnt[k] = 0;
+        E *bufA = reinterpret_cast<E *>(inter_) + base;
+        E *bufB = reinterpret_cast<E *>(scratch_) + big_soff[idx];
+        // rows -> Cp (the reference's histogram + cs_cumsum restricted to this bucket)
+        for (int k = tid; k <= rb; k += BIG_THREADS) rowcnt[k] = 0;
         __syncthreads();
-        for (int e = tid; e < nb; e += BK_THREADS)
-            atomicAdd(&rowcnt[(VALUES ? inter[e].row : interp[e].row) - R0], 1);
+        for (int e = tid; e < nb; e += BIG_THREADS) atomicAdd(&rowcnt[bufA[e].row - R0], 1);
         __syncthreads();
-        block_scan_rows(rowcnt, rowstart, nrows, warp_tot);
-        for (int rl = tid; rl < nrows; rl += BK_THREADS) Cp[R0 + rl] = base + rowstart[rl];
-        if (b == nbuckets - 1 && tid == 0) Cp[m] = base + nb;
-        for (int k = tid; k <= rb; k += BK_THREADS) rowcnt[k] = 0;      // reused as fill cursors
-        __syncthreads();
-        for (int e = tid; e < nb; e += BK_THREADS) {
-            int row, col;
-            double val = 0.0;
-            if (VALUES) { const Entry en = inter[e]; row = en.row; col = en.col; val = en.val; }
-            else        { const EntryP en = interp[e]; row = en.row; col = en.col; }
-            const int pos = base + rowstart[row - R0] + atomicAdd(&rowcnt[row - R0], 1);
-            Ci[pos] = col;
-            if (VALUES) Cx[pos] = val;
-        }
-        __syncthreads();
-        // rows: one thread (<= 32, in place), one warp (<= BIG_WROW, staged in the warp's
-        // shared-memory slice), the whole CTA (<= BK_CAP staged in shared memory, longer
-        // rows sorted in place in global memory)
-        for (int rl = tid; rl < nrows; rl += BK_THREADS) {
-            const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
-            if (len > 1 && len <= FIX_SHORT) thread_fix_row<VALUES>(R0 + rl, Ci + s, Cx + s, len, Ap, Ai, Ax);
-        }
         {
-            const int lane = tid & 31, wid = tid >> 5;
-            int *wcol = reinterpret_cast<int *>(stage + BK_CAP * 8) + wid * BIG_WROW;
-            double *wval = reinterpret_cast<double *>(stage) + wid * BIG_WROW;
-            for (int rl = wid; rl < nrows; rl += BK_THREADS / 32) {
-                const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
-                if (len <= FIX_SHORT || len > BIG_WROW) continue;
-                for (int t = lane; t < len; t += 32) { wcol[t] = Ci[s + t]; if (VALUES) wval[t] = Cx[s + t]; }
-                __syncwarp();
-                if (group_fix_row<32, VALUES>(R0 + rl, wcol, wval, len, Ap, Ai, Ax, lane, nullptr))
-                    for (int t = lane; t < len; t += 32) { Ci[s + t] = wcol[t]; if (VALUES) Cx[s + t] = wval[t]; }
-                __syncwarp();
-            }
+            const int c = tid < nrows ? rowcnt[tid] : 0;          // rb <= BK_RB_MAX == BIG_THREADS
+            const int before = block_excl(c);
+            if (tid <= nrows) rowstart[tid] = before;
+            if (tid < nrows) Cp[R0 + tid] = base + before;
         }
-        __syncthreads();
-        for (int rl = 0; rl < nrows; rl++) {
-            const int s = base + rowstart[rl], len = rowstart[rl + 1] - rowstart[rl];
-            if (len <= BIG_WROW) continue;
-            if (len <= BK_CAP) {
-                int *ccol = reinterpret_cast<int *>(stage + BK_CAP * 8);
-                double *cval = reinterpret_cast<double *>(stage);
-                for (int t = tid; t < len; t += BK_THREADS) { ccol[t] = Ci[s + t]; if (VALUES) cval[t] = Cx[s + t]; }
-                __syncthreads();
-                if (group_fix_row<BK_THREADS, VALUES>(R0 + rl, ccol, cval, len, Ap, Ai, Ax, tid, &flag))
-                    for (int t = tid; t < len; t += BK_THREADS) { Ci[s + t] = ccol[t]; if (VALUES) Cx[s + t] = cval[t]; }
-                __syncthreads();
-            } else {
-                group_fix_row<BK_THREADS, VALUES>(R0 + rl, Ci + s, Cx + s, len, Ap, Ai, Ax, tid, &flag);
+        if (b == nbuckets - 1 && tid == 0) Cp[m] = base + nb;
+
+        const int per = ((nb + BIG_WARPS - 1) / BIG_WARPS + 31) & ~31;     // segment of a warp
+        const int seg_lo = min(nb, wid * per), seg_hi = min(nb, seg_lo + per);
+        for (int pass = 0; pass < npasses; pass++) {
+            const E *src = (pass & 1) ? bufB : bufA;
+            E *dst = (pass & 1) ? bufA : bufB;
+            const bool last = pass == npasses - 1;
+            const int shift = pass * width;
+            for (int k = tid; k < nbins * BIG_WARPS; k += BIG_THREADS) cursors[k] = 0;
+            __syncthreads();
+            // digit counts per warp segment
+            for (int e0 = seg_lo; e0 < seg_hi; e0 += 32 * BIG_UNROLL) {
+                int d[BIG_UNROLL];
+#pragma unroll
+                for (int u = 0; u < BIG_UNROLL; u++) {
+                    const int e = e0 + u * 32 + lane;
+                    d[u] = -1;
+                    if (e < seg_hi) {
+                        const EntryP rc = *reinterpret_cast<const EntryP *>(&src[e]);
+                        const unsigned long long key = ((unsigned long long)(rc.row - R0) << colbits) | (unsigned)rc.col;
+                        d[u] = (int)((key >> shift) & (nbins - 1));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < BIG_UNROLL; u++) {
+                    const unsigned amask = __ballot_sync(0xffffffffu, d[u] >= 0);
+                    if (d[u] >= 0) {
+                        const unsigned peers = __match_any_sync(amask, d[u]);
+                        if ((peers & lt) == 0) cursors[d[u] * BIG_WARPS + wid] += __popc(peers);
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            {   // exclusive scan of cursors in (digit, warp) order
+                const int chunk = nbins * BIG_WARPS / BIG_THREADS;     // nbins >= 32 => chunk >= 1
+                int sum = 0;
+                for (int k = 0; k < chunk; k++) sum += cursors[tid * chunk + k];
+                int before = block_excl(sum);
+                for (int k = 0; k < chunk; k++) { const int c = cursors[tid * chunk + k]; cursors[tid * chunk + k] = before; before += c; }
+            }
+            __syncthreads();
+            // stable scatter: every warp walks its segment in order
+            for (int e0 = seg_lo; e0 < seg_hi; e0 += 32 * BIG_UNROLL) {
+                E en[BIG_UNROLL];
+                int d[BIG_UNROLL];
+#pragma unroll
+                for (int u = 0; u < BIG_UNROLL; u++) {
+                    const int e = e0 + u * 32 + lane;
+                    d[u] = -1;
+                    if (e < seg_hi) {
+                        en[u] = src[e];
+                        const unsigned long long key = ((unsigned long long)(en[u].row - R0) << colbits) | (unsigned)en[u].col;
+                        d[u] = (int)((key >> shift) & (nbins - 1));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < BIG_UNROLL; u++) {
+                    const unsigned amask = __ballot_sync(0xffffffffu, d[u] >= 0);
+                    if (d[u] >= 0) {
+                        const unsigned peers = __match_any_sync(amask, d[u]);
+                        const int leader = __ffs(peers) - 1;
+                        int pos = 0;
+                        if (lane == leader) {
+                            pos = cursors[d[u] * BIG_WARPS + wid];
+                            cursors[d[u] * BIG_WARPS + wid] = pos + __popc(peers);
+                        }
+                        pos = __shfl_sync(peers, pos, leader) + __popc(peers & lt);
+                        if (!last) dst[pos] = en[u];
+                        else {
+                            Ci[base + pos] = en[u].col;
+                            if constexpr (VALUES) Cx[base + pos] = en[u].val;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        }
+        if (VALUES) {
+            // duplicates of one (i,j) pair: their values go out in A's storage order
+            for (int t = tid; t + 1 < nb; t += BIG_THREADS) {
+                const int c = Ci[base + t];
+                if (c != Ci[base + t + 1]) continue;
+                const int rl = upper_row(rowstart, 0, nrows - 1, t);
+                if (t + 1 >= rowstart[rl + 1]) continue;                      // next entry is another row's
+                if (t > rowstart[rl] && Ci[base + t - 1] == c) continue;      // not the head of its group
+                int g = 2;
+                while (t + g < rowstart[rl + 1] && Ci[base + t + g] == c) g++;
+                fix_tied_group(Ap, Ai, Ax, R0 + rl, c, Cx + base + t, g);
             }
         }
         __syncthreads();
@@ -779,18 +858,34 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
         TR_LAUNCHED();
     }
     if (nnz > bcap) {
-        DevBuf<int> big_list;
-        if ((st = big_list.alloc((size_t)nbuckets + 1)) != CSB200_OK) return fail(st);
-        int *big_count = big_list.ptr + nbuckets;
-        TR_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int), s));
-        k_find_big<<<ceil_div(nbuckets, 256), 256, 0, s>>>(nbuckets, bstart.ptr, bcap, big_list.ptr, big_count);
+        DevBuf<int> big_list, big_soff, big_ct;
+        DevBuf<unsigned char> scratch;
+        if ((st = big_list.alloc((size_t)nbuckets)) || (st = big_soff.alloc((size_t)nbuckets)) ||
+            (st = big_ct.alloc(2)))
+            return fail(st);
+        TR_CUDA(cudaMemsetAsync(big_ct.ptr, 0, 2 * sizeof(int), s));
+        k_find_big<<<ceil_div(nbuckets, 256), 256, 0, s>>>(nbuckets, bstart.ptr, bcap, big_list.ptr, big_soff.ptr, big_ct.ptr);
         TR_LAUNCHED();
-        const int grid = min(nbuckets, 148 * 2);
-        TR_CUDA(cudaFuncSetAttribute(k_bucket_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
-        TR_CUDA(cudaFuncSetAttribute(k_bucket_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_CAP * 12));
-        if (has_x) k_bucket_big<true><<<grid, BK_THREADS, BK_CAP * 12, s>>>(m, log_rb, nbuckets, big_list.ptr, big_count, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-        else       k_bucket_big<false><<<grid, BK_THREADS, BK_CAP * 12, s>>>(m, log_rb, nbuckets, big_list.ptr, big_count, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
-        TR_LAUNCHED();
+        int h_ct[2] = {0, 0};
+        TR_CUDA(cudaMemcpyAsync(h_ct, big_ct.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TR_CUDA(cudaStreamSynchronize(s));
+        if (h_ct[0] > 0) {
+            // key = (local row, source column): colbits + log_rb bits, in an odd number of passes
+            int colbits = 1;
+            while (colbits < 31 && (1LL << colbits) < (long long)n) colbits++;
+            const int bits = colbits + log_rb;
+            const int npasses = bits <= BIG_MAX_WIDTH ? 1 : bits <= 3 * BIG_MAX_WIDTH ? 3 : 5;
+            int width = (bits + npasses - 1) / npasses;
+            if (width < 5) width = 5;                    // the scan wants one cursor per thread at least
+            if ((st = scratch.alloc((size_t)h_ct[1] * (has_x ? sizeof(Entry) : sizeof(EntryP)))) != CSB200_OK) return fail(st);
+            const int smem = (int)((sizeof(int) * BIG_WARPS) << width);
+            const int grid = min(h_ct[0], 148);
+            TR_CUDA(cudaFuncSetAttribute(k_bucket_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            TR_CUDA(cudaFuncSetAttribute(k_bucket_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            if (has_x) k_bucket_big<true><<<grid, BIG_THREADS, smem, s>>>(m, log_rb, nbuckets, colbits, width, npasses, big_list.ptr, big_soff.ptr, h_ct[0], bstart.ptr, inter.ptr, scratch.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+            else       k_bucket_big<false><<<grid, BIG_THREADS, smem, s>>>(m, log_rb, nbuckets, colbits, width, npasses, big_list.ptr, big_soff.ptr, h_ct[0], bstart.ptr, inter.ptr, scratch.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+            TR_LAUNCHED();
+        }
     }
 #undef TR_CUDA
 #undef TR_LAUNCHED
