@@ -179,6 +179,11 @@ class DeviceMatrix(object):
         _lib.check(_lib.lib().csb200_gaxpy_force_plan(self._h, code))
 
 
+def force_transpose_path(path: Optional[str]):
+    """Tests / benchmarks: None or "auto" = automatic choice, "radix" = always the stable radix sort."""
+    _lib.check(_lib.lib().csb200_transpose_force_path({None: 0, "auto": 0, "radix": 1}[path]))
+
+
 def upload(A, validate: bool = True) -> DeviceMatrix:
     """Copy a CSC ``cs`` (lists, array.array or numpy) into HBM."""
     if isinstance(A, DeviceMatrix):

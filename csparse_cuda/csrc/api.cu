@@ -56,6 +56,7 @@ int ensure_device()
 
 // implemented in transpose.cu / spmv.cu / spgemm.cu
 int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out);
+extern int g_force_radix;
 int spmv_run(csb200_mat *AT, const double *d_x, double *d_y);
 int spmv_build_plan(csb200_mat *AT);
 void spmv_plan_free(SpmvPlan *pl);
@@ -343,6 +344,13 @@ int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
     if (!A || !C) return set_error(CSB200_ERR_ARG, "cs_transpose: null argument");
     *C = nullptr;
     return transpose_impl(A, values != 0, C);
+}
+
+int csb200_transpose_force_path(int path)
+{
+    if (path < 0 || path > 1) return set_error(CSB200_ERR_ARG, "bad transpose path");
+    g_force_radix = path;
+    return CSB200_OK;
 }
 
 int csb200_transpose_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,

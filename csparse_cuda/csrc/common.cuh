@@ -87,6 +87,11 @@ constexpr size_t MAT_PAD = 8;
 // scan.cu : p[0..n] = exclusive scan(c), c[i] <- p[i]; d_total (int64) and
 //           d_max (max element, may be null) are device scalars.
 int launch_excl_scan(csi *d_p, csi *d_c, csi n, long long *d_total, int *d_max);
+// radix.cu : stable LSD radix sort of (key, a, v) triples by key in [0, nkeys) and the
+//            column pointers Cp[0..nkeys] of the result; a == nullptr derives the int payload
+//            from Ap as "the column holding this position"; v == nullptr sorts pattern only.
+int stable_sort_by_key(long long nnz, int nkeys, const int *key, const int *a, const csi *Ap, int ncols,
+                       const double *v, csi *Cp, csi *a_out, double *v_out);
 
 }  // namespace csb
 

@@ -1,0 +1,272 @@
+// radix.cu -- stable LSD radix sort of (key, int payload, double payload) triples by an
+// integer key in [0, nkeys), plus the column-pointer array of the result.
+//
+// This is the reference's stable counting-sort scatter (cs_transpose, csparse.py:2305-2314;
+// cs_compress, csparse.py:663-671) for inputs whose key distribution defeats the two-level
+// bucket sort of transpose.cu (power-law rows) or whose entries are in no particular order
+// (triplets).  Stability gives the reference's order inside every output column -- ascending
+// source position -- by construction, so nothing has to be repaired afterwards.
+//
+//   k_rs_hist    digit histograms of every pass in one read of the keys
+//   k_rs_starts  256-entry exclusive scans -> first output slot of every digit
+//   k_rs_pass    one 8-bit pass, "onesweep" style: a tile of 4096 entries is ranked with
+//                __match_any (each warp owns 256 consecutive entries and a private counter
+//                per digit, so ranks follow the source order without atomics), the tile's
+//                digit counts are chained to the previous tiles with a decoupled look-back
+//                (one thread per digit), then every entry goes straight to its final slot
+//                of this pass.  Intermediate passes move 16-byte {key, a, v} records.
+//   k_rs_bounds  Cp[r] = first slot whose key is >= r (binary search in the sorted keys)
+//
+// Algorithmic bytes per entry: 4 (histogram) + 32 per pass (read + write a record) + 8
+// (sorted keys written and searched); ceil(log2(nkeys) / 8) passes.
+#include "common.cuh"
+#include <type_traits>
+
+namespace csb {
+
+constexpr int RS_THREADS = 512;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_EPT = 8;                       // entries per thread
+constexpr int RS_TILE = RS_THREADS * RS_EPT;    // 4096 entries per tile
+constexpr int RS_SEG = 32 * RS_EPT;             // consecutive entries owned by one warp
+constexpr int RS_BINS = 256;
+constexpr int RS_MAX_PASSES = 4;
+
+struct __align__(16) RsRec { int key; int a; double v; };
+struct __align__(8) RsRecP { int key; int a; };
+
+constexpr unsigned long long RS_AGG = 1ull << 62, RS_PREFIX = 2ull << 62;
+
+__global__ void __launch_bounds__(256)
+k_rs_hist(const int *__restrict__ key, long long nnz, int npasses, unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned h[RS_MAX_PASSES][RS_BINS];
+    for (int k = threadIdx.x; k < RS_MAX_PASSES * RS_BINS; k += 256) (&h[0][0])[k] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * 256 * 4;
+    for (long long p = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; p < nnz; p += stride) {
+        int k4[4];
+        if (p + 3 < nnz) {
+            const int4 r = ldg_stream(reinterpret_cast<const int4 *>(key + p));
+            k4[0] = r.x; k4[1] = r.y; k4[2] = r.z; k4[3] = r.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) k4[e] = p + e < nnz ? key[p + e] : -1;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (k4[e] >= 0)
+                for (int q = 0; q < npasses; q++) atomicAdd(&h[q][(k4[e] >> (8 * q)) & 255], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < npasses * RS_BINS; k += 256) {
+        const unsigned c = (&h[0][0])[k];
+        if (c) atomicAdd(&hist[k], (unsigned long long)c);
+    }
+}
+
+__global__ void __launch_bounds__(RS_BINS)
+k_rs_starts(int npasses, unsigned long long *hist)
+{
+    __shared__ unsigned long long wsum[RS_BINS / 32];
+    const int d = threadIdx.x, lane = d & 31, wid = d >> 5;
+    for (int q = 0; q < npasses; q++) {
+        const unsigned long long c = hist[q * RS_BINS + d];
+        unsigned long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        unsigned long long before = inc - c;
+        for (int w = 0; w < wid; w++) before += wsum[w];
+        hist[q * RS_BINS + d] = before;
+        __syncthreads();
+    }
+}
+
+// SRC: 0 = separate key / a / v arrays, 1 = records, 2 = separate key / v arrays with the
+//      int payload derived as "the column of Ap that holds this position" (cs_transpose)
+// DST: 0 = separate arrays (last pass; the sorted keys are written too), 1 = records
+template <int SRC, int DST, bool VALUES>
+__global__ void __launch_bounds__(RS_THREADS, 2)
+k_rs_pass(long long nnz, int shift,
+          const int *__restrict__ key_in, const int *__restrict__ a_in, const double *__restrict__ v_in,
+          const void *__restrict__ rec_in, const csi *__restrict__ Ap, int ncols,
+          int *__restrict__ key_out, int *__restrict__ a_out, double *__restrict__ v_out, void *__restrict__ rec_out,
+          const unsigned long long *__restrict__ digit_start, volatile unsigned long long *status, unsigned *ticket)
+{
+    using Rec = typename std::conditional<VALUES, RsRec, RsRecP>::type;
+    __shared__ int cnt[RS_WARPS][RS_BINS];
+    __shared__ long long gbase[RS_BINS];
+    __shared__ unsigned s_tile;
+    __shared__ int s_col[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt = lanemask_lt();
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int k = tid; k < RS_WARPS * RS_BINS; k += RS_THREADS) (&cnt[0][0])[k] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const long long base = (long long)tile * RS_TILE;
+    const long long seg = base + wid * RS_SEG;
+    const Rec *rin = reinterpret_cast<const Rec *>(rec_in);
+    if (SRC == 2 && tid < 2) {
+        // columns holding the first and the last position of this tile
+        const long long pe = tid == 0 ? base : min(nnz, base + RS_TILE) - 1;
+        s_col[tid] = upper_row(Ap, 0, ncols, (int)pe);
+    }
+
+    // ---- ranks in source order --------------------------------------------------------
+    int key[RS_EPT];
+    int rank[RS_EPT];
+#pragma unroll
+    for (int u = 0; u < RS_EPT; u++) {
+        const long long e = seg + u * 32 + lane;
+        key[u] = -1;
+        if (e < nnz) key[u] = SRC == 1 ? rin[e].key : key_in[e];
+    }
+#pragma unroll
+    for (int u = 0; u < RS_EPT; u++) {
+        // warp-uniform control flow: lanes past the end get a digit of their own (256 + lane) so
+        // that they match nobody; a shuffle whose mask differs between lanes would split the warp
+        const bool valid = key[u] >= 0;
+        const int d = valid ? ((key[u] >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        int r = 0;
+        if (valid && lane == leader) { r = cnt[wid][d]; cnt[wid][d] = r + __popc(peers); }
+        rank[u] = __shfl_sync(0xffffffffu, r, leader) + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- tile counts -> look-back -> global base of every digit ---------------------------
+    if (tid < RS_BINS) {
+        const int d = tid;
+        int sum = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) { const int c = cnt[w][d]; cnt[w][d] = sum; sum += c; }
+        volatile unsigned long long *mine = status + (size_t)tile * RS_BINS + d;
+        long long prefix = 0;
+        if (tile == 0) {
+            *mine = RS_PREFIX | (unsigned long long)sum;
+        } else {
+            *mine = RS_AGG | (unsigned long long)sum;
+            for (long long t = (long long)tile - 1; t >= 0; t--) {
+                volatile unsigned long long *pst = status + (size_t)t * RS_BINS + d;
+                unsigned long long w = *pst;
+                while ((w >> 62) == 0) w = *pst;
+                prefix += (long long)(w & 0xffffffffull);
+                if (w & RS_PREFIX) break;
+            }
+            *mine = RS_PREFIX | (unsigned long long)(prefix + sum);
+        }
+        gbase[d] = (long long)digit_start[d] + prefix;
+    }
+    __syncthreads();
+
+    // ---- scatter: payloads are loaded now, every entry goes to its slot of this pass --------
+    const int j_lo = SRC == 2 ? s_col[0] : 0, j_hi = SRC == 2 ? s_col[1] : 0;
+#pragma unroll
+    for (int u = 0; u < RS_EPT; u++) {
+        const long long e = seg + u * 32 + lane;
+        if (key[u] < 0) continue;
+        const int d = (key[u] >> shift) & (RS_BINS - 1);
+        const long long pos = gbase[d] + cnt[wid][d] + rank[u];
+        int a;
+        double v = 0.0;
+        if (SRC == 1) {
+            const Rec r = rin[e];
+            a = r.a;
+            if constexpr (VALUES) v = r.v;
+        } else {
+            a = SRC == 2 ? upper_row(Ap, j_lo, j_hi, (int)e) : a_in[e];
+            if (VALUES) v = v_in[e];
+        }
+        if (DST == 1) {
+            Rec r;
+            r.key = key[u]; r.a = a;
+            if constexpr (VALUES) r.v = v;
+            reinterpret_cast<Rec *>(rec_out)[pos] = r;
+        } else {
+            key_out[pos] = key[u];
+            a_out[pos] = a;
+            if (VALUES) v_out[pos] = v;
+        }
+    }
+}
+
+// Cp[r] = number of entries with key < r, r = 0..nkeys (keys sorted ascending)
+__global__ void k_rs_bounds(const int *__restrict__ keys, long long nnz, int nkeys, csi *__restrict__ Cp)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > nkeys) return;
+    long long lo = 0, hi = nnz;            // first index with keys[idx] >= r
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (keys[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    Cp[r] = (csi)lo;
+}
+
+#define RS_CUDA(expr) CSB_CUDA(expr)
+
+template <bool VALUES>
+static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, const csi *Ap, int ncols,
+                     const double *v, csi *Cp, csi *a_out, double *v_out)
+{
+    cudaStream_t s = stream();
+    int bits = 1;
+    while (bits < 31 && (1LL << bits) < (long long)nkeys) bits++;
+    const int npasses = (bits + 7) / 8;
+    const int ntiles = ceil_div(nnz, RS_TILE);
+    const size_t recsz = VALUES ? sizeof(RsRec) : sizeof(RsRecP);
+
+    DevBuf<unsigned long long> hist, status;
+    DevBuf<unsigned> ticket;
+    DevBuf<unsigned char> bufA, bufB;
+    DevBuf<int> keys_sorted;
+    CSB_TRY(hist.alloc(RS_MAX_PASSES * RS_BINS));
+    CSB_TRY(status.alloc((size_t)ntiles * RS_BINS));
+    CSB_TRY(ticket.alloc(RS_MAX_PASSES));
+    CSB_TRY(keys_sorted.alloc((size_t)nnz));
+    if (npasses >= 2) CSB_TRY(bufA.alloc((size_t)nnz * recsz));
+    if (npasses >= 3) CSB_TRY(bufB.alloc((size_t)nnz * recsz));
+    RS_CUDA(cudaMemsetAsync(hist.ptr, 0, RS_MAX_PASSES * RS_BINS * sizeof(unsigned long long), s));
+    RS_CUDA(cudaMemsetAsync(ticket.ptr, 0, RS_MAX_PASSES * sizeof(unsigned), s));
+    k_rs_hist<<<min(ceil_div(nnz, 1024 * 8), 148 * 8), 256, 0, s>>>(key, nnz, npasses, hist.ptr);
+    CSB_LAUNCHED();
+    k_rs_starts<<<1, RS_BINS, 0, s>>>(npasses, hist.ptr);
+    CSB_LAUNCHED();
+    const int src0 = a ? 0 : 2;
+    for (int q = 0; q < npasses; q++) {
+        RS_CUDA(cudaMemsetAsync(status.ptr, 0, (size_t)ntiles * RS_BINS * sizeof(unsigned long long), s));
+        const bool first = q == 0, last = q == npasses - 1;
+        const void *rin = first ? nullptr : ((q & 1) ? bufA.ptr : bufB.ptr);
+        void *rout = last ? nullptr : ((q & 1) ? bufB.ptr : bufA.ptr);
+        const unsigned long long *ds = hist.ptr + q * RS_BINS;
+#define RS_LAUNCH(SRC, DST)                                                                       \
+        k_rs_pass<SRC, DST, VALUES><<<ntiles, RS_THREADS, 0, s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
+            keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q)
+        if (first && last)      { if (src0 == 0) RS_LAUNCH(0, 0); else RS_LAUNCH(2, 0); }
+        else if (first)         { if (src0 == 0) RS_LAUNCH(0, 1); else RS_LAUNCH(2, 1); }
+        else if (last)          RS_LAUNCH(1, 0);
+        else                    RS_LAUNCH(1, 1);
+#undef RS_LAUNCH
+        CSB_LAUNCHED();
+    }
+    k_rs_bounds<<<ceil_div((long long)nkeys + 1, 256), 256, 0, s>>>(keys_sorted.ptr, nnz, nkeys, Cp);
+    CSB_LAUNCHED();
+    return CSB200_OK;
+}
+
+// Sorts nnz > 0 triples (key[e], a[e], v[e]) stably by key; a == nullptr derives the int
+// payload from Ap (ncols columns) as the column holding position e; v == nullptr sorts
+// pattern only.  Outputs a_out / v_out (nnz) and Cp (nkeys + 1).  All device pointers.
+int stable_sort_by_key(long long nnz, int nkeys, const int *key, const int *a, const csi *Ap, int ncols,
+                       const double *v, csi *Cp, csi *a_out, double *v_out)
+{
+    if (v) return sort_impl<true>(nnz, nkeys, key, a, Ap, ncols, v, Cp, a_out, v_out);
+    return sort_impl<false>(nnz, nkeys, key, a, Ap, ncols, nullptr, Cp, a_out, nullptr);
+}
+
+}  // namespace csb

@@ -85,10 +85,11 @@ __device__ __forceinline__ void block_minmax(int lo, int hi, int *s_red, int &bm
 // ---- bucket histogram ------------------------------------------------------------
 // A tile of consecutive entries touches a narrow window of buckets for banded
 // matrices: count in a shared-memory window and flush one global atomic per
-// (tile, bucket).  Tiles whose window does not fit fall back to one global atomic
-// per entry (random matrices: the atomics are spread, which L2 handles well).
+// (tile, bucket).  Tiles whose window does not fit are only counted (wide_tiles):
+// such a matrix is transposed by the stable radix sort of radix.cu.
 __global__ void __launch_bounds__(TR_THREADS)
-k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__restrict__ bcount)
+k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__restrict__ bcount,
+              int *__restrict__ wide_tiles)
 {
     __shared__ int cnt[HIST_WIN];
     __shared__ int s_red[16];
@@ -121,9 +122,10 @@ k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__rest
         __syncthreads();
         for (int k = threadIdx.x; k < win; k += TR_THREADS)
             if (cnt[k]) atomicAdd(&bcount[bmin + k], cnt[k]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 16; k++) if (b[k] >= 0) atomicAdd(&bcount[b[k]], 1);
+    } else if (threadIdx.x == 0) {
+        // rows all over the matrix: the bucket sort would need one global atomic per entry here
+        // and in the partition; the caller switches to the radix sort instead
+        atomicAdd(wide_tiles, 1);
     }
 }
 
@@ -717,11 +719,9 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
                 }
 #pragma unroll
                 for (int u = 0; u < BIG_UNROLL; u++) {
-                    const unsigned amask = __ballot_sync(0xffffffffu, d[u] >= 0);
-                    if (d[u] >= 0) {
-                        const unsigned peers = __match_any_sync(amask, d[u]);
-                        if ((peers & lt) == 0) cursors[d[u] * BIG_WARPS + wid] += __popc(peers);
-                    }
+                    // lanes past the end match nobody (digit nbins + lane); control flow stays uniform
+                    const unsigned peers = __match_any_sync(0xffffffffu, d[u] >= 0 ? d[u] : nbins + lane);
+                    if (d[u] >= 0 && (peers & lt) == 0) cursors[d[u] * BIG_WARPS + wid] += __popc(peers);
                     __syncwarp();
                 }
             }
@@ -750,16 +750,16 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
                 }
 #pragma unroll
                 for (int u = 0; u < BIG_UNROLL; u++) {
-                    const unsigned amask = __ballot_sync(0xffffffffu, d[u] >= 0);
-                    if (d[u] >= 0) {
-                        const unsigned peers = __match_any_sync(amask, d[u]);
-                        const int leader = __ffs(peers) - 1;
-                        int pos = 0;
-                        if (lane == leader) {
-                            pos = cursors[d[u] * BIG_WARPS + wid];
-                            cursors[d[u] * BIG_WARPS + wid] = pos + __popc(peers);
-                        }
-                        pos = __shfl_sync(peers, pos, leader) + __popc(peers & lt);
+                    const bool valid = d[u] >= 0;
+                    const unsigned peers = __match_any_sync(0xffffffffu, valid ? d[u] : nbins + lane);
+                    const int leader = __ffs(peers) - 1;
+                    int pos = 0;
+                    if (valid && lane == leader) {
+                        pos = cursors[d[u] * BIG_WARPS + wid];
+                        cursors[d[u] * BIG_WARPS + wid] = pos + __popc(peers);
+                    }
+                    pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(peers & lt);
+                    if (valid) {
                         if (!last) dst[pos] = en[u];
                         else {
                             Ci[base + pos] = en[u].col;
@@ -789,6 +789,8 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
 }
 
 // ---- host side -------------------------------------------------------------------
+int g_force_radix = 0;     // tests: send every transpose through the radix path
+
 int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
 {
     const csi m = A->m, n = A->n;
@@ -828,17 +830,43 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     DevBuf<int> bstart, bfill, tile_col;
     DevBuf<long long> total;
     DevBuf<unsigned char> inter;
-    if ((st = bstart.alloc((size_t)nbuckets + 1)) || (st = bfill.alloc((size_t)nbuckets + 1)) ||
-        (st = tile_col.alloc((size_t)ntiles + 1)) || (st = total.alloc(1)) ||
-        (st = inter.alloc((size_t)nnz * (has_x ? sizeof(Entry) : sizeof(EntryP)))))
+    if ((st = bstart.alloc((size_t)nbuckets + 1)) || (st = bfill.alloc((size_t)nbuckets + 2)) ||
+        (st = tile_col.alloc((size_t)ntiles + 1)) || (st = total.alloc(1)))
         return fail(st);
-    TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 1) * sizeof(int), s));
+    auto radix_path = [&]() {
+        int st2 = stable_sort_by_key(nnz, m, A->i, nullptr, A->p, n, has_x ? A->x : nullptr, C->p, C->i, C->x);
+        if (st2 != CSB200_OK) return fail(st2);
+        *out = C;
+        return (int)CSB200_OK;
+    };
+    if (g_force_radix) return radix_path();
+    TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 2) * sizeof(int), s));
     {
-        k_bucket_hist<<<ceil_div(nnz, TR_TILE), TR_THREADS, 0, s>>>(A->i, nnz, log_rb, bfill.ptr);
+        int *wide = bfill.ptr + nbuckets + 1, h_wide = 0;
+        k_bucket_hist<<<ceil_div(nnz, TR_TILE), TR_THREADS, 0, s>>>(A->i, nnz, log_rb, bfill.ptr, wide);
         TR_LAUNCHED();
+        TR_CUDA(cudaMemcpyAsync(&h_wide, wide, sizeof(int), cudaMemcpyDeviceToHost, s));
+        TR_CUDA(cudaStreamSynchronize(s));
+        if (h_wide > 0) return radix_path();
     }
     // bstart = exclusive scan of the counts; bfill <- bstart (the fill cursors)
     if ((st = launch_excl_scan(bstart.ptr, bfill.ptr, nbuckets, total.ptr, nullptr)) != CSB200_OK) return fail(st);
+    // oversized buckets (power-law rows): a few are sorted one CTA each (k_bucket_big); when they
+    // hold a sizeable share of the matrix the whole transpose goes through the stable radix sort
+    DevBuf<int> big_list, big_soff, big_ct;
+    int h_ct[2] = {0, 0};
+    if (nnz > bcap) {
+        if ((st = big_list.alloc((size_t)nbuckets)) || (st = big_soff.alloc((size_t)nbuckets)) ||
+            (st = big_ct.alloc(2)))
+            return fail(st);
+        TR_CUDA(cudaMemsetAsync(big_ct.ptr, 0, 2 * sizeof(int), s));
+        k_find_big<<<ceil_div(nbuckets, 256), 256, 0, s>>>(nbuckets, bstart.ptr, bcap, big_list.ptr, big_soff.ptr, big_ct.ptr);
+        TR_LAUNCHED();
+        TR_CUDA(cudaMemcpyAsync(h_ct, big_ct.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TR_CUDA(cudaStreamSynchronize(s));
+        if ((long long)h_ct[1] * 8 > nnz) return radix_path();
+    }
+    if ((st = inter.alloc((size_t)nnz * (has_x ? sizeof(Entry) : sizeof(EntryP)))) != CSB200_OK) return fail(st);
     k_tile_cols<<<ceil_div(ntiles + 1, 256), 256, 0, s>>>(A->p, n, nnz, ntiles, tile_col.ptr);
     TR_LAUNCHED();
     if (has_x) k_partition<true><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
@@ -857,18 +885,8 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
         else       k_bucket_sort<false><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
         TR_LAUNCHED();
     }
-    if (nnz > bcap) {
-        DevBuf<int> big_list, big_soff, big_ct;
+    {
         DevBuf<unsigned char> scratch;
-        if ((st = big_list.alloc((size_t)nbuckets)) || (st = big_soff.alloc((size_t)nbuckets)) ||
-            (st = big_ct.alloc(2)))
-            return fail(st);
-        TR_CUDA(cudaMemsetAsync(big_ct.ptr, 0, 2 * sizeof(int), s));
-        k_find_big<<<ceil_div(nbuckets, 256), 256, 0, s>>>(nbuckets, bstart.ptr, bcap, big_list.ptr, big_soff.ptr, big_ct.ptr);
-        TR_LAUNCHED();
-        int h_ct[2] = {0, 0};
-        TR_CUDA(cudaMemcpyAsync(h_ct, big_ct.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-        TR_CUDA(cudaStreamSynchronize(s));
         if (h_ct[0] > 0) {
             // key = (local row, source column): colbits + log_rb bits, in an odd number of passes
             int colbits = 1;

@@ -86,6 +86,9 @@ CSB200_API int csb200_mat_free(csb200_mat *A);
  * p, i, x are bit-identical to the reference's.  C has values iff values != 0
  * and A has values. */
 CSB200_API int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C);
+/* which algorithm later transposes use: 0 = automatic (two-level bucket sort, stable radix sort
+ * when power-law rows overflow the buckets), 1 = always the radix sort; for tests and benchmarks */
+CSB200_API int csb200_transpose_force_path(int path);
 /* one-shot form on host buffers: Cp has m+1 slots, Ci/Cx nnz slots (Cx may be NULL) */
 CSB200_API int csb200_transpose_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
                           csi *Cp, csi *Ci, double *Cx);

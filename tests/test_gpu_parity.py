@@ -138,6 +138,40 @@ def test_transpose_unsorted_duplicates_long_rows():
     assert_same_matrix(cc.cs_transpose(to_cs(A2, lists=False), True), orc.cs_transpose(A2, True), "long row")
 
 
+@pytest.fixture
+def radix_path():
+    cc.force_transpose_path("radix")
+    yield
+    cc.force_transpose_path(None)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_transpose_radix_fixtures(name, radix_path):
+    """the stable radix sort (power-law path) on every fixture: same bits as the reference"""
+    test_transpose_fixtures(name)
+
+
+def test_transpose_radix_synthetic(radix_path):
+    for gen in (lambda: synth.lap2d(300), lambda: synth.st27(20), lambda: synth.rmat(16, 16)):
+        test_transpose_synthetic(gen)
+    test_transpose_unsorted_duplicates_long_rows()
+    # pattern only, > 1 pass, ragged tail tile
+    m, n, p, i, x = synth.rmat(17, 8)
+    A = orc.csc(m, n, p, i, None)
+    C = cc.cs_transpose(to_cs(A, lists=False), False)
+    assert_same_matrix(C, orc.cs_transpose(A, False), "radix pattern")
+
+
+def test_transpose_power_law_takes_radix_path_and_matches():
+    """R-MAT rows overflow the row buckets: the automatic choice must still be bit-exact"""
+    m, n, p, i, x = synth.rmat(18, 16)
+    A = orc.csc(m, n, p, i, x)
+    R = orc.cs_transpose(A, True)
+    cp, ci, cx = cc.cs_transpose(cc.from_arrays(m, n, p, i, x), True).arrays()
+    assert np.array_equal(cp, R.p) and np.array_equal(ci, R.i[:A.nnz])
+    assert np.array_equal(bits(cx), bits(R.x[:A.nnz]))
+
+
 def test_transpose_deterministic():
     m, n, p, i, x = synth.rmat(14, 16)
     dA = cc.from_arrays(m, n, p, i, x)
