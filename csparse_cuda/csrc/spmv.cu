@@ -39,7 +39,10 @@ constexpr int MP_TILE = MP_THREADS * MP_ITEMS;   // merge items per CTA
 
 // Products of the slice [base, base+cnt) of (col, val) with x, into prods[0..cnt).
 // 128-bit loads on the 4-entry-aligned interior, scalar at the ragged ends.
-template <int THREADS>
+// PAD: element b lives at b + (b >> 3).  The merge kernel's threads walk runs of 8 consecutive
+// products each; unpadded, the 16 lanes of a 64-bit shared-memory phase would all hit the same
+// two banks (stride 64 B), padded they hit 16 different bank pairs (stride 72 B).
+template <int THREADS, bool PAD = false>
 __device__ __forceinline__ void stream_products(const csi *__restrict__ col, const double *__restrict__ val,
                                                 const double *__restrict__ x, int base, int cnt,
                                                 double *prods)
@@ -52,16 +55,20 @@ __device__ __forceinline__ void stream_products(const csi *__restrict__ col, con
             const double2 v0 = ldg_stream(reinterpret_cast<const double2 *>(val + k));
             const double2 v1 = ldg_stream(reinterpret_cast<const double2 *>(val + k + 2));
             const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
-            double *o = prods + (k - base);
+            const int q = k - base;
+            double *o = prods + (PAD ? q + (q >> 3) : q);
             o[0] = __dmul_rn(v0.x, x0);
-            o[1] = __dmul_rn(v0.y, x1);
-            o[2] = __dmul_rn(v1.x, x2);
-            o[3] = __dmul_rn(v1.y, x3);
+            o[PAD ? 1 + (((q + 1) >> 3) - (q >> 3)) : 1] = __dmul_rn(v0.y, x1);
+            o[PAD ? 2 + (((q + 2) >> 3) - (q >> 3)) : 2] = __dmul_rn(v1.x, x2);
+            o[PAD ? 3 + (((q + 3) >> 3) - (q >> 3)) : 3] = __dmul_rn(v1.y, x3);
         } else {
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int q = k + e;
-                if (q >= base && q < end) prods[q - base] = __dmul_rn(val[q], __ldg(x + col[q]));
+                if (q >= base && q < end) {
+                    const int o = q - base;
+                    prods[PAD ? o + (o >> 3) : o] = __dmul_rn(val[q], __ldg(x + col[q]));
+                }
             }
         }
     }
@@ -283,7 +290,7 @@ k_spmv_merge(int m, int nnz, const csi *__restrict__ rowptr, const csi *__restri
              const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
              const int *__restrict__ part, int *__restrict__ carry_row, double *__restrict__ carry_val)
 {
-    __shared__ double prods[MP_TILE];
+    __shared__ double prods[MP_TILE + MP_TILE / 8];
     __shared__ double rowsum[MP_TILE];
     __shared__ int re[MP_TILE + 1];          // row ends, local nnz coordinates
     __shared__ int ckey[MP_THREADS];
@@ -299,7 +306,7 @@ k_spmv_merge(int m, int nnz, const csi *__restrict__ rowptr, const csi *__restri
     const int nb = b1 - b0;                  // nonzeros consumed in this tile
 
     for (int k = threadIdx.x; k < na; k += MP_THREADS) re[k] = rowptr[a0 + k + 1] - b0;
-    stream_products<MP_THREADS>(col, val, x, b0, nb, prods);
+    stream_products<MP_THREADS, true>(col, val, x, b0, nb, prods);
     __syncthreads();
 
     // per-thread run of MP_ITEMS merge items
@@ -312,22 +319,35 @@ k_spmv_merge(int m, int nnz, const csi *__restrict__ rowptr, const csi *__restri
     for (int it = 0; it < MP_ITEMS; it++) {
         if (a + b < items) {
             if (a < na && re[a] <= b) { rowsum[a] = run; run = 0.0; a++; }
-            else                      { run = __dadd_rn(run, prods[b]); b++; }
+            else                      { run = __dadd_rn(run, prods[b + (b >> 3)]); b++; }
         }
     }
-    ckey[threadIdx.x] = a;                   // row this thread was still accumulating
-    cval[threadIdx.x] = run;
-    __syncthreads();
-
-    // carries: runs of equal keys are summed in thread order by the run's first thread
+    // carries: thread t was still accumulating row `a` when its items ran out.  Keys are
+    // non-decreasing in t; the partial sums of a run of equal keys are combined by a segmented
+    // warp scan plus a walk over the preceding warps' tails -- a fixed order, so the result is
+    // deterministic, and no thread ever loops over a whole tile (one row may span all of it).
     {
-        const int t = threadIdx.x;
-        const int key = ckey[t];
-        if (t == 0 || ckey[t - 1] != key) {
-            double s = cval[t];
-            for (int u = t + 1; u < MP_THREADS && ckey[u] == key; u++) s = __dadd_rn(s, cval[u]);
-            if (key < na) rowsum[key] = __dadd_rn(s, rowsum[key]);   // earlier threads' part comes first
-            else { carry_row[c] = a0 + key; carry_val[c] = s; }      // key == na: unfinished tail row
+        const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+        const int key = a;
+        double v = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double vu = __shfl_up_sync(0xffffffffu, v, o);
+            const int ku = __shfl_up_sync(0xffffffffu, key, o);
+            if (lane >= o && ku == key) v = __dadd_rn(vu, v);
+        }
+        if (lane == 31) { ckey[wid] = key; cval[wid] = v; }                 // tail of this warp
+        if (lane == 0) ckey[MP_THREADS / 32 + wid] = key;                   // head of this warp
+        __syncthreads();
+        int knext = __shfl_down_sync(0xffffffffu, key, 1);
+        if (lane == 31) knext = wid + 1 < MP_THREADS / 32 ? ckey[MP_THREADS / 32 + wid + 1] : -1;
+        const int key0 = __shfl_sync(0xffffffffu, key, 0);
+        if (knext != key) {                                                  // last thread of its run
+            double s = v;
+            if (key0 == key)                                                 // run reaches back past lane 0
+                for (int w = wid - 1; w >= 0 && ckey[w] == key; w--) s = __dadd_rn(cval[w], s);
+            if (key < na) rowsum[key] = __dadd_rn(s, rowsum[key]);           // earlier threads' part comes first
+            else { carry_row[c] = a0 + key; carry_val[c] = s; }              // key == na: unfinished tail row
         }
     }
     __syncthreads();
