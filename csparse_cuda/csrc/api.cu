@@ -334,6 +334,9 @@ int csb200_mat_free(csb200_mat *A)
     dev_free(A->p);
     dev_free(A->i);
     dev_free(A->x);
+    dev_free(A->c32_blk);
+    dev_free(A->c32_mask);
+    dev_free(A->c32_len);
     delete A;
     return CSB200_OK;
 }

@@ -110,6 +110,11 @@ struct csb200_mat {
     csb200_mat *csr = nullptr;   // cached transpose with values == CSR view of this matrix
     SpmvPlan *plan = nullptr;    // gaxpy plan over this matrix interpreted as a CSR view (columns = rows)
     int forced_plan = 0;
+    // cs_multiply's symbolic phase: every column as (32-row block, bit mask) pairs, stored at the
+    // column's own offset p[j] with c32_len[j] pairs (spgemm.cu, built on first use as left factor)
+    csi *c32_blk = nullptr;
+    unsigned *c32_mask = nullptr;
+    csi *c32_len = nullptr;
 };
 
 // ---- device helpers -----------------------------------------------------------

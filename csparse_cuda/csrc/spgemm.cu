@@ -106,77 +106,136 @@ __device__ __forceinline__ int warp_find_or_insert(int *keys, int hmask, int i, 
     return (int)h;
 }
 
-// ---- symbolic, one warp per column, hash set in shared memory ---------------------
-// Shared memory per warp: keys[H] and slots[CAP] (the slots this column filled, so
-// the table is emptied by undoing cnt entries instead of clearing H).  OPTIMISTIC:
-// the column's bound ub exceeds CAP but its true size usually does not; a column
-// that does outgrow CAP is undone and appended to ovf_list for the next tier.
-template <int LOGH, int CAP, int WARPS, bool OPTIMISTIC, bool CANON>
+// ---- compressed columns for the symbolic phase ------------------------------------------
+// Column k of A as pairs (block = row >> 5, mask = bits of the rows present in that block),
+// runs of equal blocks merged (sorted columns of a stencil shrink ~3x).  The pairs of column k
+// live at offset Ap[k] of blk / mask (no second pointer array), len32[k] of them.
+__global__ void __launch_bounds__(256)
+k_compress_cols(int n, const csi *__restrict__ Ap, const csi *__restrict__ Ai,
+                csi *__restrict__ blk32, unsigned *__restrict__ mask32, csi *__restrict__ len32)
+{
+    const int lane = threadIdx.x & 31;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n) return;
+    const int b = Ap[k], e = Ap[k + 1];
+    int out = 0;                                               // warp-uniform: pairs written so far
+    for (int p0 = b; p0 < e; p0 += 32) {
+        const int p = p0 + lane;
+        const bool valid = p < e;
+        const int row = valid ? Ai[p] : 0;
+        const int blk = valid ? (row >> 5) : -1 - lane;        // past the end: matches no neighbour
+        unsigned v = valid ? 1u << (row & 31) : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {                     // segmented inclusive OR over runs
+            const unsigned u = __shfl_up_sync(0xffffffffu, v, o);
+            const int bu = __shfl_up_sync(0xffffffffu, blk, o);
+            if (lane >= o && bu == blk) v |= u;
+        }
+        const int bnext = __shfl_down_sync(0xffffffffu, blk, 1);
+        const bool tail = valid && (lane == 31 || bnext != blk);
+        const unsigned tails = __ballot_sync(0xffffffffu, tail);
+        if (tail) {
+            const int q = b + out + __popc(tails & lanemask_lt());
+            blk32[q] = blk;
+            mask32[q] = v;
+        }
+        out += __popc(tails);
+    }
+    if (lane == 0) len32[k] = out;
+}
+
+// ---- symbolic on compressed columns, one warp per column of B ------------------------------
+// The (block, mask) pairs of all A(:,k), k in B(:,j), are taken 32 at a time regardless of
+// which A column they come from (flattened), so the lanes stay busy for short columns.  The
+// hash set is keyed by block; masks are OR-ed in and the newly set bits counted.  Two lanes may
+// carry the same block in one step, hence shared-memory atomics (CAS insert, OR); the count is
+// a set size, so the order does not matter.  Tables are emptied by undoing the touched slots.
+template <int LOGH, int CAP, int WARPS, bool OPTIMISTIC>
 __global__ void __launch_bounds__(WARPS * 32)
-k_sym_warp(const int *__restrict__ list, const int *__restrict__ ncols_dev, int ncols_host,
-           const csi *__restrict__ Ap, const csi *__restrict__ Ai,
+k_sym_flat(const int *__restrict__ list, const int *__restrict__ ncols_dev, int ncols_host,
+           const csi *__restrict__ Ap, const csi *__restrict__ blk32, const unsigned *__restrict__ mask32,
+           const csi *__restrict__ len32,
            const csi *__restrict__ Bp, const csi *__restrict__ Bi, int *__restrict__ cnt_out,
            int *__restrict__ ovf_list, int *ovf_count)
 {
     constexpr int H = 1 << LOGH;
     static_assert(H >= CAP + 64 && H <= 65536, "table must never fill");
-    constexpr int PER_WARP = H * 4 + CAP * 2;
+    constexpr int PER_WARP = H * 8 + CAP * 2;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int *keys = reinterpret_cast<int *>(sm_raw + (size_t)wid * PER_WARP);
-    unsigned short *slots = reinterpret_cast<unsigned short *>(keys + H);
+    unsigned *masks = reinterpret_cast<unsigned *>(keys + H);
+    unsigned short *slots = reinterpret_cast<unsigned short *>(masks + H);
     const unsigned lt = lanemask_lt();
     const int ncols = ncols_dev ? *ncols_dev : ncols_host;
     const int nwarps = gridDim.x * WARPS;
-    for (int s = lane; s < H; s += 32) keys[s] = EMPTY;
+    for (int s = lane; s < H; s += 32) { keys[s] = EMPTY; masks[s] = 0; }
     __syncwarp();
     for (int idx = blockIdx.x * WARPS + wid; idx < ncols; idx += nwarps) {
         const int j = list[idx];
-        int cnt = 0;                                   // warp-uniform
+        int nslots = 0;                                // warp-uniform: distinct blocks so far
+        int mine = 0;                                  // rows first seen by this lane
         bool ovf = false;
         const int pb_end = Bp[j + 1];
         for (int pb0 = Bp[j]; pb0 < pb_end && !ovf; pb0 += 32) {
-            const int my_pb = pb0 + lane;
-            int my_ab = 0, my_ae = 0;
-            if (my_pb < pb_end) {
-                const int k = Bi[my_pb];
-                my_ab = Ap[k];
-                my_ae = Ap[k + 1];
+            int base = 0, len = 0;
+            if (pb0 + lane < pb_end) {
+                const int k = Bi[pb0 + lane];
+                base = Ap[k];
+                len = len32[k];
             }
-            const int nb = min(32, pb_end - pb0);
-            for (int s = 0; s < nb && !ovf; s++) {
-                const int ab = __shfl_sync(0xffffffffu, my_ab, s);
-                const int ae = __shfl_sync(0xffffffffu, my_ae, s);
-                for (int pa0 = ab; pa0 < ae; pa0 += 32) {
-                    const int pa = pa0 + lane;
-                    const bool active = pa < ae;
-                    const int i = active ? Ai[pa] : 0;
-                    // duplicates inside a column of A: one lane per distinct row inserts
-                    bool leader = active;
-                    if (!CANON) {
-                        const unsigned act = __ballot_sync(0xffffffffu, active);
-                        if (active) leader = (__ffs(__match_any_sync(act, i)) - 1) == lane;
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - len;
+            for (int f0 = 0; f0 < total; f0 += 32) {
+                const int f = f0 + lane;
+                const bool valid = f < total;
+                int s = 0;                             // source lane: the largest s with excl[s] <= f
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int es = __shfl_sync(0xffffffffu, excl, (s + step) & 31);
+                    if (es <= f) s += step;            // s + step <= 31 always
+                }
+                const int sb = __shfl_sync(0xffffffffu, base, s);
+                const int se = __shfl_sync(0xffffffffu, excl, s);
+                int slot = 0;
+                bool isnew = false;
+                if (valid) {
+                    const int blk = blk32[sb + (f - se)];
+                    const unsigned m = mask32[sb + (f - se)];
+                    unsigned h = hash_row(blk, LOGH);
+                    while (true) {
+                        const int old = atomicCAS(&keys[h], EMPTY, blk);
+                        if (old == EMPTY) { isnew = true; break; }
+                        if (old == blk) break;
+                        h = (h + 1) & (H - 1);
                     }
-                    bool isnew;
-                    const int slot = warp_find_or_insert(keys, H - 1, i, leader, hash_row(i, LOGH), isnew);
-                    const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
-                    if (newmask) {
-                        const int pos = cnt + __popc(newmask & lt);
-                        if (isnew) {
-                            if (pos < CAP) slots[pos] = (unsigned short)slot;
-                            else keys[slot] = EMPTY;          // beyond the undo list: undo now
-                        }
-                        cnt += __popc(newmask);
-                        __syncwarp();
-                        if (cnt > CAP) { ovf = true; break; }
+                    slot = (int)h;
+                    const unsigned before = atomicOr(&masks[slot], m);
+                    mine += __popc(m & ~before);
+                }
+                const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
+                if (newmask) {
+                    const int pos = nslots + __popc(newmask & lt);
+                    __syncwarp();                                           // this step's ORs have landed
+                    if (isnew) {
+                        if (pos < CAP) slots[pos] = (unsigned short)slot;
+                        else { keys[slot] = EMPTY; masks[slot] = 0; }      // beyond the undo list: undo now
                     }
+                    nslots += __popc(newmask);
+                    if (nslots > CAP) { ovf = true; break; }
                 }
             }
         }
-        const int filled = min(cnt, CAP);
-        for (int t = lane; t < filled; t += 32) keys[slots[t]] = EMPTY;
+        __syncwarp();
+        const int filled = min(nslots, CAP);
+        for (int t = lane; t < filled; t += 32) { const int sl = slots[t]; keys[sl] = EMPTY; masks[sl] = 0; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
         if (lane == 0) {
-            if (!ovf) cnt_out[j] = cnt;
+            if (!ovf) cnt_out[j] = mine;
             else if (OPTIMISTIC) ovf_list[atomicAdd(ovf_count, 1)] = j;
         }
         __syncwarp();
@@ -423,24 +482,38 @@ int mat_is_canonical(csb200_mat *A, int *out)
 
 // ---- host side ---------------------------------------------------------------------------
 // ncols_dev != null: the number of listed columns is read on the device (no host round trip)
+static int ensure_compressed(csb200_mat *A)
+{
+    if (A->c32_len) return CSB200_OK;
+    const size_t cap = (size_t)(A->nnz > 0 ? A->nnz : 1);
+    CSB_TRY(dev_alloc(&A->c32_blk, cap));
+    CSB_TRY(dev_alloc(&A->c32_mask, cap));
+    csi *len = nullptr;
+    CSB_TRY(dev_alloc(&len, (size_t)A->n + 1));
+    if (A->n > 0) {
+        k_compress_cols<<<ceil_div((long long)A->n * 32, 256), 256, 0, stream()>>>(A->n, A->p, A->i, A->c32_blk,
+                                                                                 A->c32_mask, len);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { dev_free(len); return set_error(CSB200_ERR_CUDA, "k_compress_cols: %s", cudaGetErrorString(e)); }
+    }
+    A->c32_len = len;
+    return CSB200_OK;
+}
+
 template <int LOGH, int CAP, int WARPS, bool OPTIMISTIC>
-static int run_sym_warp(const int *list, const int *ncols_dev, int ncols, const csb200_mat *A,
-                        const csb200_mat *B, int *cnt, bool canon, int *ovf_list, int *ovf_count)
+static int run_sym_flat(const int *list, const int *ncols_dev, int ncols, const csb200_mat *A,
+                        const csb200_mat *B, int *cnt, int *ovf_list, int *ovf_count)
 {
     if (!ncols_dev && ncols == 0) return CSB200_OK;
-    const size_t smem = (size_t)WARPS * ((size_t)(1 << LOGH) * 4 + CAP * 2);
-    const int resident = (int)min((size_t)16, (size_t)(220 * 1024) / smem);
+    const size_t smem = (size_t)WARPS * ((size_t)(1 << LOGH) * 8 + CAP * 2);
+    const int resident = (int)min((size_t)(2048 / (WARPS * 32)), (size_t)(220 * 1024) / smem);
     const int grid = ncols_dev ? 148 * resident
                                : (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * resident);
-#define SYM_LAUNCH(K)                                                                             \
-    do {                                                                                          \
-        auto kern = k_sym_warp<LOGH, CAP, WARPS, OPTIMISTIC, K>;                                  \
-        CSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, WARPS * 32, smem, stream()>>>(list, ncols_dev, ncols, A->p, A->i, B->p, B->i, cnt, \
-                                                   ovf_list, ovf_count);                          \
-    } while (0)
-    if (canon) SYM_LAUNCH(true); else SYM_LAUNCH(false);
-#undef SYM_LAUNCH
+    auto kern = k_sym_flat<LOGH, CAP, WARPS, OPTIMISTIC>;
+    CSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, WARPS * 32, smem, stream()>>>(list, ncols_dev, ncols, A->p, A->c32_blk, A->c32_mask, A->c32_len,
+                                               B->p, B->i, cnt, ovf_list, ovf_count);
     CSB_LAUNCHED();
     return CSB200_OK;
 }
@@ -505,21 +578,20 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
         k_ub<<<ceil_div(n, 256), 256, 0, s>>>(n, B->p, B->i, A->p, ub.ptr, flops.ptr);
         MM_LAUNCHED();
         // symbolic classes by min(ub, m): <=256 (cannot outgrow the small table) |
-        // <=8192 (optimistic: small table first, columns that outgrow it -> list 2) | dense
-        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, m, 256, 8192, 8192, lists.ptr, counts.ptr);
+        // <=8000 (optimistic: small table first, columns that outgrow it -> list 2) | dense
+        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, m, 256, 8000, 8000, lists.ptr, counts.ptr);
         MM_LAUNCHED();
         MM_CUDA(cudaMemcpyAsync(h_counts, counts.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
         MM_CUDA(cudaMemcpyAsync(&h_flops, flops.ptr, sizeof(h_flops), cudaMemcpyDeviceToHost, s));
         MM_CUDA(cudaStreamSynchronize(s));
         tls().last_flops = (int64_t)h_flops;
         int *ovf_list = lists.ptr + 2 * ncap, *ovf_count = counts.ptr + 2;
-        MM_TRY((run_sym_warp<9, 256, 8, false>(lists.ptr, nullptr, h_counts[0], A, B, cnt.ptr, canon != 0,
-                                               nullptr, nullptr)));
+        if (h_counts[0] + h_counts[1] > 0) MM_TRY(ensure_compressed(A));
+        MM_TRY((run_sym_flat<9, 256, 8, false>(lists.ptr, nullptr, h_counts[0], A, B, cnt.ptr, nullptr, nullptr)));
         if (h_counts[1] > 0) {
-            MM_TRY((run_sym_warp<9, 256, 8, true>(lists.ptr + ncap, nullptr, h_counts[1], A, B, cnt.ptr,
-                                                  canon != 0, ovf_list, ovf_count)));
-            MM_TRY((run_sym_warp<14, 8192, 2, false>(ovf_list, ovf_count, 0, A, B, cnt.ptr, canon != 0,
-                                                     nullptr, nullptr)));
+            MM_TRY((run_sym_flat<9, 256, 8, true>(lists.ptr + ncap, nullptr, h_counts[1], A, B, cnt.ptr,
+                                                  ovf_list, ovf_count)));
+            MM_TRY((run_sym_flat<13, 8000, 2, false>(ovf_list, ovf_count, 0, A, B, cnt.ptr, nullptr, nullptr)));
         }
         if (h_counts[3] > 0) {
             const int ctas = min(DENSE_CTAS, h_counts[3]);
