@@ -11,6 +11,17 @@ Same names, argument meaning and error behaviour as the reference module
     cs_gaxpy      csparse.py:1199-1213 y += A*x
     cs_multiply   csparse.py:1608-1642 C = A*B
 
+and, built from the same kernels, the callers / data formats either side of that path:
+
+    cs_add        csparse.py:163-192   C = alpha*A + beta*B
+    cs_norm       csparse.py:1647-1663 1-norm
+    cs_compress   csparse.py:647-672   triplet -> compressed column
+    cs_dupl       csparse.py:1035-1063 sum duplicates
+    cs_fkeep      csparse.py:1172-1196 (fixed predicates), cs_dropzeros :1024, cs_droptol :1007
+    cs_permute    csparse.py:1666-1693 C = P A Q
+    cs_symperm    csparse.py:2220-2255 C = P A P'
+    cs_pinv       csparse.py:1696-1710 (host helper)
+
 Every function runs on the GPU through libcsparse_b200.so (hand-written sm_100a
 CUDA, include/csparse_b200.h) -- there is no CPU fallback.  ``cs`` objects may be
 backed by Python lists (as in the reference), ``array.array`` or numpy arrays;
@@ -32,7 +43,9 @@ from . import _lib
 from ._lib import CSparseCudaError  # noqa: F401
 
 __all__ = ["cs", "CS_CSC", "CS_TRIPLET", "cs_cumsum", "cs_transpose", "cs_gaxpy", "cs_multiply",
-           "DeviceMatrix", "upload", "CSparseCudaError"]
+           "cs_add", "cs_norm", "cs_compress", "cs_dupl", "cs_fkeep", "cs_dropzeros", "cs_droptol",
+           "cs_permute", "cs_symperm", "cs_pinv", "cs_ifkeep", "KEEP_NONZERO", "KEEP_TOL", "KEEP_OFFDIAG",
+           "KEEP_UPPER", "DeviceMatrix", "upload", "CSparseCudaError"]
 
 
 class cs(object):
@@ -326,6 +339,242 @@ def cs_multiply(A, B):
     if isinstance(A, DeviceMatrix) and isinstance(B, DeviceMatrix):
         return dC
     return dC.download(trim=True)
+
+
+# ---- the callers and data formats either side of the hot path ----------
+
+def _padded(dC: "DeviceMatrix", nzmax: int) -> cs:
+    """Download into a cs whose i / x lists have cs_spalloc's length nzmax (zero tail)."""
+    p, i, x = dC.arrays()
+    A = cs()
+    A.m, A.n, A.nz, A.nzmax = dC.m, dC.n, -1, nzmax
+    pad = nzmax - len(i)
+    A.p = p.tolist()
+    A.i = i.tolist() + [0] * pad
+    A.x = None if x is None else x.tolist() + [0.0] * pad
+    return A
+
+
+def _nnz_of(A) -> int:
+    return A.nnz if isinstance(A, DeviceMatrix) else int(A.p[A.n])
+
+
+def cs_add(A, B, alpha, beta):
+    """C = alpha*A + beta*B.
+
+    Reference: csparse.py:163-192.  None unless both are compressed-column with equal
+    dimensions.  Runs as [A B] * [alpha I; beta I] on the SpGEMM kernels, so the columns of C
+    are in the reference's order (A's entries, then B's new rows) with its rounding.
+    C.nzmax = max(nnz(A) + nnz(B), 1) as cs_spalloc leaves it (the reference does not trim).
+    """
+    if not CS_CSC(A) or not CS_CSC(B):
+        return None
+    if A.m != B.m or A.n != B.n:
+        return None
+    nzmax = max(_nnz_of(A) + _nnz_of(B), 1)
+    dA, ta = _as_device(A)
+    dB, tb = (dA, False) if B is A else _as_device(B)
+    out = C.c_void_p()
+    _lib.check(_lib.lib().csb200_add(dA._h, dB._h, float(alpha), float(beta), C.byref(out)), "cs_add")
+    dC = DeviceMatrix(out.value)
+    if ta:
+        dA.free()
+    if tb:
+        dB.free()
+    if isinstance(A, DeviceMatrix) and isinstance(B, DeviceMatrix):
+        return dC
+    return _padded(dC, nzmax)
+
+
+def cs_norm(A):
+    """1-norm of a sparse matrix = largest column sum of |x| (csparse.py:1647-1663).
+    -1 if A is not compressed-column or has no values."""
+    if not CS_CSC(A):
+        return -1
+    if (not A.has_values) if isinstance(A, DeviceMatrix) else (A.x is None):
+        return -1
+    dA, tmp = _as_device(A)
+    v = C.c_double()
+    _lib.check(_lib.lib().csb200_norm(dA._h, C.byref(v)), "cs_norm")
+    if tmp:
+        dA.free()
+    return v.value
+
+
+def compress_device(T) -> "DeviceMatrix":
+    """cs_compress leaving the result in HBM."""
+    nz = T.nz
+    ti, tj = _i32(T.i, nz), _i32(T.p, nz)
+    tx = None if T.x is None else _f64(T.x, nz)
+    out = C.c_void_p()
+    st = _lib.check(_lib.lib().csb200_compress(T.m, T.n, nz, _ptr(ti), _ptr(tj), _ptr(tx), C.byref(out)),
+                    "cs_compress")
+    if st == _lib.ERR_ARG:
+        raise ValueError(_lib.last_error())
+    return DeviceMatrix(out.value)
+
+
+def cs_compress(T):
+    """C = compressed-column form of a triplet matrix T (csparse.py:647-672).  None unless T is
+    a triplet matrix.  Columns are not sorted and duplicates stay; the entries of a column keep
+    their input order (stable radix sort on the column index)."""
+    if not CS_TRIPLET(T):
+        return None
+    return compress_device(T).download(trim=False)
+
+
+def cs_dupl(A):
+    """Removes and sums duplicate entries (csparse.py:1035-1063).  In place on a list-backed
+    cs: p, i, x are replaced, nzmax = nnz; returns True (False unless compressed-column).
+    Device matrices are immutable: use ``dupl_device``."""
+    if not CS_CSC(A):
+        return False
+    if isinstance(A, DeviceMatrix):
+        raise TypeError("cs_dupl works in place on a host cs; use dupl_device(A) for device matrices")
+    if A.x is None:
+        raise TypeError("cs_dupl: matrix has no numerical values (A.x is None)")
+    dC = dupl_device(A)
+    p, i, x = dC.arrays()
+    A.p[: A.n + 1] = p.tolist()
+    A.i, A.x, A.nzmax = i.tolist(), x.tolist(), dC.nnz
+    return True
+
+
+def dupl_device(A) -> "DeviceMatrix":
+    dA, tmp = _as_device(A)
+    out = C.c_void_p()
+    st = _lib.check(_lib.lib().csb200_dupl(dA._h, C.byref(out)), "cs_dupl")
+    if tmp:
+        dA.free()
+    if st == _lib.ERR_ARG:
+        raise TypeError(_lib.last_error())
+    return DeviceMatrix(out.value)
+
+
+KEEP_NONZERO, KEEP_TOL, KEEP_OFFDIAG, KEEP_UPPER = 0, 1, 2, 3
+
+
+class cs_ifkeep(object):
+    """The reference's predicate interface (csparse.py:1160-1169).  The GPU path evaluates a
+    fixed set of predicates; subclasses name one through ``code``."""
+    code = None
+
+    def fkeep(self, i, j, aij, other):
+        raise NotImplementedError
+
+
+class _cs_nonzero(cs_ifkeep):
+    code = KEEP_NONZERO
+
+    def fkeep(self, i, j, aij, other):
+        return aij != 0
+
+
+class _cs_tol(cs_ifkeep):
+    code = KEEP_TOL
+
+    def fkeep(self, i, j, aij, other):
+        return abs(aij) > float(other)
+
+
+class cs_offdiag(cs_ifkeep):
+    """csparse_test.py's Dropdiag: keep the off-diagonal entries."""
+    code = KEEP_OFFDIAG
+
+    def fkeep(self, i, j, aij, other):
+        return i != j
+
+
+class cs_upper(cs_ifkeep):
+    code = KEEP_UPPER
+
+    def fkeep(self, i, j, aij, other):
+        return i <= j
+
+
+def fkeep_device(A, code: int, tol: float = 0.0) -> "DeviceMatrix":
+    dA, tmp = _as_device(A)
+    out = C.c_void_p()
+    _lib.check(_lib.lib().csb200_fkeep(dA._h, int(code), float(tol), C.byref(out)), "cs_fkeep")
+    if tmp:
+        dA.free()
+    return DeviceMatrix(out.value)
+
+
+def cs_fkeep(A, fkeep, other):
+    """Drops entries from a sparse matrix (csparse.py:1172-1196); in place, returns the new
+    number of entries, -1 unless compressed-column.  ``fkeep`` is one of the predicate objects
+    of this module (cs_dropzeros / cs_droptol's, cs_offdiag, cs_upper) or a KEEP_* code: the
+    predicate runs on the GPU, arbitrary Python callables cannot."""
+    if not CS_CSC(A):
+        return -1
+    code = fkeep if isinstance(fkeep, int) else getattr(fkeep, "code", None)
+    if code is None:
+        raise NotImplementedError("cs_fkeep on the GPU supports the fixed predicates KEEP_NONZERO, "
+                                  "KEEP_TOL, KEEP_OFFDIAG, KEEP_UPPER")
+    if isinstance(A, DeviceMatrix):
+        raise TypeError("cs_fkeep works in place on a host cs; use fkeep_device(A, code, tol)")
+    dC = fkeep_device(A, code, 0.0 if other is None else float(other))
+    p, i, x = dC.arrays()
+    A.p[: A.n + 1] = p.tolist()
+    A.i = i.tolist()
+    A.x = None if A.x is None else x.tolist()
+    A.nzmax = dC.nnz
+    return dC.nnz
+
+
+def cs_droptol(A, tol):
+    """Removes entries with absolute value <= tol (csparse.py:1007-1014)."""
+    return cs_fkeep(A, _cs_tol(), tol)
+
+
+def cs_dropzeros(A):
+    """Removes numerically zero entries (csparse.py:1024-1030)."""
+    return cs_fkeep(A, _cs_nonzero(), None)
+
+
+def cs_pinv(p, n):
+    """pinv[p[k]] = k (csparse.py:1696-1710); None if p is None.  Host helper."""
+    if p is None:
+        return None
+    pinv = [0] * n
+    for k in range(n):
+        pinv[p[k]] = k
+    return pinv
+
+
+def cs_permute(A, pinv, q, values):
+    """C = P A Q (csparse.py:1666-1693): column k of C is column q[k] of A, row i of A is row
+    pinv[i] of C; pinv / q may be None.  None unless compressed-column."""
+    if not CS_CSC(A):
+        return None
+    dA, tmp = _as_device(A)
+    pv = None if pinv is None else _i32(pinv, dA.m)
+    qv = None if q is None else _i32(q, dA.n)
+    out = C.c_void_p()
+    _lib.check(_lib.lib().csb200_permute(dA._h, _ptr(pv), _ptr(qv), 1 if values else 0, C.byref(out)), "cs_permute")
+    dC = DeviceMatrix(out.value)
+    if not tmp:
+        return dC
+    dA.free()
+    return dC.download(trim=False)
+
+
+def cs_symperm(A, pinv, values):
+    """C = P A P' for a symmetric A whose upper triangular part is stored/used
+    (csparse.py:2220-2255).  C.nzmax = max(nnz(A), 1) as the reference allocates it."""
+    if not CS_CSC(A):
+        return None
+    nzmax = max(_nnz_of(A), 1)
+    dA, tmp = _as_device(A)
+    pv = None if pinv is None else _i32(pinv, dA.n)
+    out = C.c_void_p()
+    _lib.check(_lib.lib().csb200_symperm(dA._h, _ptr(pv), 1 if values else 0, C.byref(out)), "cs_symperm")
+    dC = DeviceMatrix(out.value)
+    if not tmp:
+        return dC
+    dA.free()
+    return _padded(dC, nzmax)
 
 
 def set_stream(cuda_stream: int = 0):

@@ -83,7 +83,7 @@ __global__ void k_rebase(const csi *__restrict__ src, int count, int base, csi *
     if (k < count) dst[k] = src[k] - base;
 }
 
-static int mat_alloc(csi m, csi n, long long nnz, bool has_x, csb200_mat **out)
+int mat_alloc(csi m, csi n, long long nnz, bool has_x, csb200_mat **out)
 {
     csb200_mat *A = new (std::nothrow) csb200_mat();
     if (!A) return set_error(CSB200_ERR_NOMEM, "out of host memory");

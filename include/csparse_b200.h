@@ -121,6 +121,33 @@ CSB200_API int csb200_multiply(const csb200_mat *A, const csb200_mat *B, csb200_
 /* number of multiply-adds of the last csb200_multiply on this thread */
 CSB200_API int64_t csb200_multiply_last_flops(void);
 
+/* ---- the callers and data formats either side of the hot path ---- */
+/* cs_add (csparse.py:163-192): C = alpha*A + beta*B as [A B] * [alpha I; beta I] on the SpGEMM
+ * kernels: column order and rounding are the reference's.  C has values iff A and B have.
+ * The handle holds exactly nnz(C) entries (the reference over-allocates nnz(A)+nnz(B)). */
+CSB200_API int csb200_add(csb200_mat *A, csb200_mat *B, double alpha, double beta, csb200_mat **C);
+/* cs_norm (csparse.py:1647-1663): largest column sum of |x|, entries added in storage order */
+CSB200_API int csb200_norm(const csb200_mat *A, double *norm);
+/* cs_compress (csparse.py:647-672): triplets (Ti, Tj, Tx or NULL; nz of them, any order,
+ * duplicates allowed) -> CSC by a stable radix sort on the column index; entries of a column
+ * keep their input order.  Host and device-buffer forms. */
+CSB200_API int csb200_compress(csi m, csi n, csi nz, const csi *Ti, const csi *Tj, const double *Tx, csb200_mat **C);
+CSB200_API int csb200_compress_dev(csi m, csi n, csi nz, const csi *d_Ti, const csi *d_Tj, const double *d_Tx,
+                        csb200_mat **C);
+/* cs_dupl (csparse.py:1035-1063): duplicates summed into their first occurrence, as A * I on the
+ * SpGEMM kernels; out of place (handles are immutable).  A must have values. */
+CSB200_API int csb200_dupl(csb200_mat *A, csb200_mat **C);
+/* cs_fkeep (csparse.py:1172-1196) with a fixed predicate: 0 keep aij != 0 (cs_dropzeros :1024),
+ * 1 keep |aij| > tol (cs_droptol :1007), 2 keep i != j (csparse_test.py Dropdiag), 3 keep i <= j.
+ * Order inside the columns is kept; out of place. */
+CSB200_API int csb200_fkeep(const csb200_mat *A, int predicate, double tol, csb200_mat **C);
+/* cs_permute (csparse.py:1666-1693): C = P A Q; pinv (m entries) / q (n entries) are host arrays
+ * or NULL for the identity */
+CSB200_API int csb200_permute(const csb200_mat *A, const csi *pinv, const csi *q, int values, csb200_mat **C);
+/* cs_symperm (csparse.py:2220-2255): C = P A P' using the upper triangular part of a symmetric A;
+ * stable radix sort on max(pinv[i], pinv[j]) */
+CSB200_API int csb200_symperm(const csb200_mat *A, const csi *pinv, int values, csb200_mat **C);
+
 #ifdef __cplusplus
 }
 #endif

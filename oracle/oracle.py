@@ -66,6 +66,10 @@ def lib():
         L.orc_dupl.argtypes = [C.c_int32, C.c_int32, _i32p, _i32p, _f64p]
         L.orc_fkeep.restype = C.c_int64
         L.orc_fkeep.argtypes = [C.c_int32, _i32p, _i32p, _f64p, C.c_int, C.c_double]
+        L.orc_permute.restype = C.c_int
+        L.orc_permute.argtypes = [C.c_int32, _i32p, _i32p, _f64p, _i32p, _i32p, _i32p, _i32p, _f64p]
+        L.orc_symperm.restype = C.c_int64
+        L.orc_symperm.argtypes = [C.c_int32, _i32p, _i32p, _f64p, _i32p, _i32p, _i32p, _f64p]
         _lib = L
     return _lib
 
@@ -216,6 +220,38 @@ def cs_fkeep(A: OMat, mode: str, tol: float = 0.0) -> int:
         A.x = A.x[:nz].copy()
     A.nzmax = nz
     return nz
+
+
+def cs_permute(A: OMat, pinv, q, values=True) -> Optional[OMat]:
+    """C = P A Q (csparse.py:1666-1693)."""
+    if A is None or A.nz != -1:
+        return None
+    nnz = A.nnz
+    nzmax = max(nnz, 1)
+    pinv = None if pinv is None else np.ascontiguousarray(pinv, np.int32)
+    q = None if q is None else np.ascontiguousarray(q, np.int32)
+    Cp = np.zeros(A.n + 1, np.int32)
+    Ci = np.zeros(nzmax, np.int32)
+    Cx = np.zeros(nzmax, np.float64) if (values and A.x is not None) else None
+    rc = lib().orc_permute(A.n, _ip(A.p), _ip(A.i), _fp(A.x if Cx is not None else None),
+                           _ip(pinv), _ip(q), _ip(Cp), _ip(Ci), _fp(Cx))
+    assert rc == 0
+    return OMat(A.m, A.n, Cp, Ci, Cx, nzmax=nzmax, nz=-1)
+
+
+def cs_symperm(A: OMat, pinv, values=True) -> Optional[OMat]:
+    """C = P A P', upper triangular part of a symmetric A (csparse.py:2220-2255)."""
+    if A is None or A.nz != -1:
+        return None
+    nzmax = max(A.nnz, 1)
+    pinv = None if pinv is None else np.ascontiguousarray(pinv, np.int32)
+    Cp = np.zeros(A.n + 1, np.int32)
+    Ci = np.zeros(nzmax, np.int32)
+    Cx = np.zeros(nzmax, np.float64) if (values and A.x is not None) else None
+    tot = lib().orc_symperm(A.n, _ip(A.p), _ip(A.i), _fp(A.x if Cx is not None else None),
+                            _ip(pinv), _ip(Cp), _ip(Ci), _fp(Cx))
+    assert tot >= 0
+    return OMat(A.n, A.n, Cp, Ci, Cx, nzmax=nzmax, nz=-1)
 
 
 def make_sym(A: OMat) -> OMat:

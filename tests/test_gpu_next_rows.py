@@ -1,0 +1,238 @@
+"""GPU parity of the rows either side of the hot path: cs_compress, cs_add,
+cs_norm, cs_dupl, cs_fkeep (cs_dropzeros / cs_droptol / off-diagonal), cs_permute, cs_symperm --
+through the C ABI, against the CPU oracle and the golden vectors made from the unmodified
+reference.  Everything here is index / copy work or the reference's own summation order:
+the bar is bit-exact p, i, x."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import csparse_cuda as cc
+from oracle import oracle as orc
+from tests.golden_util import ALL, FIXTURES, GOLDEN, KNOWN, KNOWN_SYM, Golden
+from tests.test_gpu_parity import as_omat, assert_same_matrix, to_cs
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(GOLDEN, "next_rows.json")) as f:
+    NEXT = json.load(f)
+
+
+def perm(n, seed):
+    return np.random.default_rng(seed).permutation(n).astype(np.int32)
+
+
+def pinv_of(p):
+    pinv = np.empty_like(p)
+    pinv[p] = np.arange(len(p), dtype=np.int32)
+    return pinv
+
+
+def triplet(m, n, ti, tj, tx, lists=True):
+    T = cc.cs()
+    T.m, T.n, T.nz, T.nzmax = m, n, len(ti), max(len(ti), 1)
+    if lists:
+        T.i, T.p, T.x = list(map(int, ti)), list(map(int, tj)), None if tx is None else list(map(float, tx))
+    else:
+        T.i, T.p, T.x = np.asarray(ti, np.int32), np.asarray(tj, np.int32), tx
+    return T
+
+
+def check_sha(M, g, what):
+    nnz = int(M.p[M.n])
+    assert (M.m, M.n, nnz) == (g["m"], g["n"], g["nnz"]), what
+    x = None if M.x is None else np.asarray(M.x[:nnz], np.float64)
+    assert (x is not None) == g["has_x"], what
+    assert orc.digest(np.asarray(M.p[: M.n + 1], np.int32), np.asarray(M.i[:nnz], np.int32), x) == g["sha"], what
+    if "nzmax" in g:
+        assert M.nzmax == g["nzmax"] and len(M.i) == g["len_i"], what + " nzmax / list length"
+
+
+# ---- cs_compress ------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_compress_fixtures(name):
+    """cs_load's triplets -> the reference's cs_compress result, bit for bit"""
+    g = Golden(name)
+    t = g.meta["T"]
+    for lists in (True, False):
+        C = cc.cs_compress(triplet(t["m"], t["n"], g.z["T_i"], g.z["T_j"], g.z["T_x"], lists))
+        g.check("A", as_omat(C))
+        assert C.nzmax == g.meta["A"]["nzmax"] and len(C.i) == g.meta["A"]["len_i"]
+
+
+def test_compress_random_unsorted_duplicates():
+    rng = np.random.default_rng(3)
+    for m, n, nz in ((7, 5, 0), (1, 1, 3), (300, 200, 5000), (5000, 70000, 400_000), (40, 3, 300_000)):
+        ti = rng.integers(0, m, nz).astype(np.int32)
+        tj = rng.integers(0, n, nz).astype(np.int32)
+        tx = rng.standard_normal(nz)
+        R = orc.cs_compress(m, n, ti, tj, tx)
+        C = cc.cs_compress(triplet(m, n, ti, tj, tx, lists=False))
+        assert_same_matrix(C, R, f"compress {m}x{n} nz={nz}")
+        Rp = orc.cs_compress(m, n, ti, tj, None)
+        Cp = cc.cs_compress(triplet(m, n, ti, tj, None, lists=False))
+        assert_same_matrix(Cp, Rp, "compress pattern")
+
+
+def test_compress_sentinels_and_bad_indices():
+    A = to_cs(Golden("t1").A())
+    assert cc.cs_compress(A) is None and cc.cs_compress(None) is None
+    with pytest.raises(ValueError):
+        cc.cs_compress(triplet(2, 2, [0, 2], [0, 1], [1.0, 2.0]))
+
+
+# ---- cs_norm ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ALL)
+def test_norm(name):
+    g = Golden(name)
+    A = g.A()
+    v = cc.cs_norm(to_cs(A))
+    assert v == orc.cs_norm(A) == g.meta["A"]["norm1"]
+    if name in KNOWN:
+        assert abs(v - KNOWN[name][1][3]) <= KNOWN[name][1][4]      # csparse_test.py's expected norm
+    P = to_cs(A)
+    P.x = None
+    assert cc.cs_norm(P) == -1 and cc.cs_norm(None) == -1
+
+
+# ---- cs_add -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_add_fixtures(name):
+    g, A = NEXT[name], Golden(name).A()
+    C = cc.cs_add(to_cs(A), to_cs(A), 2.5, -0.75)
+    check_sha(C, g["add_same"], "2.5A - 0.75A")
+    assert_same_matrix(C, orc.cs_add(A, A, 2.5, -0.75), "add vs oracle")
+    if A.m == A.n:
+        AT = cc.cs_transpose(to_cs(A), True)
+        check_sha(cc.cs_add(to_cs(A, lists=False), AT, 1.0, 3.0), g["add_AT"], "A + 3A'")
+
+
+def test_add_sentinels_pattern_and_empty():
+    A = to_cs(Golden("ash219").A())
+    B = to_cs(Golden("t1").A())
+    assert cc.cs_add(A, B, 1, 1) is None and cc.cs_add(None, B, 1, 1) is None
+    P = to_cs(Golden("t1").A())
+    P.x = None
+    C = cc.cs_add(P, B, 1.0, 2.0)
+    Pn = Golden("t1").A()
+    Pn.x = None
+    assert_same_matrix(C, orc.cs_add(Pn, Golden("t1").A(), 1.0, 2.0), "pattern + values -> pattern")
+    E = cc.cs()
+    E.m, E.n, E.nz, E.nzmax, E.p, E.i, E.x = 3, 2, -1, 1, [0, 0, 0], [0], [0.0]
+    Z = cc.cs_add(E, E, 1.0, 1.0)
+    assert (Z.m, Z.n, Z.p, Z.nzmax, Z.i, Z.x) == (3, 2, [0, 0, 0], 1, [0], [0.0])
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_reference_flow_on_device(name):
+    """CSparseTest1's flow (csparse_test.py:235-266) with every step on the GPU and the matrices
+    staying in HBM: compress, transpose, multiply, norm, add -- against the reference's own
+    expected values (csparse_test.py:269-426) and its recorded D."""
+    g = Golden(name)
+    t = g.meta["T"]
+    _, (m, n, nnz, nrm, d), (nrmT, dT), (nnzD, nrmD, dD_tol) = KNOWN[name]
+    dA = cc.compress_device(triplet(t["m"], t["n"], g.z["T_i"], g.z["T_j"], g.z["T_x"], lists=False))
+    assert (dA.m, dA.n, dA.nnz) == (m, n, nnz) and abs(cc.cs_norm(dA) - nrm) <= d
+    dAT = cc.cs_transpose(dA, True)
+    assert abs(cc.cs_norm(dAT) - nrmT) <= dT
+    dC = cc.cs_multiply(dA, dAT)
+    mm = dA.m
+    eye = triplet(mm, mm, np.arange(mm), np.arange(mm), np.ones(mm), lists=False)
+    dEye = cc.compress_device(eye)
+    dD = cc.cs_add(dC, dEye, 1, cc.cs_norm(dC))
+    assert dD.nnz == nnzD and abs(cc.cs_norm(dD) - nrmD) <= dD_tol
+    g.check("D", as_omat(dD.download()))
+
+
+# ---- cs_dupl -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ALL)
+def test_dupl(name):
+    g = Golden(name)
+    A = to_cs(g.A())
+    assert cc.cs_dupl(A) is True
+    g.check("Adupl", as_omat(A))
+    assert A.nzmax == g.meta["Adupl"]["nzmax"] and len(A.i) == g.meta["Adupl"]["len_i"]
+
+
+def test_dupl_many_duplicates():
+    rng = np.random.default_rng(5)
+    m, n, nz = 50, 400, 60_000
+    R = orc.cs_compress(m, n, rng.integers(0, m, nz), rng.integers(0, n, nz), rng.standard_normal(nz))
+    A = to_cs(R, lists=False)
+    assert orc.cs_dupl(R) and cc.cs_dupl(A)
+    assert_same_matrix(A, R, "dupl")
+    assert cc.cs_dupl(None) is False
+
+
+# ---- cs_fkeep -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_drop(name):
+    g, A0 = NEXT[name], Golden(name).A()
+    A = to_cs(A0)
+    assert cc.cs_dropzeros(A) == g["dropzeros_ret"]
+    check_sha(A, g["dropzeros"], "dropzeros")
+    A = to_cs(A0, lists=False)
+    assert cc.cs_droptol(A, g["droptol_tol"]) == g["droptol_ret"]
+    check_sha(A, g["droptol"], "droptol")
+    R = A0.copy()
+    orc.cs_fkeep(R, "dropdiag")
+    A = to_cs(A0)
+    assert cc.cs_fkeep(A, cc.cs_offdiag(), None) == R.nnz
+    assert_same_matrix(A, R, "offdiag")
+    assert cc.cs_fkeep(None, cc.KEEP_NONZERO, None) == -1
+    with pytest.raises(NotImplementedError):
+        cc.cs_fkeep(to_cs(A0), cc.cs_ifkeep(), None)
+
+
+@pytest.mark.parametrize("name", ["bcsstk01", "bcsstk16"])
+def test_make_sym(name):
+    """csparse_test.py:115-121: C = A + triu(A',1) -- transpose, drop the diagonal, add"""
+    g = Golden(name)
+    dA = cc.upload(to_cs(g.A(), lists=False))
+    dAT = cc.fkeep_device(cc.cs_transpose(dA, True), cc.KEEP_OFFDIAG)
+    dS = cc.cs_add(dA, dAT, 1, 1)
+    S = dS.download()
+    g.check("S", as_omat(S))
+    nnz, nrm = KNOWN_SYM[name]
+    assert dS.nnz == nnz and cc.cs_norm(dS) == nrm          # csparse_test.py:505/525
+    g.check("ST", as_omat(cc.cs_transpose(dS, True).download()))
+
+
+# ---- cs_permute / cs_symperm ----------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_permute_symperm(name):
+    g, A = NEXT[name], Golden(name).A()
+    p = perm(A.m, 11)
+    pinv = cc.cs_pinv(p.tolist(), A.m)
+    assert orc.digest(np.array(pinv, np.int32)) == g["pinv_sha"]
+    q = perm(A.n, 12)
+    C = cc.cs_permute(to_cs(A), pinv, q.tolist(), True)
+    check_sha(C, g["permute"], "permute")
+    check_sha(cc.cs_permute(to_cs(A, lists=False), None, q, False), g["permute_pattern_q_only"], "permute pattern")
+    assert_same_matrix(cc.cs_permute(to_cs(A), pinv, None, True), orc.cs_permute(A, pinv_of(p), None, True), "P A")
+    if A.m == A.n:
+        check_sha(cc.cs_symperm(to_cs(A), pinv, True), g["symperm"], "symperm")
+        check_sha(cc.cs_symperm(to_cs(A), None, False), g["symperm_identity_pattern"], "symperm identity")
+    assert cc.cs_permute(None, None, None, True) is None and cc.cs_symperm(None, None, True) is None
+    with pytest.raises(ValueError):
+        cc.cs_permute(to_cs(A), [A.m] * A.m, None, True)
+
+
+def test_symperm_larger():
+    from csparse_cuda import synth
+    m, n, p, i, x = synth.lap2d(150)
+    A = orc.csc(m, n, p, i, x)
+    pinv = pinv_of(perm(n, 3))
+    R = orc.cs_symperm(A, pinv, True)
+    C = cc.cs_symperm(to_cs(A, lists=False), pinv, True)
+    assert_same_matrix(C, R, "symperm lap2d")
+    R2 = orc.cs_permute(A, pinv, perm(n, 4), True)
+    assert_same_matrix(cc.cs_permute(to_cs(A, lists=False), pinv, perm(n, 4), True), R2, "permute lap2d")
