@@ -26,7 +26,7 @@ namespace csb {
 
 constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_EPT = 8;                       // entries per thread
+constexpr int RS_EPT = 16;                      // entries per thread
 constexpr int RS_TILE = RS_THREADS * RS_EPT;    // 4096 entries per tile
 constexpr int RS_SEG = 32 * RS_EPT;             // consecutive entries owned by one warp
 constexpr int RS_BINS = 256;
@@ -98,6 +98,10 @@ k_rs_pass(long long nnz, int shift,
     using Rec = typename std::conditional<VALUES, RsRec, RsRecP>::type;
     __shared__ int cnt[RS_WARPS][RS_BINS];
     __shared__ long long gbase[RS_BINS];
+    __shared__ int toff[RS_BINS];
+    __shared__ int wtot[RS_BINS / 32];
+    __shared__ unsigned short perm[RS_TILE];
+    __shared__ unsigned char sdig[RS_TILE];
     __shared__ unsigned s_tile;
     __shared__ int s_col[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -140,11 +144,13 @@ k_rs_pass(long long nnz, int shift,
     __syncthreads();
 
     // ---- tile counts -> look-back -> global base of every digit ---------------------------
+    int my_total = 0;
     if (tid < RS_BINS) {
         const int d = tid;
         int sum = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) { const int c = cnt[w][d]; cnt[w][d] = sum; sum += c; }
+        my_total = sum;
         volatile unsigned long long *mine = status + (size_t)tile * RS_BINS + d;
         long long prefix = 0;
         if (tile == 0) {
@@ -162,33 +168,59 @@ k_rs_pass(long long nnz, int shift,
         }
         gbase[d] = (long long)digit_start[d] + prefix;
     }
+    // first slot of every digit inside the tile's own sorted order (exclusive scan of the totals)
+    {
+        int inc = my_total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (tid < RS_BINS && lane == 31) wtot[wid] = inc;
+        __syncthreads();
+        if (tid < RS_BINS) {
+            int before = inc - my_total;
+            for (int w = 0; w < wid; w++) before += wtot[w];
+            toff[tid] = before;
+        }
+    }
     __syncthreads();
 
-    // ---- scatter: payloads are loaded now, every entry goes to its slot of this pass --------
-    const int j_lo = SRC == 2 ? s_col[0] : 0, j_hi = SRC == 2 ? s_col[1] : 0;
+    // ---- the tile's permutation goes through shared memory so that consecutive threads write
+    //      consecutive slots of a digit's run (full sectors / bursts instead of 16-byte shards)
 #pragma unroll
     for (int u = 0; u < RS_EPT; u++) {
-        const long long e = seg + u * 32 + lane;
         if (key[u] < 0) continue;
         const int d = (key[u] >> shift) & (RS_BINS - 1);
-        const long long pos = gbase[d] + cnt[wid][d] + rank[u];
-        int a;
+        const int tpos = toff[d] + cnt[wid][d] + rank[u];
+        perm[tpos] = (unsigned short)(wid * RS_SEG + u * 32 + lane);
+        sdig[tpos] = (unsigned char)d;
+    }
+    __syncthreads();
+    const int tile_n = (int)min((long long)RS_TILE, nnz - base);
+    const int j_lo = SRC == 2 ? s_col[0] : 0, j_hi = SRC == 2 ? s_col[1] : 0;
+#pragma unroll
+    for (int k = 0; k < RS_EPT; k++) {
+        const int tpos = k * RS_THREADS + tid;
+        if (tpos >= tile_n) continue;
+        const long long e = base + perm[tpos];
+        const int d = sdig[tpos];
+        const long long pos = gbase[d] + (tpos - toff[d]);
+        int kk, a;
         double v = 0.0;
         if (SRC == 1) {
             const Rec r = rin[e];
-            a = r.a;
+            kk = r.key; a = r.a;
             if constexpr (VALUES) v = r.v;
         } else {
+            kk = key_in[e];
             a = SRC == 2 ? upper_row(Ap, j_lo, j_hi, (int)e) : a_in[e];
             if (VALUES) v = v_in[e];
         }
         if (DST == 1) {
             Rec r;
-            r.key = key[u]; r.a = a;
+            r.key = kk; r.a = a;
             if constexpr (VALUES) r.v = v;
             reinterpret_cast<Rec *>(rec_out)[pos] = r;
         } else {
-            key_out[pos] = key[u];
+            key_out[pos] = kk;
             a_out[pos] = a;
             if (VALUES) v_out[pos] = v;
         }
