@@ -62,6 +62,37 @@ int spmv_build_plan(csb200_mat *AT);
 void spmv_plan_free(SpmvPlan *pl);
 int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out);
 int spmv_plan_kind(const SpmvPlan *pl);
+int spmv_rows_align(csb200_mat *AT, int *align);
+int spmv_run_rows(csb200_mat *AT, const double *d_x, double *d_y, int ra, int rb, cudaStream_t s);
+
+// copy streams and events of the chunked host pipeline of csb200_gaxpy, one set per thread
+struct HostPipe {
+    static constexpr int MAX_CHUNKS = 8;
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t start = nullptr, xdone = nullptr, end = nullptr, up[MAX_CHUNKS] = {}, done[MAX_CHUNKS] = {};
+    int device = -1;
+    int init()
+    {
+        int dev = 0;
+        CSB_CUDA(cudaGetDevice(&dev));
+        if (device == dev) return CSB200_OK;
+        CSB_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        CSB_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        cudaEvent_t *all[] = {&start, &xdone, &end};
+        for (cudaEvent_t *e : all) CSB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (int c = 0; c < MAX_CHUNKS; c++) {
+            CSB_CUDA(cudaEventCreateWithFlags(&up[c], cudaEventDisableTiming));
+            CSB_CUDA(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+        }
+        device = dev;
+        return CSB200_OK;
+    }
+};
+static HostPipe &host_pipe()
+{
+    static thread_local HostPipe hp;
+    return hp;
+}
 
 // p[0] == 0, p non-decreasing, 0 <= i < m
 __global__ void k_validate(int m, int n, const csi *__restrict__ p, const csi *__restrict__ i, long long nnz, int *bad)
@@ -414,6 +445,42 @@ int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
     CSB_TRY(d_x.alloc((size_t)A->n));
     CSB_TRY(d_y.alloc((size_t)A->m));
     cudaStream_t s = stream();
+    // Large row-stream matrices: y travels in row chunks on two copy streams, so the D2H of a
+    // finished chunk overlaps the H2D of the next ones (PCIe is full duplex) and the SpMV of a
+    // chunk starts as soon as its slice of y has landed.  x must be complete before any row.
+    int align = 0;
+    if (A->m >= (1 << 20)) {
+        CSB_TRY(ensure_csr(A));
+        CSB_TRY(spmv_rows_align(A->csr, &align));
+    }
+    if (align > 0) {
+        HostPipe &hp = host_pipe();
+        CSB_TRY(hp.init());
+        const int m = A->m;
+        int rows = (m + HostPipe::MAX_CHUNKS - 1) / HostPipe::MAX_CHUNKS;
+        rows = ((rows + align - 1) / align) * align;
+        CSB_CUDA(cudaEventRecord(hp.start, s));                      // d_x / d_y exist, earlier work is done
+        CSB_CUDA(cudaStreamWaitEvent(hp.h2d, hp.start, 0));
+        CSB_CUDA(cudaMemcpyAsync(d_x.ptr, x, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, hp.h2d));
+        CSB_CUDA(cudaEventRecord(hp.xdone, hp.h2d));
+        CSB_CUDA(cudaStreamWaitEvent(s, hp.xdone, 0));
+        int c = 0;
+        for (int ra = 0; ra < m; ra += rows, c++) {
+            const int rb = ra + rows < m ? ra + rows : m;
+            const size_t bytes = (size_t)(rb - ra) * sizeof(double);
+            CSB_CUDA(cudaMemcpyAsync(d_y.ptr + ra, y + ra, bytes, cudaMemcpyHostToDevice, hp.h2d));
+            CSB_CUDA(cudaEventRecord(hp.up[c], hp.h2d));
+            CSB_CUDA(cudaStreamWaitEvent(s, hp.up[c], 0));
+            CSB_TRY(spmv_run_rows(A->csr, d_x.ptr, d_y.ptr, ra, rb, s));
+            CSB_CUDA(cudaEventRecord(hp.done[c], s));
+            CSB_CUDA(cudaStreamWaitEvent(hp.d2h, hp.done[c], 0));
+            CSB_CUDA(cudaMemcpyAsync(y + ra, d_y.ptr + ra, bytes, cudaMemcpyDeviceToHost, hp.d2h));
+        }
+        CSB_CUDA(cudaEventRecord(hp.end, hp.d2h));
+        CSB_CUDA(cudaStreamWaitEvent(s, hp.end, 0));                 // the buffers are freed on s after the last copy
+        CSB_CUDA(cudaStreamSynchronize(hp.d2h));
+        return CSB200_OK;
+    }
     if (A->n > 0) CSB_CUDA(cudaMemcpyAsync(d_x.ptr, x, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, s));
     if (A->m > 0) CSB_CUDA(cudaMemcpyAsync(d_y.ptr, y, (size_t)A->m * sizeof(double), cudaMemcpyHostToDevice, s));
     CSB_TRY(csb200_gaxpy_dev(A, d_x.ptr, d_y.ptr));

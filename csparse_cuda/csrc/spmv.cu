@@ -479,6 +479,33 @@ int spmv_run(csb200_mat *AT, const double *d_x, double *d_y)
     return CSB200_OK;
 }
 
+// Rows [ra, rb) only, for the chunked host pipeline of csb200_gaxpy: possible when the plan is
+// the row-stream kernel (row blocks are independent) and ra is a multiple of the plan's block
+// height.  *align receives that height.
+int spmv_rows_align(csb200_mat *AT, int *align)
+{
+    CSB_TRY(spmv_build_plan(AT));
+    *align = AT->plan->kind == 1 ? AT->plan->rows_per_cta : 0;
+    return CSB200_OK;
+}
+
+int spmv_run_rows(csb200_mat *AT, const double *d_x, double *d_y, int ra, int rb, cudaStream_t s)
+{
+    SpmvPlan *pl = AT->plan;
+    if (!pl || pl->kind != 1 || ra % pl->rows_per_cta != 0) return set_error(CSB200_ERR_ARG, "spmv_run_rows: bad range");
+    if (rb <= ra) return CSB200_OK;
+    const int R = pl->rows_per_cta;
+    const int nblocks = ceil_div(rb - ra, R);
+    int dev = 0, sms = 0;
+    CSB_CUDA(cudaGetDevice(&dev));
+    CSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+    k_spmv_tma<<<min(nblocks, 2 * sms), TS_THREADS, TS_SMEM, s>>>(rb - ra, nblocks, R, AT->p + ra, AT->i, AT->x,
+                                                                   d_x, d_y + ra);
+    CSB_LAUNCHED();
+    return CSB200_OK;
+}
+
 }  // namespace csb
 
 namespace csb {
