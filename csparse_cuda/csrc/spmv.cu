@@ -34,7 +34,14 @@ constexpr int SP_THREADS = 512;
 constexpr int SP_TILE = 4096;          // products parked per CTA (32 KB)
 
 constexpr int MP_THREADS = 256;
-constexpr int MP_ITEMS = 8;
+#ifndef MP_ITEMS_DEF
+#define MP_ITEMS_DEF 7
+#endif
+#ifndef MP_MINB
+#define MP_MINB 5
+#endif
+constexpr int MP_ITEMS = MP_ITEMS_DEF;                      // odd: the threads' runs of products start 56 B apart, so the
+                                                 // 16 lanes of a 64-bit shared-memory phase hit 16 bank pairs
 constexpr int MP_TILE = MP_THREADS * MP_ITEMS;   // merge items per CTA
 
 // Products of the slice [base, base+cnt) of (col, val) with x, into prods[0..cnt).
@@ -285,13 +292,14 @@ __global__ void k_merge_partition(const csi *__restrict__ rowptr, int m, int nnz
     part[c] = merge_search(rowptr + 1, m, nnz, (int)d, 0);
 }
 
-__global__ void __launch_bounds__(MP_THREADS)
+__global__ void __launch_bounds__(MP_THREADS, MP_MINB)
 k_spmv_merge(int m, int nnz, const csi *__restrict__ rowptr, const csi *__restrict__ col,
              const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
              const int *__restrict__ part, int *__restrict__ carry_row, double *__restrict__ carry_val)
 {
-    __shared__ double prods[MP_TILE + MP_TILE / 8];
-    __shared__ double rowsum[MP_TILE];
+    // products of the tile's nb nonzeros at the front, row sums of its na finished rows at the
+    // back of one buffer: na + nb <= MP_TILE, so they never meet (22 KB per CTA: 8 CTAs per SM)
+    __shared__ double prods[MP_TILE];
     __shared__ int re[MP_TILE + 1];          // row ends, local nnz coordinates
     __shared__ int ckey[MP_THREADS];
     __shared__ double cval[MP_THREADS];
@@ -304,9 +312,10 @@ k_spmv_merge(int m, int nnz, const csi *__restrict__ rowptr, const csi *__restri
     const int b0 = d0 - a0, b1 = d1 - a1;
     const int na = a1 - a0;                  // rows completed in this tile
     const int nb = b1 - b0;                  // nonzeros consumed in this tile
+    double *rowsum = prods + (MP_TILE - na);
 
     for (int k = threadIdx.x; k < na; k += MP_THREADS) re[k] = rowptr[a0 + k + 1] - b0;
-    stream_products<MP_THREADS, true>(col, val, x, b0, nb, prods);
+    stream_products<MP_THREADS>(col, val, x, b0, nb, prods);
     __syncthreads();
 
     // per-thread run of MP_ITEMS merge items
@@ -319,7 +328,7 @@ k_spmv_merge(int m, int nnz, const csi *__restrict__ rowptr, const csi *__restri
     for (int it = 0; it < MP_ITEMS; it++) {
         if (a + b < items) {
             if (a < na && re[a] <= b) { rowsum[a] = run; run = 0.0; a++; }
-            else                      { run = __dadd_rn(run, prods[b + (b >> 3)]); b++; }
+            else                      { run = __dadd_rn(run, prods[b]); b++; }
         }
     }
     // carries: thread t was still accumulating row `a` when its items ran out.  Keys are
