@@ -386,6 +386,11 @@ def cs_add(A, B, alpha, beta):
     return _padded(dC, nzmax)
 
 
+def force_add_path(path: Optional[str]):
+    """Tests: None / "auto" = automatic, "spgemm" = cs_add always on the SpGEMM kernels."""
+    _lib.check(_lib.lib().csb200_add_force_path({None: 0, "auto": 0, "spgemm": 1}[path]))
+
+
 def cs_norm(A):
     """1-norm of a sparse matrix = largest column sum of |x| (csparse.py:1647-1663).
     -1 if A is not compressed-column or has no values."""

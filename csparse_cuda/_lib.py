@@ -54,6 +54,7 @@ PROTOTYPES = {
     "csb200_multiply": (C.c_int, [mat_t, mat_t, matp]),
     "csb200_multiply_last_flops": (C.c_int64, []),
     "csb200_add": (C.c_int, [mat_t, mat_t, C.c_double, C.c_double, matp]),
+    "csb200_add_force_path": (C.c_int, [C.c_int]),
     "csb200_norm": (C.c_int, [mat_t, f64p]),
     "csb200_compress": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, matp]),
     "csb200_compress_dev": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, matp]),

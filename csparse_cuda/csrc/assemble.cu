@@ -22,6 +22,8 @@
 namespace csb {
 
 int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out);
+int mat_is_canonical(csb200_mat *A, int *out);
+int g_add_force_spgemm = 0;          // tests: send cs_add through the SpGEMM kernels even for canonical operands
 int mat_alloc(csi m, csi n, long long nnz, bool has_x, csb200_mat **out);
 
 // ---- small builders ------------------------------------------------------------------
@@ -52,6 +54,92 @@ __global__ void k_identity(int n, csi *__restrict__ p, csi *__restrict__ i, doub
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) { p[j] = j; i[j] = j; x[j] = 1.0; }
     if (j == n) p[n] = n;
+}
+
+// ---- cs_add on canonical operands ---------------------------------------------------------
+// When every column of A and of B is strictly increasing (no duplicates), column j of
+// alpha*A + beta*B is A(:,j) in order followed by the rows of B(:,j) that A(:,j) lacks, in
+// order (that is what the two cs_scatter calls of csparse.py:186-187 discover), with values
+// alpha*a, alpha*a + beta*b, beta*b -- each product rounded, then the sum.  Membership is a
+// binary search in the sorted column of A.  G = 1: one thread per column (short columns);
+// G = 32: one warp per column.
+template <int G>
+__device__ __forceinline__ int add_find(const csi *__restrict__ Ai, int lo, int hi, int r)
+{
+    while (lo < hi) {                        // first position in [lo, hi) with Ai[pos] >= r
+        const int mid = (lo + hi) >> 1;
+        if (Ai[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+k_add_count(int n, const csi *__restrict__ Ap, const csi *__restrict__ Ai,
+            const csi *__restrict__ Bp, const csi *__restrict__ Bi, int *__restrict__ cnt)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = t / G, lane = t % G;
+    if (j >= n) return;
+    const int a0 = Ap[j], a1 = Ap[j + 1], b0 = Bp[j], b1 = Bp[j + 1];
+    int fresh = 0;
+    for (int q = b0 + lane; q < b1; q += G) {
+        const int r = Bi[q];
+        const int pos = add_find<G>(Ai, a0, a1, r);
+        fresh += !(pos < a1 && Ai[pos] == r);
+    }
+    if (G == 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
+    }
+    if (lane == 0) cnt[j] = (a1 - a0) + fresh;
+}
+
+template <int G, bool VALUES>
+__global__ void __launch_bounds__(256)
+k_add_fill(int n, double alpha, double beta,
+           const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+           const csi *__restrict__ Bp, const csi *__restrict__ Bi, const double *__restrict__ Bx,
+           const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = t / G, lane = t % G;
+    if (j >= n) return;
+    const int a0 = Ap[j], a1 = Ap[j + 1], b0 = Bp[j], b1 = Bp[j + 1];
+    const int c0 = Cp[j];
+    for (int q = a0 + lane; q < a1; q += G) {
+        Ci[c0 + (q - a0)] = Ai[q];
+        if (VALUES) Cx[c0 + (q - a0)] = __dmul_rn(alpha, Ax[q]);
+    }
+    if (G == 32) __syncwarp();
+    int out = c0 + (a1 - a0);                                   // next free slot (uniform in a warp)
+    for (int q0 = b0; q0 < b1; q0 += G) {
+        const int q = q0 + lane;
+        const bool valid = q < b1;
+        int r = 0, pos = a1;
+        bool found = false;
+        if (valid) {
+            r = Bi[q];
+            pos = add_find<G>(Ai, a0, a1, r);
+            found = pos < a1 && Ai[pos] == r;
+        }
+        const double bv = (VALUES && valid) ? __dmul_rn(beta, Bx[q]) : 0.0;
+        if (G == 32) {
+            const unsigned fresh = __ballot_sync(0xffffffffu, valid && !found);
+            if (valid) {
+                if (found) { if (VALUES) Cx[c0 + (pos - a0)] = __dadd_rn(Cx[c0 + (pos - a0)], bv); }
+                else {
+                    const int k = out + __popc(fresh & lanemask_lt());
+                    Ci[k] = r;
+                    if (VALUES) Cx[k] = bv;
+                }
+            }
+            out += __popc(fresh);
+        } else if (valid) {
+            if (found) { if (VALUES) Cx[c0 + (pos - a0)] = __dadd_rn(Cx[c0 + (pos - a0)], bv); }
+            else { Ci[out] = r; if (VALUES) Cx[out] = bv; out++; }
+        }
+    }
 }
 
 // ---- cs_norm ---------------------------------------------------------------------------
@@ -207,6 +295,49 @@ int csb200_add(csb200_mat *A, csb200_mat *B, double alpha, double beta, csb200_m
         return set_error(CSB200_ERR_OVERFLOW, "cs_add: nnz(A) + nnz(B) does not fit int32");
     const bool values = A->x && B->x;                                    // csparse.py:180
     cudaStream_t s = stream();
+    int ca = 0, cb = 0;
+    CSB_TRY(mat_is_canonical(A, &ca));
+    CSB_TRY(mat_is_canonical(B, &cb));
+    if (ca && cb && !g_add_force_spgemm) {
+        // both operands sorted without duplicates: membership by binary search, two passes
+        DevBuf<int> cnt;
+        DevBuf<long long> total;
+        DevBuf<int> dmax;
+        CSB_TRY(cnt.alloc((size_t)n + 1));
+        CSB_TRY(total.alloc(1));
+        MatGuard R;
+        csb200_mat *Cm = new csb200_mat();
+        R.m = Cm;
+        Cm->m = m; Cm->n = n; Cm->device = A->device;
+        CSB_TRY(dev_alloc(&Cm->p, (size_t)n + 1 + MAT_PAD));
+        const long long avg = n > 0 ? (A->nnz + B->nnz) / n : 0;
+        const bool warp = avg > 24;                                      // long columns: a warp each
+        if (n > 0) {
+            if (warp) k_add_count<32><<<ceil_div((long long)n * 32, 256), 256, 0, s>>>(n, A->p, A->i, B->p, B->i, cnt.ptr);
+            else      k_add_count<1><<<ceil_div(n, 256), 256, 0, s>>>(n, A->p, A->i, B->p, B->i, cnt.ptr);
+            CSB_LAUNCHED();
+        }
+        CSB_TRY(launch_excl_scan(Cm->p, cnt.ptr, n, total.ptr, nullptr));
+        long long h_total = 0;
+        CSB_CUDA(cudaMemcpyAsync(&h_total, total.ptr, sizeof(h_total), cudaMemcpyDeviceToHost, s));
+        CSB_CUDA(cudaStreamSynchronize(s));
+        Cm->nnz = h_total;
+        const size_t cap = (size_t)(h_total > 0 ? h_total : 1) + MAT_PAD;
+        CSB_TRY(dev_alloc(&Cm->i, cap));
+        if (values) CSB_TRY(dev_alloc(&Cm->x, cap));
+        if (h_total > 0) {
+            const int grid = warp ? ceil_div((long long)n * 32, 256) : ceil_div(n, 256);
+#define ADD_FILL(G, V) k_add_fill<G, V><<<grid, 256, 0, s>>>(n, alpha, beta, A->p, A->i, A->x, B->p, B->i, B->x, \
+                                                            Cm->p, Cm->i, Cm->x)
+            if (warp) { if (values) ADD_FILL(32, true); else ADD_FILL(32, false); }
+            else      { if (values) ADD_FILL(1, true); else ADD_FILL(1, false); }
+#undef ADD_FILL
+            CSB_LAUNCHED();
+        }
+        *C = R.m;
+        R.m = nullptr;
+        return CSB200_OK;
+    }
     MatGuard M, S;
     CSB_TRY(mat_alloc(m, 2 * n, A->nnz + B->nnz, values, &M.m));
     CSB_TRY(mat_alloc(2 * n, n, 2LL * n, values, &S.m));
@@ -221,6 +352,13 @@ int csb200_add(csb200_mat *A, csb200_mat *B, double alpha, double beta, csb200_m
     k_add_rhs<<<ceil_div((long long)n + 1, 256), 256, 0, s>>>(n, alpha, beta, S.m->p, S.m->i, S.m->x);
     CSB_LAUNCHED();
     return multiply_impl(M.m, S.m, C);
+}
+
+int csb200_add_force_path(int path)
+{
+    if (path < 0 || path > 1) return set_error(CSB200_ERR_ARG, "bad cs_add path");
+    g_add_force_spgemm = path;
+    return CSB200_OK;
 }
 
 // ---- cs_norm -----------------------------------------------------------------------------------
@@ -285,6 +423,9 @@ int csb200_dupl(csb200_mat *A, csb200_mat **C)
     if (!A || !C || !A->x) return set_error(CSB200_ERR_ARG, "cs_dupl: null argument or no values");
     *C = nullptr;
     const csi n = A->n;
+    int canon = 0;
+    CSB_TRY(mat_is_canonical(A, &canon));
+    if (canon) return csb200_mat_col_slice(A, 0, n, C);        // strictly increasing columns hold no duplicates
     MatGuard I;
     CSB_TRY(mat_alloc(n, n, n, true, &I.m));
     k_identity<<<ceil_div((long long)n + 1, 256), 256, 0, stream()>>>(n, I.m->p, I.m->i, I.m->x);

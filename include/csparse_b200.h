@@ -126,6 +126,9 @@ CSB200_API int64_t csb200_multiply_last_flops(void);
  * kernels: column order and rounding are the reference's.  C has values iff A and B have.
  * The handle holds exactly nnz(C) entries (the reference over-allocates nnz(A)+nnz(B)). */
 CSB200_API int csb200_add(csb200_mat *A, csb200_mat *B, double alpha, double beta, csb200_mat **C);
+/* cs_add's algorithm: 0 = automatic (sorted duplicate-free operands: binary-search merge kernels,
+ * otherwise the SpGEMM kernels), 1 = always the SpGEMM kernels; for tests */
+CSB200_API int csb200_add_force_path(int path);
 /* cs_norm (csparse.py:1647-1663): largest column sum of |x|, entries added in storage order */
 CSB200_API int csb200_norm(const csb200_mat *A, double *norm);
 /* cs_compress (csparse.py:647-672): triplets (Ti, Tj, Tx or NULL; nz of them, any order,

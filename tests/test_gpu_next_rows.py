@@ -112,6 +112,33 @@ def test_add_fixtures(name):
         check_sha(cc.cs_add(to_cs(A, lists=False), AT, 1.0, 3.0), g["add_AT"], "A + 3A'")
 
 
+@pytest.mark.parametrize("name", FIXTURES)
+def test_add_fixtures_spgemm_path(name):
+    """the same through the SpGEMM kernels ([A B] * [alpha I; beta I]), which canonical operands
+    normally bypass"""
+    cc.force_add_path("spgemm")
+    try:
+        test_add_fixtures(name)
+    finally:
+        cc.force_add_path(None)
+
+
+def test_add_canonical_long_and_short_columns():
+    """sorted duplicate-free operands: thread-per-column and warp-per-column merge kernels"""
+    from csparse_cuda import synth
+    rng = np.random.default_rng(9)
+    for gen in (lambda: synth.lap2d(200), lambda: synth.st27(18), lambda: synth.rmat(12, 40)):
+        m, n, p, i, x = gen()
+        A = orc.csc(m, n, p, i, x)
+        B = orc.cs_transpose(A, True)                      # canonical too, different pattern for rmat
+        for al, be in ((1.0, 1.0), (-2.5, 0.125)):
+            R = orc.cs_add(A, B, al, be)
+            C = cc.cs_add(to_cs(A, lists=False), to_cs(B, lists=False), al, be)
+            assert_same_matrix(C, R, "canonical add")
+        Ap = A.copy(); Ap.x = None
+        assert_same_matrix(cc.cs_add(to_cs(Ap, lists=False), to_cs(B, lists=False), 1, 1), orc.cs_add(Ap, B, 1, 1), "pattern")
+
+
 def test_add_sentinels_pattern_and_empty():
     A = to_cs(Golden("ash219").A())
     B = to_cs(Golden("t1").A())
