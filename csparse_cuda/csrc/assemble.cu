@@ -219,18 +219,23 @@ __global__ void k_perm_lens(int n, const csi *__restrict__ Ap, const csi *__rest
     if (k < n) { const int j = q ? q[k] : k; len[k] = Ap[j + 1] - Ap[j]; }
 }
 
-__global__ void k_perm_copy(int n, long long nnz, const csi *__restrict__ Ap, const csi *__restrict__ Ai,
-                            const double *__restrict__ Ax, const csi *__restrict__ pinv, const csi *__restrict__ q,
-                            const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+// G = 1: one thread per output column (short columns), G = 32: one warp per output column
+template <int G>
+__global__ void __launch_bounds__(256)
+k_perm_copy(int n, const csi *__restrict__ Ap, const csi *__restrict__ Ai,
+            const double *__restrict__ Ax, const csi *__restrict__ pinv, const csi *__restrict__ q,
+            const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nnz) return;
-    const int k = upper_row(Cp, 0, n, (int)t);                   // output column of slot t
+    const int k = (int)(t / G), lane = (int)(t % G);
+    if (k >= n) return;
     const int j = q ? q[k] : k;
-    const int s = Ap[j] + ((int)t - Cp[k]);
-    const int i = Ai[s];
-    Ci[t] = pinv ? pinv[i] : i;
-    if (Cx) Cx[t] = Ax[s];
+    const int s0 = Ap[j], len = Ap[j + 1] - s0, d0 = Cp[k];
+    for (int e = lane; e < len; e += G) {
+        const int i = Ai[s0 + e];
+        Ci[d0 + e] = pinv ? pinv[i] : i;
+        if (Cx) Cx[d0 + e] = Ax[s0 + e];
+    }
 }
 
 __global__ void k_check_range(const csi *__restrict__ v, long long count, int bound, int *bad)
@@ -485,9 +490,14 @@ int csb200_permute(const csb200_mat *A, const csi *pinv, const csi *q, int value
     k_perm_lens<<<ceil_div(n, 256), 256, 0, s>>>(n, A->p, q ? d_q.ptr : nullptr, len.ptr);
     CSB_LAUNCHED();
     CSB_TRY(launch_excl_scan(R.m->p, len.ptr, n, total.ptr, nullptr));
-    k_perm_copy<<<ceil_div(nnz, 256), 256, 0, s>>>(n, nnz, A->p, A->i, has_x ? A->x : nullptr,
-                                                   pinv ? d_pinv.ptr : nullptr, q ? d_q.ptr : nullptr,
-                                                   R.m->p, R.m->i, R.m->x);
+    if (nnz / n > 12)
+        k_perm_copy<32><<<ceil_div((long long)n * 32, 256), 256, 0, s>>>(n, A->p, A->i, has_x ? A->x : nullptr,
+                                                                         pinv ? d_pinv.ptr : nullptr, q ? d_q.ptr : nullptr,
+                                                                         R.m->p, R.m->i, R.m->x);
+    else
+        k_perm_copy<1><<<ceil_div(n, 256), 256, 0, s>>>(n, A->p, A->i, has_x ? A->x : nullptr,
+                                                        pinv ? d_pinv.ptr : nullptr, q ? d_q.ptr : nullptr,
+                                                        R.m->p, R.m->i, R.m->x);
     CSB_LAUNCHED();
     CSB_CUDA(cudaStreamSynchronize(s));                                   // d_pinv / d_q die with this call
     *C = R.m;
