@@ -64,6 +64,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out);
 int spmv_plan_kind(const SpmvPlan *pl);
 int spmv_rows_align(csb200_mat *AT, int *align);
 int spmv_run_rows(csb200_mat *AT, const double *d_x, double *d_y, int ra, int rb, cudaStream_t s);
+int spmv_chunk_maxcol(csb200_mat *AT, int rows, int count, const int **out);
 
 // copy streams and events of the chunked host pipeline of csb200_gaxpy, one set per thread
 struct HostPipe {
@@ -447,7 +448,7 @@ int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
     cudaStream_t s = stream();
     // Large row-stream matrices: y travels in row chunks on two copy streams, so the D2H of a
     // finished chunk overlaps the H2D of the next ones (PCIe is full duplex) and the SpMV of a
-    // chunk starts as soon as its slice of y has landed.  x must be complete before any row.
+    // chunk starts as soon as its slice of y and the part of x it reads have landed.
     int align = 0;
     if (A->m >= (1 << 20)) {
         CSB_TRY(ensure_csr(A));
@@ -459,15 +460,29 @@ int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
         const int m = A->m;
         int rows = (m + HostPipe::MAX_CHUNKS - 1) / HostPipe::MAX_CHUNKS;
         rows = ((rows + align - 1) / align) * align;
+        const int nchunks = (m + rows - 1) / rows;
+        const int *maxcol = nullptr;
+        CSB_TRY(spmv_chunk_maxcol(A->csr, rows, nchunks, &maxcol));
         CSB_CUDA(cudaEventRecord(hp.start, s));                      // d_x / d_y exist, earlier work is done
         CSB_CUDA(cudaStreamWaitEvent(hp.h2d, hp.start, 0));
-        CSB_CUDA(cudaMemcpyAsync(d_x.ptr, x, (size_t)A->n * sizeof(double), cudaMemcpyHostToDevice, hp.h2d));
-        CSB_CUDA(cudaEventRecord(hp.xdone, hp.h2d));
-        CSB_CUDA(cudaStreamWaitEvent(s, hp.xdone, 0));
+        // x goes up in pieces as well, each just before the first row chunk that reads it: a banded
+        // matrix starts computing after 2/8 of x; an unstructured one needs all of x first, as before
+        const long long nx = A->n;
+        const long long xstep = ((nx + nchunks - 1) / nchunks + 1) & ~1LL;
+        long long x_sent = 0;
         int c = 0;
         for (int ra = 0; ra < m; ra += rows, c++) {
             const int rb = ra + rows < m ? ra + rows : m;
             const size_t bytes = (size_t)(rb - ra) * sizeof(double);
+            long long need = (long long)maxcol[c] + 1;               // x[0 .. need) must have landed
+            for (int u = 0; u < c; u++) need = need > maxcol[u] + 1 ? need : maxcol[u] + 1;
+            long long upto = ((need + xstep - 1) / xstep) * xstep;
+            if (upto > nx) upto = nx;
+            if (upto > x_sent) {
+                CSB_CUDA(cudaMemcpyAsync(d_x.ptr + x_sent, x + x_sent, (size_t)(upto - x_sent) * sizeof(double),
+                                         cudaMemcpyHostToDevice, hp.h2d));
+                x_sent = upto;
+            }
             CSB_CUDA(cudaMemcpyAsync(d_y.ptr + ra, y + ra, bytes, cudaMemcpyHostToDevice, hp.h2d));
             CSB_CUDA(cudaEventRecord(hp.up[c], hp.h2d));
             CSB_CUDA(cudaStreamWaitEvent(s, hp.up[c], 0));
@@ -476,8 +491,10 @@ int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
             CSB_CUDA(cudaStreamWaitEvent(hp.d2h, hp.done[c], 0));
             CSB_CUDA(cudaMemcpyAsync(y + ra, d_y.ptr + ra, bytes, cudaMemcpyDeviceToHost, hp.d2h));
         }
+        CSB_CUDA(cudaEventRecord(hp.xdone, hp.h2d));
         CSB_CUDA(cudaEventRecord(hp.end, hp.d2h));
-        CSB_CUDA(cudaStreamWaitEvent(s, hp.end, 0));                 // the buffers are freed on s after the last copy
+        CSB_CUDA(cudaStreamWaitEvent(s, hp.xdone, 0));               // the buffers are freed on s after the last copies
+        CSB_CUDA(cudaStreamWaitEvent(s, hp.end, 0));
         CSB_CUDA(cudaStreamSynchronize(hp.d2h));
         return CSB200_OK;
     }

@@ -26,6 +26,9 @@ struct SpmvPlan {
     int *carry_row = nullptr;       // per CTA: row of the unfinished tail
     double *carry_val = nullptr;    // per CTA: its partial sum
     csi max_len = 0;
+    // host pipeline of csb200_gaxpy: largest column index used by each row chunk (cached)
+    int chunk_rows = 0, chunk_count = 0;
+    int chunk_maxcol[8] = {0};
 };
 
 namespace csb {
@@ -495,6 +498,41 @@ int spmv_rows_align(csb200_mat *AT, int *align)
 {
     CSB_TRY(spmv_build_plan(AT));
     *align = AT->plan->kind == 1 ? AT->plan->rows_per_cta : 0;
+    return CSB200_OK;
+}
+
+__global__ void k_chunk_maxcol(const csi *__restrict__ rowptr, const csi *__restrict__ col, int m, int rows,
+                               int *__restrict__ out)
+{
+    // one CTA per (chunk, slice): the entries of chunk c are col[rowptr[c*rows] .. rowptr[min(m,(c+1)*rows)])
+    const int c = blockIdx.y;
+    const int ra = min(m, c * rows), rb = min(m, ra + rows);
+    const long long b = rowptr[ra], e = rowptr[rb];
+    int mx = -1;
+    for (long long k = b + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < e; k += (long long)gridDim.x * blockDim.x)
+        mx = max(mx, col[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(&out[c], mx);
+}
+
+// largest column each chunk of `rows` rows touches (host array of `count` ints, cached in the plan)
+int spmv_chunk_maxcol(csb200_mat *AT, int rows, int count, const int **out)
+{
+    SpmvPlan *pl = AT->plan;
+    if (!pl || count > 8) return set_error(CSB200_ERR_ARG, "spmv_chunk_maxcol: bad arguments");
+    if (pl->chunk_rows != rows || pl->chunk_count != count) {
+        DevBuf<int> d;
+        CSB_TRY(d.alloc(8));
+        CSB_CUDA(cudaMemsetAsync(d.ptr, 0xff, 8 * sizeof(int), stream()));
+        k_chunk_maxcol<<<dim3(148, count), 256, 0, stream()>>>(AT->p, AT->i, AT->n, rows, d.ptr);
+        CSB_LAUNCHED();
+        CSB_CUDA(cudaMemcpyAsync(pl->chunk_maxcol, d.ptr, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+        CSB_CUDA(cudaStreamSynchronize(stream()));
+        pl->chunk_rows = rows;
+        pl->chunk_count = count;
+    }
+    *out = pl->chunk_maxcol;
     return CSB200_OK;
 }
 
