@@ -580,6 +580,49 @@ def extras(a, torch, cc, synth, peak):
         ex["cs_gaxpy rmat 2^24 (merge path)"] = {"ms": ms, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak,
                                                  "nnz": nnz, "GFLOP/s": 2 * nnz / ms / 1e6}
         dA.free()
+        # the rows either side of the hot path, lap2d 4096^2, device-resident
+        m, n, p, i, x = synth.lap2d(4096)
+        nnz = len(i)
+        dA = cc.from_arrays(m, n, p, i, x)
+        dAT = cc.cs_transpose(dA, True)
+
+        def add():
+            hold.clear()
+            hold["c"] = cc.cs_add(dA, dAT, 1.0, 1.0)
+        ms = timed(add, 2, 5)
+        b = 12 * (2 * nnz + hold["c"].nnz) + 12 * (n + 1)
+        ex["cs_add A+A' lap2d 4096^2"] = {"ms": ms, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak}
+        hold.clear(); dAT.free()
+        cols = torch.repeat_interleave(torch.arange(n, dtype=torch.int32, device="cuda"),
+                                       torch.from_numpy(np.diff(p).astype(np.int64)).cuda())
+        perm = torch.randperm(nnz, device="cuda")
+        tj, ti, tx = cols[perm].contiguous(), torch.from_numpy(i).cuda()[perm].contiguous(), \
+            torch.from_numpy(x).cuda()[perm].contiguous()
+        del cols, perm
+        import ctypes as C
+        from csparse_cuda import _lib
+
+        def compress():
+            hold.clear()
+            out = C.c_void_p()
+            _lib.check(_lib.lib().csb200_compress_dev(m, n, nnz, C.c_void_p(ti.data_ptr()), C.c_void_p(tj.data_ptr()),
+                                                      C.c_void_p(tx.data_ptr()), C.byref(out)))
+            hold["c"] = cc.DeviceMatrix(out.value)
+        ms = timed(compress, 2, 5)
+        b = 32 * nnz + 4 * (n + 1)
+        ex["cs_compress lap2d 4096^2 (shuffled triplets, radix path)"] = {"ms": ms, "GB/s": b / ms / 1e6,
+                                                                         "frac_of_peak": b / ms / 1e6 / peak}
+        hold.clear(); dA.free()
+        del ti, tj, tx
+        # CPU baseline of the second headline metric: oracle cs_multiply on a bounded sample
+        from oracle import oracle as orc
+        orc.build()
+        ms_, ns_, ps_, is_, xs_ = synth.st27(48)
+        Ao = orc.csc(ms_, ns_, ps_, is_, xs_)
+        t0 = time.perf_counter()
+        Co = orc.cs_multiply(Ao, Ao)
+        dt = time.perf_counter() - t0
+        ex["cpu_baseline cs_multiply (oracle port, 1 core, st27 48^3 sample)"] = {"s": dt, "nnz(C)/s": Co.nnz / dt}
     except Exception as e:  # secondary numbers never sink the headline
         ex["error"] = repr(e)
     return ex
