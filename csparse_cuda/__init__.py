@@ -320,8 +320,11 @@ def cs_multiply(A, B):
 
     Reference: csparse.py:1608-1642 (inner kernel cs_scatter, :1961-1989).
     Returns None unless both are compressed-column and A.n == B.m.  Structural
-    zeros are kept; the columns of C are in the reference's discovery order;
-    C.x is None when A or B is pattern-only; nzmax == nnz(C) (possibly 0).
+    zeros are kept; C.x is None when A or B is pattern-only; nzmax == nnz(C)
+    (possibly 0).  Host ``cs`` operands: the columns of C are in the reference's
+    discovery order (p, i, x bit-identical on canonical inputs).  Two device
+    matrices: the faster blocked numeric kernel may emit a column's rows block by
+    block (same set of rows, same values; see ``force_multiply_path``).
     """
     if not CS_CSC(A) or not CS_CSC(B):
         return None
@@ -330,7 +333,9 @@ def cs_multiply(A, B):
     dA, ta = _as_device(A)
     dB, tb = (dA, False) if B is A else _as_device(B)
     out = C.c_void_p()
-    _lib.check(_lib.lib().csb200_multiply(dA._h, dB._h, C.byref(out)), "cs_multiply")
+    both_dev = isinstance(A, DeviceMatrix) and isinstance(B, DeviceMatrix)
+    fn = _lib.lib().csb200_multiply if both_dev else _lib.lib().csb200_multiply_ordered
+    _lib.check(fn(dA._h, dB._h, C.byref(out)), "cs_multiply")
     dC = DeviceMatrix(out.value)
     if ta:
         dA.free()
@@ -602,6 +607,12 @@ def gaxpy_host(m, n, Ap, Ai, Ax, x, y):
     def ad(a):
         return C.c_void_p(a) if isinstance(a, int) else _ptr(a)
     _lib.check(_lib.lib().csb200_gaxpy_host(m, n, ad(Ap), ad(Ai), ad(Ax), ad(x), ad(y)), "gaxpy_host")
+
+
+def force_multiply_path(path: Optional[str]):
+    """None / "auto": device-matrix products may use the blocked numeric kernel (rows of a column
+    block by block); "ordered": always the reference's discovery order."""
+    _lib.check(_lib.lib().csb200_multiply_force_path({None: 0, "auto": 0, "ordered": 1}[path]))
 
 
 def last_multiply_flops() -> int:

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "csb200_gaxpy_plan": (C.c_int, [mat_t, intp]),
     "csb200_gaxpy_force_plan": (C.c_int, [mat_t, C.c_int]),
     "csb200_multiply": (C.c_int, [mat_t, mat_t, matp]),
+    "csb200_multiply_ordered": (C.c_int, [mat_t, mat_t, matp]),
+    "csb200_multiply_force_path": (C.c_int, [C.c_int]),
     "csb200_multiply_last_flops": (C.c_int64, []),
     "csb200_add": (C.c_int, [mat_t, mat_t, C.c_double, C.c_double, matp]),
     "csb200_add_force_path": (C.c_int, [C.c_int]),

@@ -57,10 +57,11 @@ int ensure_device()
 // implemented in transpose.cu / spmv.cu / spgemm.cu
 int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out);
 extern int g_force_radix;
+extern int g_multiply_ordered;
 int spmv_run(csb200_mat *AT, const double *d_x, double *d_y);
 int spmv_build_plan(csb200_mat *AT);
 void spmv_plan_free(SpmvPlan *pl);
-int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out);
+int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered);
 int spmv_plan_kind(const SpmvPlan *pl);
 int spmv_rows_align(csb200_mat *AT, int *align);
 int spmv_run_rows(csb200_mat *AT, const double *d_x, double *d_y, int ra, int rb, cudaStream_t s);
@@ -524,7 +525,22 @@ int csb200_multiply(const csb200_mat *A, const csb200_mat *B, csb200_mat **C)
     if (!A || !B || !C) return set_error(CSB200_ERR_ARG, "cs_multiply: null argument");
     *C = nullptr;
     if (A->n != B->m) return set_error(CSB200_ERR_ARG, "cs_multiply: A.n != B.m");   // csparse.py:1618-1619
-    return multiply_impl(const_cast<csb200_mat *>(A), const_cast<csb200_mat *>(B), C);
+    return multiply_impl(const_cast<csb200_mat *>(A), const_cast<csb200_mat *>(B), C, false);
+}
+
+int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B, csb200_mat **C)
+{
+    if (!A || !B || !C) return set_error(CSB200_ERR_ARG, "cs_multiply: null argument");
+    *C = nullptr;
+    if (A->n != B->m) return set_error(CSB200_ERR_ARG, "cs_multiply: A.n != B.m");
+    return multiply_impl(const_cast<csb200_mat *>(A), const_cast<csb200_mat *>(B), C, true);
+}
+
+int csb200_multiply_force_path(int path)
+{
+    if (path < 0 || path > 1) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
+    g_multiply_ordered = path;
+    return CSB200_OK;
 }
 
 int64_t csb200_multiply_last_flops(void) { return tls().last_flops; }

@@ -21,7 +21,7 @@
 
 namespace csb {
 
-int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out);
+int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered);
 int mat_is_canonical(csb200_mat *A, int *out);
 int g_add_force_spgemm = 0;          // tests: send cs_add through the SpGEMM kernels even for canonical operands
 int mat_alloc(csi m, csi n, long long nnz, bool has_x, csb200_mat **out);
@@ -356,7 +356,7 @@ int csb200_add(csb200_mat *A, csb200_mat *B, double alpha, double beta, csb200_m
     }
     k_add_rhs<<<ceil_div((long long)n + 1, 256), 256, 0, s>>>(n, alpha, beta, S.m->p, S.m->i, S.m->x);
     CSB_LAUNCHED();
-    return multiply_impl(M.m, S.m, C);
+    return multiply_impl(M.m, S.m, C, true);
 }
 
 int csb200_add_force_path(int path)
@@ -435,7 +435,7 @@ int csb200_dupl(csb200_mat *A, csb200_mat **C)
     CSB_TRY(mat_alloc(n, n, n, true, &I.m));
     k_identity<<<ceil_div((long long)n + 1, 256), 256, 0, stream()>>>(n, I.m->p, I.m->i, I.m->x);
     CSB_LAUNCHED();
-    return multiply_impl(A, I.m, C);
+    return multiply_impl(A, I.m, C, true);
 }
 
 // ---- cs_fkeep with a fixed predicate -------------------------------------------------------------

@@ -28,6 +28,8 @@
 namespace csb {
 
 constexpr int EMPTY = -1;
+constexpr int BLK_STRIDE = 64;          // (block, mask) pairs kept per column for the blocked numeric kernel
+constexpr int BLK_CAP = 256;            // rows per column the blocked numeric kernel holds
 
 __device__ __forceinline__ unsigned hash_row(int i, int logh)
 {
@@ -156,7 +158,7 @@ k_sym_flat(const int *__restrict__ list, const int *__restrict__ ncols_dev, int 
            const csi *__restrict__ Ap, const csi *__restrict__ blk32, const unsigned *__restrict__ mask32,
            const csi *__restrict__ len32,
            const csi *__restrict__ Bp, const csi *__restrict__ Bi, int *__restrict__ cnt_out,
-           int *__restrict__ ovf_list, int *ovf_count)
+           int *__restrict__ ovf_list, int *ovf_count, int2 *__restrict__ blk_out, int *__restrict__ nblk_out)
 {
     constexpr int H = 1 << LOGH;
     static_assert(H >= CAP + 64 && H <= 65536, "table must never fill");
@@ -231,6 +233,16 @@ k_sym_flat(const int *__restrict__ list, const int *__restrict__ ncols_dev, int 
         }
         __syncwarp();
         const int filled = min(nslots, CAP);
+        if (blk_out) {
+            // the column's (block, mask) set in discovery order, for the blocked numeric kernel
+            const bool keep = !ovf && nslots <= BLK_STRIDE;
+            if (keep)
+                for (int t = lane; t < nslots; t += 32) {
+                    const int sl = slots[t];
+                    blk_out[(size_t)j * BLK_STRIDE + t] = make_int2(keys[sl], (int)masks[sl]);
+                }
+            if (lane == 0 && !ovf) nblk_out[j] = keep ? nslots : -1;
+        }
         for (int t = lane; t < filled; t += 32) { const int sl = slots[t]; keys[sl] = EMPTY; masks[sl] = 0; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
@@ -374,6 +386,129 @@ k_num_warp(const int *__restrict__ list, int ncols,
     }
 }
 
+// ---- numeric on the symbolic phase's block tables, one warp per column ------------------------
+// The symbolic phase leaves the column's pattern as (32-row block, mask) pairs.  With that known,
+// the numeric phase needs no inserts, no first-touch bookkeeping and no ranks: the pairs go back
+// into a small hash set keyed by block, every block gets the offset of its first row (prefix sum
+// of the mask popcounts), and a product for row i lands at base[block] + popc(mask & bits below
+// i).  Per multiply-add that is one probe, one popcount and one accumulate -- about 40 warp
+// instructions per 32 products against 100 for k_num_warp.  Rows of a column come out block by
+// block in the blocks' discovery order, ascending inside a block (not the reference's discovery
+// order; the pattern is the same set, and every value is summed in the reference's sequence).
+// Shared memory per warp: vals[BLK_CAP] doubles, rows[BLK_CAP] ints, slot table {key, mask, base}.
+template <bool VALUES, bool CANON>
+__global__ void __launch_bounds__(256)
+k_num_blocked(const int *__restrict__ list, int ncols,
+              const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+              const csi *__restrict__ Bp, const csi *__restrict__ Bi, const double *__restrict__ Bx,
+              const int2 *__restrict__ blk_in, const int *__restrict__ nblk_in,
+              const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+{
+    constexpr int H = 128, LOGH = 7;                       // >= 2 * BLK_STRIDE slots
+    constexpr int PER_WARP = BLK_CAP * 8 + BLK_CAP * 4 + H * 12;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *base_ptr = sm_raw + (size_t)wid * PER_WARP;
+    double *vals = reinterpret_cast<double *>(base_ptr);
+    int *rows = reinterpret_cast<int *>(base_ptr + BLK_CAP * 8);
+    int *keys = rows + BLK_CAP;                            // H
+    int2 *mb = reinterpret_cast<int2 *>(keys + H);          // H x {mask, base}
+    const int nwarps = gridDim.x * 8;
+    for (int s = lane; s < H; s += 32) keys[s] = EMPTY;
+    __syncwarp();
+    for (int idx = blockIdx.x * 8 + wid; idx < ncols; idx += nwarps) {
+        const int j = list[idx];
+        const int nblk = nblk_in[j];
+        const int out = Cp[j];
+        const int cnt = Cp[j + 1] - out;
+        // ---- the block table: insert (distinct keys), offsets, row list -------------------------
+        int my_slot[BLK_STRIDE / 32];
+        int running = 0;
+#pragma unroll
+        for (int r = 0; r < BLK_STRIDE / 32; r++) {
+            const int t = r * 32 + lane;
+            const bool valid = t < nblk;
+            int2 bm = make_int2(0, 0);
+            if (valid) bm = blk_in[(size_t)j * BLK_STRIDE + t];
+            bool isnew;
+            const int slot = warp_find_or_insert(keys, H - 1, bm.x, valid, hash_row(bm.x, LOGH), isnew);
+            my_slot[r] = valid ? slot : -1;
+            const int c = valid ? __popc((unsigned)bm.y) : 0;
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            const int first = running + inc - c;
+            if (valid) {
+                mb[slot] = make_int2(bm.y, first);
+                unsigned mk = (unsigned)bm.y;
+                int q = first;
+                while (mk) { const int bit = __ffs(mk) - 1; rows[q++] = (bm.x << 5) + bit; mk &= mk - 1; }
+            }
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        // -0.0 is the exact additive identity (-0.0 + x == x bit for bit, also for x == -0.0), so the
+        // first product of a row lands as the reference's first-touch assignment
+        if (VALUES) for (int t = lane; t < cnt; t += 32) vals[t] = -0.0;
+        __syncwarp();
+        // ---- accumulate --------------------------------------------------------------------------
+        if (VALUES) {
+            const int pb_end = Bp[j + 1];
+            for (int pb0 = Bp[j]; pb0 < pb_end; pb0 += 32) {
+                const int my_pb = pb0 + lane;
+                int my_ab = 0, my_ae = 0;
+                double my_beta = 0.0;
+                if (my_pb < pb_end) {
+                    const int k = Bi[my_pb];
+                    my_ab = Ap[k];
+                    my_ae = Ap[k + 1];
+                    my_beta = Bx[my_pb];
+                }
+                const int nb = min(32, pb_end - pb0);
+                for (int s = 0; s < nb; s++) {
+                    const int ab = __shfl_sync(0xffffffffu, my_ab, s);
+                    const int ae = __shfl_sync(0xffffffffu, my_ae, s);
+                    const double beta = __shfl_sync(0xffffffffu, my_beta, s);
+                    for (int pa0 = ab; pa0 < ae; pa0 += 32) {
+                        const int pa = pa0 + lane;
+                        const bool active = pa < ae;
+                        int pos = 0;
+                        double prod = 0.0;
+                        if (active) {
+                            const int i = Ai[pa];
+                            prod = __dmul_rn(beta, Ax[pa]);
+                            const int blk = i >> 5;
+                            unsigned h = hash_row(blk, LOGH);
+                            while (keys[h] != blk) h = (h + 1) & (H - 1);       // present by construction
+                            const int2 e = mb[h];
+                            pos = e.y + __popc((unsigned)e.x & ((1u << (i & 31)) - 1u));
+                        }
+                        if (CANON) {
+                            if (active) vals[pos] = __dadd_rn(vals[pos], prod);  // distinct rows in a step
+                        } else {
+                            unsigned pend = __ballot_sync(0xffffffffu, active);  // duplicates: storage (= lane) order
+                            while (pend) {
+                                const int l = __ffs(pend) - 1;
+                                if (lane == l) vals[pos] = __dadd_rn(vals[pos], prod);
+                                pend &= pend - 1;
+                                __syncwarp();
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        // ---- emit, empty the table -----------------------------------------------------------------
+        for (int t = lane; t < cnt; t += 32) {
+            Ci[out + t] = rows[t];
+            if (VALUES) Cx[out + t] = vals[t];
+        }
+#pragma unroll
+        for (int r = 0; r < BLK_STRIDE / 32; r++) if (my_slot[r] >= 0) keys[my_slot[r]] = EMPTY;
+        __syncwarp();
+    }
+}
+
 // ---- numeric, one CTA per column, dense workspaces in global memory -----------------
 // The reference's algorithm verbatim per column: marks w[m], accumulator x[m]
 // (csparse.py:1624-1626), discovery order by a block-wide rank of the new rows.
@@ -503,7 +638,8 @@ static int ensure_compressed(csb200_mat *A)
 
 template <int LOGH, int CAP, int WARPS, bool OPTIMISTIC>
 static int run_sym_flat(const int *list, const int *ncols_dev, int ncols, const csb200_mat *A,
-                        const csb200_mat *B, int *cnt, int *ovf_list, int *ovf_count)
+                        const csb200_mat *B, int *cnt, int *ovf_list, int *ovf_count,
+                        int2 *blk_out = nullptr, int *nblk_out = nullptr)
 {
     if (!ncols_dev && ncols == 0) return CSB200_OK;
     const size_t smem = (size_t)WARPS * ((size_t)(1 << LOGH) * 8 + CAP * 2);
@@ -513,7 +649,7 @@ static int run_sym_flat(const int *list, const int *ncols_dev, int ncols, const 
     auto kern = k_sym_flat<LOGH, CAP, WARPS, OPTIMISTIC>;
     CSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, WARPS * 32, smem, stream()>>>(list, ncols_dev, ncols, A->p, A->c32_blk, A->c32_mask, A->c32_len,
-                                               B->p, B->i, cnt, ovf_list, ovf_count);
+                                               B->p, B->i, cnt, ovf_list, ovf_count, blk_out, nblk_out);
     CSB_LAUNCHED();
     return CSB200_OK;
 }
@@ -540,9 +676,25 @@ static int run_num_warp(const int *list, int ncols, const csb200_mat *A, const c
     return CSB200_OK;
 }
 
-int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
+// numeric class selection for the blocked kernel: 1 where the symbolic phase kept the column's
+// block list and the column fits BLK_CAP rows; the ordered kernels then skip it (size 0)
+__global__ void k_pick_blocked(int n, const int *__restrict__ nblk, int *__restrict__ size, int *__restrict__ pick)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const bool b = nblk[j] >= 0 && size[j] > 0 && size[j] <= BLK_CAP;
+    pick[j] = b ? 1 : 0;
+    if (b) size[j] = 0;
+}
+
+int g_multiply_ordered = 0;        // csb200_multiply_force_path: 1 = always the reference's discovery order
+
+// ordered: the columns of C must come out in the reference's discovery order (cs_add / cs_dupl are
+// built on that); otherwise the blocked numeric kernel may emit them block by block.
+int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
 {
     const csi m = A->m, n = B->n;
+    if (g_multiply_ordered) ordered = true;
     const bool values = A->x != nullptr && B->x != nullptr;      // csparse.py:1625
     cudaStream_t s = stream();
 
@@ -555,8 +707,11 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
     int canon = 1;
     if ((st = mat_is_canonical(A, &canon)) != CSB200_OK) return fail(st);
 
-    DevBuf<int> ub, cnt, lists, counts, marks, marks_num;
+    DevBuf<int> ub, cnt, lists, counts, marks, marks_num, nblk, pick;
+    DevBuf<int2> blkbuf;
     DevBuf<double> acc;
+    // the blocked numeric path keeps BLK_STRIDE pairs per column (512 B): only while that stays modest
+    const bool blocked = !ordered && n > 0 && (size_t)n * BLK_STRIDE * sizeof(int2) <= ((size_t)4 << 30);
     DevBuf<unsigned long long> flops;
     DevBuf<long long> total;
     const size_t ncap = (size_t)(n > 0 ? n : 1);
@@ -587,10 +742,17 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
         tls().last_flops = (int64_t)h_flops;
         int *ovf_list = lists.ptr + 2 * ncap, *ovf_count = counts.ptr + 2;
         if (h_counts[0] + h_counts[1] > 0) MM_TRY(ensure_compressed(A));
-        MM_TRY((run_sym_flat<9, 256, 8, false>(lists.ptr, nullptr, h_counts[0], A, B, cnt.ptr, nullptr, nullptr)));
+        if (blocked) {
+            MM_TRY(nblk.alloc(ncap));
+            MM_TRY(pick.alloc(ncap));
+            MM_TRY(blkbuf.alloc((size_t)n * BLK_STRIDE));
+            MM_CUDA(cudaMemsetAsync(nblk.ptr, 0xff, ncap * sizeof(int), s));
+        }
+        MM_TRY((run_sym_flat<9, 256, 8, false>(lists.ptr, nullptr, h_counts[0], A, B, cnt.ptr, nullptr, nullptr,
+                                               blkbuf.ptr, nblk.ptr)));
         if (h_counts[1] > 0) {
             MM_TRY((run_sym_flat<9, 256, 8, true>(lists.ptr + ncap, nullptr, h_counts[1], A, B, cnt.ptr,
-                                                  ovf_list, ovf_count)));
+                                                  ovf_list, ovf_count, blkbuf.ptr, nblk.ptr)));
             MM_TRY((run_sym_flat<13, 8000, 2, false>(ovf_list, ovf_count, 0, A, B, cnt.ptr, nullptr, nullptr)));
         }
         if (h_counts[3] > 0) {
@@ -623,6 +785,32 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out)
         // exact sizes: ub[j] = Cp[j+1] - Cp[j]
         k_col_sizes<<<ceil_div(n, 256), 256, 0, s>>>(n, C->p, ub.ptr);
         MM_LAUNCHED();
+        int n_blocked = 0;
+        if (blocked) {
+            // columns whose block list was kept go to the blocked kernel (list 3 region is free here)
+            k_pick_blocked<<<ceil_div(n, 256), 256, 0, s>>>(n, nblk.ptr, ub.ptr, pick.ptr);
+            MM_LAUNCHED();
+            MM_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * sizeof(int), s));
+            k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, pick.ptr, INT_MAX, 1, 1, 1, lists.ptr, counts.ptr);
+            MM_LAUNCHED();
+            MM_CUDA(cudaMemcpyAsync(&n_blocked, counts.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+            MM_CUDA(cudaStreamSynchronize(s));
+            if (n_blocked > 0) {
+                constexpr int smem = 8 * (BLK_CAP * 12 + 128 * 12);
+                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * 6);
+#define BLK_LAUNCH(V, K)                                                                              \
+                do {                                                                                      \
+                    auto kern = k_num_blocked<V, K>;                                                      \
+                    MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+                    kern<<<grid, 256, smem, s>>>(lists.ptr, n_blocked, A->p, A->i, A->x, B->p, B->i, B->x,   \
+                                                 blkbuf.ptr, nblk.ptr, C->p, C->i, C->x);                 \
+                } while (0)
+                if (values) { if (canon) BLK_LAUNCH(true, true); else BLK_LAUNCH(true, false); }
+                else        { if (canon) BLK_LAUNCH(false, true); else BLK_LAUNCH(false, false); }
+#undef BLK_LAUNCH
+                MM_LAUNCHED();
+            }
+        }
         MM_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * sizeof(int), s));
         // numeric classes by exact column size: <=128 | <=512 | <=2048 | dense
         k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, INT_MAX, 128, 512, 2048, lists.ptr, counts.ptr);

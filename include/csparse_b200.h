@@ -118,6 +118,15 @@ CSB200_API int csb200_gaxpy_force_plan(csb200_mat *A, int kind);
  * Columns of C come out in the reference's discovery order.  C has values iff
  * both A and B have. */
 CSB200_API int csb200_multiply(const csb200_mat *A, const csb200_mat *B, csb200_mat **C);
+/* cs_multiply with the rows of every column of C in the reference's discovery order (what the
+ * Python layer uses for host `cs` operands, so that p, i, x equal the reference's bit for bit) */
+CSB200_API int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B, csb200_mat **C);
+/* Order of the rows inside C's columns for csb200_multiply: 0 = automatic -- columns whose pattern fits the blocked
+ * numeric kernel come out block by block (32-row blocks in discovery order, ascending inside a
+ * block), the rest in the reference's discovery order; 1 = always the reference's discovery order
+ * (then p, i, x are bit-identical to cs_multiply on canonical inputs).  The set of rows and every
+ * value are the same either way. */
+CSB200_API int csb200_multiply_force_path(int path);
 /* number of multiply-adds of the last csb200_multiply on this thread */
 CSB200_API int64_t csb200_multiply_last_flops(void);
 

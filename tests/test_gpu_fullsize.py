@@ -51,8 +51,19 @@ def test_c4_st27_multiply():
     A = orc.csc(m, n, p, i, x)
     R = orc.cs_multiply(A, A)
     dA = cc.from_arrays(m, n, p, i, x)
-    cp, ci, cx = cc.cs_multiply(dA, dA).arrays()
     assert R.nnz == (5 * 64 - 6) ** 3
+    # default device path (blocked numeric kernel): the contract -- pattern after canonical sort, values
+    dC = cc.cs_multiply(dA, dA)
+    cp, ci, cx = dC.arrays()
+    Cz, Rz = orc.canonical(orc.csc(m, n, cp, ci, cx)), orc.canonical(R)
+    assert np.array_equal(cp, R.p) and np.array_equal(Cz.i, Rz.i)
+    assert np.array_equal(bits(Cz.x), bits(Rz.x))                          # same summation sequence: bit-equal
+    del dC, Cz, Rz
+    cc.force_multiply_path("ordered")
+    try:
+        cp, ci, cx = cc.cs_multiply(dA, dA).arrays()
+    finally:
+        cc.force_multiply_path(None)
     assert np.array_equal(cp, R.p) and np.array_equal(ci, R.i[:R.nnz])      # discovery order
     assert np.array_equal(bits(cx), bits(R.x[:R.nnz]))
     del R, cp, ci, cx

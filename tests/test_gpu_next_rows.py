@@ -167,13 +167,21 @@ def test_reference_flow_on_device(name):
     assert (dA.m, dA.n, dA.nnz) == (m, n, nnz) and abs(cc.cs_norm(dA) - nrm) <= d
     dAT = cc.cs_transpose(dA, True)
     assert abs(cc.cs_norm(dAT) - nrmT) <= dT
-    dC = cc.cs_multiply(dA, dAT)
     mm = dA.m
     eye = triplet(mm, mm, np.arange(mm), np.arange(mm), np.ones(mm), lists=False)
     dEye = cc.compress_device(eye)
-    dD = cc.cs_add(dC, dEye, 1, cc.cs_norm(dC))
-    assert dD.nnz == nnzD and abs(cc.cs_norm(dD) - nrmD) <= dD_tol
-    g.check("D", as_omat(dD.download()))
+    for path in (None, "ordered"):
+        cc.force_multiply_path(path)
+        try:
+            dC = cc.cs_multiply(dA, dAT)
+        finally:
+            cc.force_multiply_path(None)
+        dD = cc.cs_add(dC, dEye, 1, cc.cs_norm(dC))
+        assert dD.nnz == nnzD and abs(cc.cs_norm(dD) - nrmD) <= dD_tol
+        # the reference's recorded D: bit-identical when C is in discovery order; with the blocked
+        # kernel's row order cs_norm(C) adds the same terms in another sequence, so the shift of the
+        # diagonal may differ in the last bit: same pattern, values within the reference's own delta
+        g.check("D", as_omat(dD.download()), order="exact" if path else "pattern")
 
 
 # ---- cs_dupl -----------------------------------------------------------------------------------

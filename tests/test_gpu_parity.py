@@ -342,9 +342,18 @@ def test_multiply_synthetic_AA(gen):
     A = orc.csc(m, n, p, i, x)
     R = orc.cs_multiply(A, A)
     dA = cc.from_arrays(m, n, p, i, x)
-    C = cc.cs_multiply(dA, dA).download(trim=True)
+    C = cc.cs_multiply(dA, dA).download(trim=True)          # device operands: blocked numeric kernel allowed
     assert_multiply_parity(C, R)
-    assert_same_matrix(C, R, "discovery order")
+    cz, rz = orc.canonical(as_omat(C)), orc.canonical(R)
+    assert np.array_equal(bits(cz.x), bits(rz.x)), "values are summed in the reference's sequence"
+    cc.force_multiply_path("ordered")
+    try:
+        C = cc.cs_multiply(dA, dA).download(trim=True)
+    finally:
+        cc.force_multiply_path(None)
+    assert_same_matrix(C, R, "discovery order")              # stronger than the contract
+    A_host = to_cs(A, lists=False)
+    assert_same_matrix(cc.cs_multiply(A_host, A_host), R, "host operands: reference order")
 
 
 def test_multiply_large_columns_dense_path():
