@@ -29,7 +29,8 @@ namespace csb {
 
 constexpr int EMPTY = -1;
 constexpr int BLK_STRIDE = 64;          // (block, mask) pairs kept per column for the blocked numeric kernel
-constexpr int BLK_CAP = 256;            // rows per column the blocked numeric kernel holds
+constexpr int BLK_CAP = 128;            // rows per column the blocked numeric kernel holds
+constexpr int BLK_LOGH = 8, BLK_H = 1 << BLK_LOGH;   // slots of its block table (>= 4 * BLK_STRIDE: short probes)
 
 __device__ __forceinline__ unsigned hash_row(int i, int logh)
 {
@@ -404,7 +405,7 @@ k_num_blocked(const int *__restrict__ list, int ncols,
               const int2 *__restrict__ blk_in, const int *__restrict__ nblk_in,
               const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
 {
-    constexpr int H = 128, LOGH = 7;                       // >= 2 * BLK_STRIDE slots
+    constexpr int H = BLK_H, LOGH = BLK_LOGH;
     constexpr int PER_WARP = BLK_CAP * 8 + BLK_CAP * 4 + H * 12;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -796,7 +797,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             MM_CUDA(cudaMemcpyAsync(&n_blocked, counts.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
             MM_CUDA(cudaStreamSynchronize(s));
             if (n_blocked > 0) {
-                constexpr int smem = 8 * (BLK_CAP * 12 + 128 * 12);
+                constexpr int smem = 8 * (BLK_CAP * 12 + BLK_H * 12);
                 const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * 6);
 #define BLK_LAUNCH(V, K)                                                                              \
                 do {                                                                                      \
