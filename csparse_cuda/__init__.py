@@ -44,8 +44,8 @@ from ._lib import CSparseCudaError  # noqa: F401
 
 __all__ = ["cs", "CS_CSC", "CS_TRIPLET", "cs_cumsum", "cs_transpose", "cs_gaxpy", "cs_multiply",
            "cs_add", "cs_norm", "cs_compress", "cs_dupl", "cs_fkeep", "cs_dropzeros", "cs_droptol",
-           "cs_permute", "cs_symperm", "cs_pinv", "cs_ifkeep", "KEEP_NONZERO", "KEEP_TOL", "KEEP_OFFDIAG",
-           "KEEP_UPPER", "DeviceMatrix", "upload", "CSparseCudaError"]
+           "cs_permute", "cs_symperm", "cs_pinv", "cs_amd_matrix", "cs_ifkeep", "KEEP_NONZERO", "KEEP_TOL",
+           "KEEP_OFFDIAG", "KEEP_UPPER", "KEEP_SHORTCOL", "DeviceMatrix", "upload", "CSparseCudaError"]
 
 
 class cs(object):
@@ -461,7 +461,7 @@ def dupl_device(A) -> "DeviceMatrix":
     return DeviceMatrix(out.value)
 
 
-KEEP_NONZERO, KEEP_TOL, KEEP_OFFDIAG, KEEP_UPPER = 0, 1, 2, 3
+KEEP_NONZERO, KEEP_TOL, KEEP_OFFDIAG, KEEP_UPPER, KEEP_SHORTCOL = 0, 1, 2, 3, 4
 
 
 class cs_ifkeep(object):
@@ -541,6 +541,42 @@ def cs_droptol(A, tol):
 def cs_dropzeros(A):
     """Removes numerically zero entries (csparse.py:1024-1030)."""
     return cs_fkeep(A, _cs_nonzero(), None)
+
+
+def cs_amd_matrix(order, A):
+    """The matrix cs_amd orders (csparse.py:228-258), pattern only, diagonal dropped:
+    order 1 (and A square): A + A'; order 2: A'A without the dense rows of A (more than
+    max(16, 10*int(sqrt(n))), capped at n-2, entries); order 3: A'A.  None for a non-CSC A or
+    another order.  Built from cs_transpose, cs_fkeep, cs_add and cs_multiply on the GPU; the
+    sequential elimination that follows in cs_amd stays out of scope.  A device matrix in gives a
+    device matrix out (rows of a column in the blocked kernel's order); a host cs gives a host cs
+    whose p and i equal the reference's C bit for bit."""
+    if not CS_CSC(A) or order <= 0 or order > 3:
+        return None
+    host = not isinstance(A, DeviceMatrix)
+    dA, tmp = _as_device(A)
+    mult = (lambda X, Y: DeviceMatrix(_mult_ordered(X, Y))) if host else cs_multiply
+    dAT = cs_transpose(dA, False)
+    m, n = dA.m, dA.n
+    dense = min(n - 2, max(16, 10 * int(np.sqrt(n))))
+    if order == 1 and n == m:
+        dC = cs_add(dA, dAT, 0, 0)                       # pattern only: A' carries no values
+    elif order == 2:
+        dAT2 = fkeep_device(dAT, KEEP_SHORTCOL, float(dense))
+        dA2 = cs_transpose(dAT2, False)
+        dC = mult(dAT2, dA2)
+    else:
+        dC = mult(dAT, dA)
+    dC = fkeep_device(dC, KEEP_OFFDIAG)
+    if tmp:
+        dA.free()
+    return dC.download(trim=True) if host else dC
+
+
+def _mult_ordered(dA, dB):
+    out = C.c_void_p()
+    _lib.check(_lib.lib().csb200_multiply_ordered(dA._h, dB._h, C.byref(out)), "cs_multiply")
+    return out.value
 
 
 def cs_pinv(p, n):

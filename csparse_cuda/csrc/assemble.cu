@@ -160,7 +160,7 @@ __global__ void k_norm1(int n, const csi *__restrict__ Ap, const double *__restr
 }
 
 // ---- cs_fkeep / cs_symperm flags ----------------------------------------------------------
-enum { KEEP_NONZERO = 0, KEEP_TOL = 1, KEEP_OFFDIAG = 2, KEEP_UPPER = 3 };
+enum { KEEP_NONZERO = 0, KEEP_TOL = 1, KEEP_OFFDIAG = 2, KEEP_UPPER = 3, KEEP_SHORTCOL = 4 };
 
 __global__ void k_keep_flags(int n, long long nnz, const csi *__restrict__ Ap, const csi *__restrict__ Ai,
                              const double *__restrict__ Ax, int mode, double tol, int *__restrict__ flag)
@@ -173,7 +173,8 @@ __global__ void k_keep_flags(int n, long long nnz, const csi *__restrict__ Ap, c
         keep = mode == KEEP_NONZERO ? (a != 0.0) : (fabs(a) > tol);
     } else {
         const int j = upper_row(Ap, 0, n, (int)p);               // column holding entry p
-        keep = mode == KEEP_OFFDIAG ? (Ai[p] != j) : (Ai[p] <= j);
+        if (mode == KEEP_SHORTCOL) keep = (double)(Ap[j + 1] - Ap[j]) <= tol;   // cs_amd's dense-column drop (:236-249)
+        else keep = mode == KEEP_OFFDIAG ? (Ai[p] != j) : (Ai[p] <= j);
     }
     flag[p] = keep;
 }
@@ -441,7 +442,7 @@ int csb200_dupl(csb200_mat *A, csb200_mat **C)
 // ---- cs_fkeep with a fixed predicate -------------------------------------------------------------
 int csb200_fkeep(const csb200_mat *A, int predicate, double tol, csb200_mat **C)
 {
-    if (!A || !C || predicate < KEEP_NONZERO || predicate > KEEP_UPPER)
+    if (!A || !C || predicate < KEEP_NONZERO || predicate > KEEP_SHORTCOL)
         return set_error(CSB200_ERR_ARG, "cs_fkeep: bad arguments");
     *C = nullptr;
     const long long nnz = A->nnz;

@@ -150,7 +150,9 @@ CSB200_API int csb200_compress_dev(csi m, csi n, csi nz, const csi *d_Ti, const 
  * SpGEMM kernels; out of place (handles are immutable).  A must have values. */
 CSB200_API int csb200_dupl(csb200_mat *A, csb200_mat **C);
 /* cs_fkeep (csparse.py:1172-1196) with a fixed predicate: 0 keep aij != 0 (cs_dropzeros :1024),
- * 1 keep |aij| > tol (cs_droptol :1007), 2 keep i != j (csparse_test.py Dropdiag), 3 keep i <= j.
+ * 1 keep |aij| > tol (cs_droptol :1007), 2 keep i != j (csparse_test.py Dropdiag, cs_amd's _cs_diag
+ * :207-211), 3 keep i <= j, 4 keep the entries of columns with at most tol entries (cs_amd's
+ * dense-column drop, :236-249).
  * Order inside the columns is kept; out of place. */
 CSB200_API int csb200_fkeep(const csb200_mat *A, int predicate, double tol, csb200_mat **C);
 /* cs_permute (csparse.py:1666-1693): C = P A Q; pinv (m entries) / q (n entries) are host arrays

@@ -41,6 +41,36 @@ def rec(A):
             "has_x": A.x is not None, "sha": digest(p, i, x)}
 
 
+def amd_matrix(order, A):
+    """csparse.py:228-258 line for line, with the reference's own functions"""
+    from math import sqrt
+    AT = ref.cs_transpose(A, False)
+    m, n = A.m, A.n
+    dense = max(16, 10 * int(sqrt(n)))
+    dense = min(n - 2, dense)
+    if order == 1 and n == m:
+        C = ref.cs_add(A, AT, 0, 0)
+    elif order == 2:
+        ATp, ATi = AT.p, AT.i
+        p2 = 0
+        for j in range(m):
+            p = ATp[j]
+            ATp[j] = p2
+            if ATp[j + 1] - p > dense:
+                continue
+            while p < ATp[j + 1]:
+                ATi[p2] = ATi[p]
+                p2 += 1
+                p += 1
+        ATp[m] = p2
+        A2 = ref.cs_transpose(AT, False)
+        C = ref.cs_multiply(AT, A2)
+    else:
+        C = ref.cs_multiply(AT, A)
+    ref.cs_fkeep(C, ref._cs_diag(), None)
+    return C
+
+
 def main():
     out = {}
     for name in FIXTURES:
@@ -70,6 +100,14 @@ def main():
         g["droptol_tol"] = tol
         g["droptol_ret"] = ref.cs_droptol(A2, tol)
         g["droptol"] = rec(A2)
+        for order in (1, 2, 3):
+            Cm = amd_matrix(order, A)
+            r = rec(Cm)
+            p_, i_, _x = arrays(Cm)
+            n_ = len(p_) - 1
+            cols = np.repeat(np.arange(n_, dtype=np.int64), np.diff(p_).astype(np.int64))
+            r["sha_canonical_pattern"] = digest(p_, i_[np.lexsort((i_, cols))])
+            g["amd_matrix_%d" % order] = r
         out[name] = g
         print(name, {k: (v["nnz"] if isinstance(v, dict) else v) for k, v in g.items()})
     with open(OUT, "w") as f:

@@ -254,6 +254,35 @@ def cs_symperm(A: OMat, pinv, values=True) -> Optional[OMat]:
     return OMat(A.n, A.n, Cp, Ci, Cx, nzmax=nzmax, nz=-1)
 
 
+def cs_amd_matrix(order: int, A: OMat) -> Optional[OMat]:
+    """The matrix cs_amd builds before its elimination loop (csparse.py:228-258): pattern of
+    A+A' (order 1, square), A'A without dense rows (order 2) or A'A (order 3), diagonal dropped."""
+    if A is None or A.nz != -1 or order <= 0 or order > 3:
+        return None
+    AT = cs_transpose(A, False)
+    m, n = A.m, A.n
+    dense = min(n - 2, max(16, 10 * int(np.sqrt(n))))           # :233-234
+    if order == 1 and n == m:
+        C = cs_add(A, AT, 0, 0)                                   # :236
+    elif order == 2:
+        lens = np.diff(AT.p[: m + 1])                             # :238-249: drop dense columns of AT
+        keepcol = lens <= dense
+        keep = np.repeat(keepcol, lens)
+        p2 = np.zeros(m + 1, np.int32)
+        np.cumsum(np.where(keepcol, lens, 0), out=p2[1:])
+        i2 = AT.i[: AT.nnz][keep]
+        AT = OMat(AT.m, AT.n, p2, np.ascontiguousarray(i2 if len(i2) else np.zeros(1, np.int32)), None,
+                  nzmax=max(len(i2), 1), nz=-1)
+        A2 = cs_transpose(AT, False)
+        C = cs_multiply(AT, A2)
+    else:
+        C = cs_multiply(AT, A)
+    if C.nnz == 0 and len(C.i) == 0:
+        C.i = np.zeros(1, np.int32)
+    cs_fkeep(C, "dropdiag")                                        # :257
+    return C
+
+
 def make_sym(A: OMat) -> OMat:
     """C = A + triu(A,1)' as in csparse_test.py:115-121."""
     AT = cs_transpose(A, True)

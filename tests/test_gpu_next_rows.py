@@ -271,3 +271,25 @@ def test_symperm_larger():
     assert_same_matrix(C, R, "symperm lap2d")
     R2 = orc.cs_permute(A, pinv, perm(n, 4), True)
     assert_same_matrix(cc.cs_permute(to_cs(A, lists=False), pinv, perm(n, 4), True), R2, "permute lap2d")
+
+
+# ---- cs_amd's front end ---------------------------------------------------------
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_amd_matrix(name):
+    """csparse.py:228-258 on the GPU: transpose, dense-column drop, pattern-only multiply / add, drop
+    the diagonal.  Host cs in: p and i equal the reference's bit for bit; device matrix in: the same
+    pattern (rows of a column in the blocked kernel's order)."""
+    A = Golden(name).A()
+    dA = cc.upload(to_cs(A, lists=False))
+    for order in (1, 2, 3):
+        g = NEXT[name]["amd_matrix_%d" % order]
+        C = cc.cs_amd_matrix(order, to_cs(A))
+        assert C.x is None
+        check_sha(C, {k: v for k, v in g.items() if k not in ("nzmax", "len_i")}, "amd host")
+        dC = cc.cs_amd_matrix(order, dA)
+        p, i, x = dC.arrays()
+        assert x is None and (dC.m, dC.n, dC.nnz) == (g["m"], g["n"], g["nnz"])
+        cols = np.repeat(np.arange(dC.n, dtype=np.int64), np.diff(p).astype(np.int64))
+        assert orc.digest(p, i[np.lexsort((i, cols))]) == g["sha_canonical_pattern"], "amd device"
+    assert cc.cs_amd_matrix(0, to_cs(A)) is None and cc.cs_amd_matrix(1, None) is None

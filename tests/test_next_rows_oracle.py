@@ -53,3 +53,12 @@ def test_oracle_next_rows(name):
     A2 = A.copy()
     assert orc.cs_fkeep(A2, "tol", g["droptol_tol"]) == g["droptol_ret"]
     check(A2, g["droptol"], "droptol")
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_amd_matrix(name):
+    """the matrix cs_amd starts from (csparse.py:228-258): A+A', A'A without dense rows, A'A"""
+    A = Golden(name).A()
+    for order in (1, 2, 3):
+        check(orc.cs_amd_matrix(order, A), NEXT[name]["amd_matrix_%d" % order], "amd matrix order %d" % order)
+    assert orc.cs_amd_matrix(0, A) is None and orc.cs_amd_matrix(4, A) is None
