@@ -430,8 +430,8 @@ int spmv_build_plan(csb200_mat *AT)
     pl->kind = kind;
     if (kind == 1) {
         // rows per block: a multiple of 4 (16-byte aligned rowptr slices), sized so that an
-        // average block fills ~85 % of a stage
-        int R = (int)(0.85 * TS_TILE / (avg > 1.0 ? avg : 1.0));
+        // average block fills ~90 % of a stage
+        int R = (int)(0.9 * TS_TILE / (avg > 1.0 ? avg : 1.0));
         R = R > TS_CONSUMERS ? TS_CONSUMERS : R;
         R &= ~3;
         pl->rows_per_cta = R < 4 ? 4 : R;
