@@ -21,6 +21,7 @@
 struct SpmvPlan {
     int kind = 0;            // 1 stream (TMA-staged), 2 merge, 3 stream (plain loads)
     int rows_per_cta = 0;    // stream
+    bool long_rows = false;  // stream: which stage-ring shape (TsLong / TsShort)
     int merge_ctas = 0;      // merge
     int *merge_part = nullptr;      // a-coordinate (row) at the start diagonal of each CTA, merge_ctas+1
     int *carry_row = nullptr;       // per CTA: row of the unfinished tail
@@ -130,11 +131,18 @@ k_spmv_stream(int m, const csi *__restrict__ rowptr, const csi *__restrict__ col
 // never waits for the dependent x gather or the per-row reduction.
 constexpr int TS_CONSUMERS = 512;               // consumer threads == max rows per block
 constexpr int TS_THREADS = TS_CONSUMERS + 32;   // + producer warp
-constexpr int TS_TILE = 2816;                   // nonzeros staged per block
-constexpr int TS_STAGES = 3;
 constexpr int TS_RP = TS_CONSUMERS + 4;         // staged row pointers (multiple of 4)
-constexpr int TS_STAGE_BYTES = TS_TILE * 12 + TS_RP * 4;
-constexpr int TS_SMEM = TS_STAGES * TS_STAGE_BYTES + 64;
+// Two shapes of the stage ring, both ~110 KB (two CTAs per SM): short rows (<= 12 entries on
+// average) run best with four stages of 2176 nonzeros, longer rows with two stages of 3200
+// (measured on lap2d 4096^2: 0.884 vs 0.825 of the copy roofline; st27 128^3: 0.563 vs 0.602).
+template <int TS_TILE, int TS_STAGES>
+struct TsShape {
+    static constexpr int tile = TS_TILE, stages = TS_STAGES;
+    static constexpr int stage_bytes = TS_TILE * 12 + TS_RP * 4;
+    static constexpr int smem = TS_STAGES * stage_bytes + 64;
+};
+using TsShort = TsShape<2176, 4>;
+using TsLong = TsShape<3200, 2>;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
@@ -163,10 +171,12 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+template <class SH>
 __global__ void __launch_bounds__(TS_THREADS, 2)
 k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi *__restrict__ col,
            const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
 {
+    constexpr int TS_TILE = SH::tile, TS_STAGES = SH::stages, TS_STAGE_BYTES = SH::stage_bytes;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TS_STAGES * TS_STAGE_BYTES);
     const int tid = threadIdx.x;
@@ -270,6 +280,24 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[TS_STAGES + stage]));
     }
+}
+
+static int launch_spmv_tma(bool long_rows, int m, int nblocks, int R, const csi *rowptr, const csi *col,
+                           const double *val, const double *x, double *y, cudaStream_t s)
+{
+    int dev = 0, sms = 0;
+    CSB_CUDA(cudaGetDevice(&dev));
+    CSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = min(nblocks, 2 * sms);          // two resident CTAs per SM
+    if (long_rows) {
+        CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma<TsLong>, cudaFuncAttributeMaxDynamicSharedMemorySize, TsLong::smem));
+        k_spmv_tma<TsLong><<<grid, TS_THREADS, TsLong::smem, s>>>(m, nblocks, R, rowptr, col, val, x, y);
+    } else {
+        CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma<TsShort>, cudaFuncAttributeMaxDynamicSharedMemorySize, TsShort::smem));
+        k_spmv_tma<TsShort><<<grid, TS_THREADS, TsShort::smem, s>>>(m, nblocks, R, rowptr, col, val, x, y);
+    }
+    CSB_LAUNCHED();
+    return CSB200_OK;
 }
 
 // ---- merge path --------------------------------------------------------------------
@@ -431,7 +459,8 @@ int spmv_build_plan(csb200_mat *AT)
     if (kind == 1) {
         // rows per block: a multiple of 4 (16-byte aligned rowptr slices), sized so that an
         // average block fills ~90 % of a stage
-        int R = (int)(0.9 * TS_TILE / (avg > 1.0 ? avg : 1.0));
+        pl->long_rows = avg > 12.0;
+        int R = (int)(0.9 * (pl->long_rows ? TsLong::tile : TsShort::tile) / (avg > 1.0 ? avg : 1.0));
         R = R > TS_CONSUMERS ? TS_CONSUMERS : R;
         R &= ~3;
         pl->rows_per_cta = R < 4 ? 4 : R;
@@ -466,16 +495,7 @@ int spmv_run(csb200_mat *AT, const double *d_x, double *d_y)
     if (pl->kind == 1) {
         const int R = pl->rows_per_cta;
         const int nblocks = ceil_div(m, R);
-        static int sms = 0;
-        if (!sms) {
-            int dev = 0;
-            CSB_CUDA(cudaGetDevice(&dev));
-            CSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-        }
-        const int grid = min(nblocks, 2 * sms);      // two resident CTAs per SM
-        k_spmv_tma<<<grid, TS_THREADS, TS_SMEM, stream()>>>(m, nblocks, R, AT->p, AT->i, AT->x, d_x, d_y);
-        CSB_LAUNCHED();
+        CSB_TRY(launch_spmv_tma(pl->long_rows, m, nblocks, R, AT->p, AT->i, AT->x, d_x, d_y, stream()));
     } else if (pl->kind == 3) {
         const int R = pl->rows_per_cta;
         k_spmv_stream<<<ceil_div(m, R), SP_THREADS, 0, stream()>>>(m, AT->p, AT->i, AT->x, d_x, d_y, R);
@@ -543,14 +563,7 @@ int spmv_run_rows(csb200_mat *AT, const double *d_x, double *d_y, int ra, int rb
     if (rb <= ra) return CSB200_OK;
     const int R = pl->rows_per_cta;
     const int nblocks = ceil_div(rb - ra, R);
-    int dev = 0, sms = 0;
-    CSB_CUDA(cudaGetDevice(&dev));
-    CSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-    k_spmv_tma<<<min(nblocks, 2 * sms), TS_THREADS, TS_SMEM, s>>>(rb - ra, nblocks, R, AT->p + ra, AT->i, AT->x,
-                                                                   d_x, d_y + ra);
-    CSB_LAUNCHED();
-    return CSB200_OK;
+    return launch_spmv_tma(pl->long_rows, rb - ra, nblocks, R, AT->p + ra, AT->i, AT->x, d_x, d_y + ra, s);
 }
 
 }  // namespace csb
