@@ -336,8 +336,8 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
     clocks = sampler.stop()
     achieved = alg_bytes_local / (kms * 1e-3) / 1e9
     # DRAM bytes per launch of k_spmv_tma on this exact config from the ncu --set full capture
-    # (profiles/r1_spmv_tma_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
-    traffic = 1342048000 + 127214848 if (world == 1 and k == 4096 and plan == "stream") else None
+    # (profiles/r1c_spmv_tma_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
+    traffic = 1342053000 + 128040704 if (world == 1 and k == 4096 and plan == "stream") else None
 
     # e2e: the reference-facing call on HOST buffers (pinned), copies inside the timed region.
     # "e2e": csb200_gaxpy(handle, x, y) -- the step's inputs (x and the y it accumulates into)
