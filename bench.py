@@ -498,6 +498,14 @@ def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_sr
     sampler.start()
     ms = device_timed(torch, dist, world, step, steps, warm)
     clocks = sampler.stop()
+    ms_local = None
+    if world > 1:
+        # the same step with C left column-distributed (no final gather): the compute part alone
+        def step_local():
+            hold.clear()
+            hold["c"] = csd.sharded_multiply(dA, dA, bounds, rank, gather=None, device="cuda", dB_local=dBl)
+        ms_local = device_timed(torch, dist, world, step_local, steps, warm)
+        step()                                     # leave a gathered product for the checks below
     launches = (cc.launch_count() - l0) * steps // (steps + warm)
     nnzc = (5 * k - 6) ** 3
     got = hold["c"].nnz if world == 1 else int(hold["c"][1][1].numel())
@@ -510,7 +518,10 @@ def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_sr
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cs_multiply A*A, 27-point stencil {k}^3 (n={n}, nnz={nnz}, nnz(C)={nnzc}), "
                                    f"column blocks of B, A replicated", "l2": "inputs + output exceed L2",
-                       "gflops": 2 * cc.last_multiply_flops() * world * steps / (ms * 1e-3) / 1e9 if world == 1 else None},
+                       "gflops": 2 * cc.last_multiply_flops() * world * steps / (ms * 1e-3) / 1e9 if world == 1 else None,
+                       "gather": "none (N = 1)" if world == 1 else "all-gather of the whole product onto every rank, inside the timed step",
+                       "nnz(C)/s with C left column-distributed": None if ms_local is None else nnzc * steps / (ms_local * 1e-3),
+                       "ms_per_step with C left column-distributed": None if ms_local is None else ms_local / steps},
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "traffic": None, "kernel": "whole cs_multiply (ub+bin+symbolic+scan+numeric)",

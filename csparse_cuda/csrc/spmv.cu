@@ -50,10 +50,7 @@ constexpr int MP_TILE = MP_THREADS * MP_ITEMS;   // merge items per CTA
 
 // Products of the slice [base, base+cnt) of (col, val) with x, into prods[0..cnt).
 // 128-bit loads on the 4-entry-aligned interior, scalar at the ragged ends.
-// PAD: element b lives at b + (b >> 3).  The merge kernel's threads walk runs of 8 consecutive
-// products each; unpadded, the 16 lanes of a 64-bit shared-memory phase would all hit the same
-// two banks (stride 64 B), padded they hit 16 different bank pairs (stride 72 B).
-template <int THREADS, bool PAD = false>
+template <int THREADS>
 __device__ __forceinline__ void stream_products(const csi *__restrict__ col, const double *__restrict__ val,
                                                 const double *__restrict__ x, int base, int cnt,
                                                 double *prods)
@@ -66,20 +63,16 @@ __device__ __forceinline__ void stream_products(const csi *__restrict__ col, con
             const double2 v0 = ldg_stream(reinterpret_cast<const double2 *>(val + k));
             const double2 v1 = ldg_stream(reinterpret_cast<const double2 *>(val + k + 2));
             const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
-            const int q = k - base;
-            double *o = prods + (PAD ? q + (q >> 3) : q);
+            double *o = prods + (k - base);
             o[0] = __dmul_rn(v0.x, x0);
-            o[PAD ? 1 + (((q + 1) >> 3) - (q >> 3)) : 1] = __dmul_rn(v0.y, x1);
-            o[PAD ? 2 + (((q + 2) >> 3) - (q >> 3)) : 2] = __dmul_rn(v1.x, x2);
-            o[PAD ? 3 + (((q + 3) >> 3) - (q >> 3)) : 3] = __dmul_rn(v1.y, x3);
+            o[1] = __dmul_rn(v0.y, x1);
+            o[2] = __dmul_rn(v1.x, x2);
+            o[3] = __dmul_rn(v1.y, x3);
         } else {
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int q = k + e;
-                if (q >= base && q < end) {
-                    const int o = q - base;
-                    prods[PAD ? o + (o >> 3) : o] = __dmul_rn(val[q], __ldg(x + col[q]));
-                }
+                if (q >= base && q < end) prods[q - base] = __dmul_rn(val[q], __ldg(x + col[q]));
             }
         }
     }
