@@ -135,7 +135,7 @@ k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__rest
 // one global atomic per (tile, bucket) reserves the slots, so the global atomics
 // are few and all in flight together.
 template <bool VALUES>
-__global__ void __launch_bounds__(TR_THREADS)
+__global__ void __launch_bounds__(TR_THREADS, 4)
 k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
             long long nnz, const int *__restrict__ tile_col, int log_rb, int *__restrict__ bfill,
             void *__restrict__ inter_)
