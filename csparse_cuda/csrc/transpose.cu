@@ -396,7 +396,7 @@ __device__ void block_scan_rows(const int *cnt, int *start, int n, int *warp_tot
 
 // ---- one CTA per bucket, staging in shared memory ---------------------------------------
 template <bool VALUES>
-__global__ void __launch_bounds__(BK_THREADS, 4)
+__global__ void __launch_bounds__(BK_THREADS, 5)
 k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
               const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
               csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
