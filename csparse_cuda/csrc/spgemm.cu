@@ -30,7 +30,7 @@ namespace csb {
 constexpr int EMPTY = -1;
 constexpr int BLK_STRIDE = 64;          // (block, mask) pairs kept per column for the blocked numeric kernel
 constexpr int BLK_CAP = 128;            // rows per column the blocked numeric kernel holds
-constexpr int BLK_LOGH = 8, BLK_H = 1 << BLK_LOGH;   // slots of its block table (>= 4 * BLK_STRIDE: short probes)
+constexpr int BLK_LOGH = 7, BLK_H = 1 << BLK_LOGH;   // slots of its block table (2 * BLK_STRIDE); 3 KB per warp: 8 CTAs per SM
 
 __device__ __forceinline__ unsigned hash_row(int i, int logh)
 {
@@ -798,7 +798,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             MM_CUDA(cudaStreamSynchronize(s));
             if (n_blocked > 0) {
                 constexpr int smem = 8 * (BLK_CAP * 12 + BLK_H * 12);
-                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * 6);
+                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * min(8, (220 * 1024) / smem));
 #define BLK_LAUNCH(V, K)                                                                              \
                 do {                                                                                      \
                     auto kern = k_num_blocked<V, K>;                                                      \
