@@ -12,9 +12,11 @@
 //                   entries per bucket (warp-aggregated: ~4 atomics per 32 entries)
 //   excl_scan       bucket offsets (scan.cu) -- also the bucket fill cursors
 //   k_tile_cols     column of the first entry of every 4096-entry tile
-//   k_partition     stream (Ai, Ax), attach the column id, append {row, col, val}
-//                   to the entry's bucket (one warp-aggregated atomic per bucket and
-//                   warp; 16-byte stores in contiguous runs)
+//   k_partition     stream (Ai, Ax), attach the column id, append one packed word
+//                   (row inside the bucket << colbits | source column) and the value
+//                   to the entry's bucket (one atomic per (tile, bucket) reserves the
+//                   slots); matrices whose packed word would need more than 31 bits
+//                   take the radix path
 //   k_bucket_sort   one CTA per bucket: count rows in shared memory (this IS the
 //                   reference's histogram + cs_cumsum, restricted to RB rows),
 //                   scatter the bucket into a shared-memory staging area, put every
@@ -51,8 +53,6 @@ constexpr int BK_SMEM = BK_CAP * 12 + 2 * (BK_RB_MAX + 1) * 4 + 64;
 constexpr int FIX_SHORT = 32;                 // rows up to this length: one thread (global-memory path)
 constexpr int FIX_THREAD = 8;                 // staged rows up to this length: one thread; up to 32: warp rank sort
 
-struct __align__(16) Entry { int row; int col; double val; };
-struct __align__(8) EntryP { int row; int col; };
 
 // ---- tile -> first column ------------------------------------------------------
 __global__ void k_tile_cols(const csi *__restrict__ Ap, int n, long long nnz, int ntiles,
@@ -137,8 +137,8 @@ k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__rest
 template <bool VALUES>
 __global__ void __launch_bounds__(TR_THREADS, 4)
 k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
-            long long nnz, const int *__restrict__ tile_col, int log_rb, int *__restrict__ bfill,
-            void *__restrict__ inter_)
+            long long nnz, const int *__restrict__ tile_col, int log_rb, int colbits, int *__restrict__ bfill,
+            int *__restrict__ ikey, double *__restrict__ ival)
 {
     __shared__ int sAp[PT_SMEM_COLS];
     __shared__ int cnt[HIST_WIN];
@@ -222,13 +222,9 @@ k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double
         if (k % 4 < cntk[k / 4]) {
             const int b = rows[k] >> log_rb;
             const long long pos = (long long)rank[k] + (windowed ? cnt[b - bmin] : 0);
-            if (VALUES) {
-                Entry en; en.row = rows[k]; en.col = cols[k]; en.val = vals[k];
-                reinterpret_cast<Entry *>(inter_)[pos] = en;
-            } else {
-                EntryP en; en.row = rows[k]; en.col = cols[k];
-                reinterpret_cast<EntryP *>(inter_)[pos] = en;
-            }
+            // one word per entry: (row inside the bucket, source column)
+            ikey[pos] = ((rows[k] & ((1 << log_rb) - 1)) << colbits) | cols[k];
+            if (VALUES) ival[pos] = vals[k];
         }
     }
 }
@@ -397,7 +393,8 @@ __device__ void block_scan_rows(const int *cnt, int *start, int n, int *warp_tot
 // ---- one CTA per bucket, staging in shared memory ---------------------------------------
 template <bool VALUES>
 __global__ void __launch_bounds__(BK_THREADS, 5)
-k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
+k_bucket_sort(int m, int log_rb, int colbits, int nbuckets, const int *__restrict__ bstart,
+              const int *__restrict__ ikey, const double *__restrict__ ival,
               const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
               csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
 {
@@ -418,17 +415,13 @@ k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, c
 
     for (int k = tid; k <= rb; k += BK_THREADS) rowcnt[k] = 0;
     __syncthreads();
-    const Entry *inter = reinterpret_cast<const Entry *>(inter_) + base;
-    const EntryP *interp = reinterpret_cast<const EntryP *>(inter_) + base;
+    const int colmask = (1 << colbits) - 1;
     int rank[BK_EPT];
 #pragma unroll
     for (int k = 0; k < BK_EPT; k++) {
         const int e = tid + k * BK_THREADS;
         rank[k] = 0;
-        if (e < nb) {
-            const int row = VALUES ? inter[e].row : interp[e].row;
-            rank[k] = atomicAdd(&rowcnt[row - R0], 1);
-        }
+        if (e < nb) rank[k] = atomicAdd(&rowcnt[ikey[base + e] >> colbits], 1);
     }
     __syncthreads();
     block_scan_rows(rowcnt, rowstart, nrows, warp_tot);
@@ -436,15 +429,10 @@ k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, c
     for (int k = 0; k < BK_EPT; k++) {
         const int e = tid + k * BK_THREADS;
         if (e < nb) {
-            if (VALUES) {
-                const Entry en = inter[e];
-                const int pos = rowstart[en.row - R0] + rank[k];
-                scol[pos] = en.col;
-                sval[pos] = en.val;
-            } else {
-                const EntryP en = interp[e];
-                scol[rowstart[en.row - R0] + rank[k]] = en.col;
-            }
+            const int key = ikey[base + e];                  // coalesced re-read (L1 / L2 hit)
+            const int pos = rowstart[key >> colbits] + rank[k];
+            scol[pos] = key & colmask;
+            if (VALUES) sval[pos] = ival[base + e];
         }
     }
     __syncthreads();
@@ -486,7 +474,8 @@ k_bucket_sort(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, c
 // pairs are staged; values are gathered from the bucket (L1/L2-resident) on output.
 template <bool VALUES>
 __global__ void __launch_bounds__(WB_WARPS * 32, 4)
-k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, const void *__restrict__ inter_,
+k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__restrict__ bstart,
+                   const int *__restrict__ ikey, const double *__restrict__ ival,
                    const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
                    csi *__restrict__ Cp, csi *Ci, double *Cx)
 {
@@ -499,8 +488,7 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
     unsigned short *sidx = reinterpret_cast<unsigned short *>(start + WB_RB_MAX + 8);
     const int nwarps = gridDim.x * WB_WARPS;
     const int rb = 1 << log_rb;
-    const Entry *inter = reinterpret_cast<const Entry *>(inter_);
-    const EntryP *interp = reinterpret_cast<const EntryP *>(inter_);
+    const int colmask = (1 << colbits) - 1;
 
     int b = blockIdx.x * WB_WARPS + wid;
     if (b >= nbuckets) return;
@@ -510,7 +498,7 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
 #pragma unroll
     for (int k = 0; k < WB_EPT; k++) {
         const int e = lane + k * 32;
-        rows[k] = (e < nb && nb <= WB_CAP) ? (VALUES ? inter[base + e].row : interp[base + e].row) : 0;
+        rows[k] = (e < nb && nb <= WB_CAP) ? ikey[base + e] : 0;      // packed (local row, column) words
     }
     while (b < nbuckets) {
         const int R0 = b << log_rb;
@@ -525,14 +513,14 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
             int slot[WB_EPT];                      // (local row << 16) | rank inside the row
 #pragma unroll
             for (int k = 0; k < WB_EPT; k++) {
-                const int rl = rows[k] - R0;
+                const int rl = rows[k] >> colbits;
                 slot[k] = (rl << 16) | ((lane + k * 32 < nb) ? atomicAdd(&cnt[rl], 1) : 0);
             }
             // the next bucket's row fields go in flight now
 #pragma unroll
             for (int k = 0; k < WB_EPT; k++) {
                 const int e = lane + k * 32;
-                rows[k] = (e < nnb && nnb <= WB_CAP) ? (VALUES ? inter[nbase + e].row : interp[nbase + e].row) : 0;
+                rows[k] = (e < nnb && nnb <= WB_CAP) ? ikey[nbase + e] : 0;
             }
             __syncwarp();
             {   // exclusive scan of cnt[0..WB_RB_MAX) -> start[0..WB_RB_MAX]; 4 consecutive rows per lane
@@ -554,7 +542,7 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
                 const int e = lane + k * 32;
                 if (e < nb) {
                     const int pos = start[slot[k] >> 16] + (slot[k] & 0xffff);
-                    scol[pos] = VALUES ? inter[base + e].col : interp[base + e].col;
+                    scol[pos] = ikey[base + e] & colmask;            // coalesced re-read (L1 hit)
                     sidx[pos] = (unsigned short)e;
                 }
             }
@@ -592,7 +580,7 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
             if (b == nbuckets - 1 && lane == 0) Cp[m] = base + nb;
             for (int t = lane; t < nb; t += 32) {
                 Ci[base + t] = scol[t];
-                if (VALUES) Cx[base + t] = inter[base + sidx[t]].val;
+                if (VALUES) Cx[base + t] = ival[base + sidx[t]];
             }
             if (VALUES && __any_sync(0xffffffffu, any_tie)) {
                 // duplicates of one (i,j) pair: their values go out in A's storage order
@@ -612,7 +600,7 @@ k_bucket_sort_warp(int m, int log_rb, int nbuckets, const int *__restrict__ bsta
 #pragma unroll
             for (int k = 0; k < WB_EPT; k++) {
                 const int e = lane + k * 32;
-                rows[k] = (e < nnb && nnb <= WB_CAP) ? (VALUES ? inter[nbase + e].row : interp[nbase + e].row) : 0;
+                rows[k] = (e < nnb && nnb <= WB_CAP) ? ikey[nbase + e] : 0;
             }
         }
         b = bn; base = nbase; nb = nnb;
@@ -649,11 +637,10 @@ template <bool VALUES>
 __global__ void __launch_bounds__(BIG_THREADS)
 k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasses,
              const int *__restrict__ big_list, const int *__restrict__ big_soff, int nbig,
-             const int *__restrict__ bstart, void *inter_, void *scratch_,
+             const int *__restrict__ bstart, int *ikey, double *ival, int *skey, double *sval,
              const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
              csi *Cp, csi *Ci, double *Cx)
 {
-    using E = typename std::conditional<VALUES, Entry, EntryP>::type;
     extern __shared__ __align__(16) int cursors[];             // [digit][warp]
     __shared__ int rowcnt[BK_RB_MAX + 1];
     __shared__ int rowstart[BK_RB_MAX + 1];
@@ -680,12 +667,14 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
         const int nb = bstart[b + 1] - base;
         const int R0 = b << log_rb;
         const int nrows = min(rb, m - R0);
-        E *bufA = reinterpret_cast<E *>(inter_) + base;
-        E *bufB = reinterpret_cast<E *>(scratch_) + big_soff[idx];
+        // the packed word (local row, column) is the sort key as it stands
+        int *keyA = ikey + base, *keyB = skey + big_soff[idx];
+        double *valA = VALUES ? ival + base : nullptr, *valB = VALUES ? sval + big_soff[idx] : nullptr;
+        const int colmask = (1 << colbits) - 1;
         // rows -> Cp (the reference's histogram + cs_cumsum restricted to this bucket)
         for (int k = tid; k <= rb; k += BIG_THREADS) rowcnt[k] = 0;
         __syncthreads();
-        for (int e = tid; e < nb; e += BIG_THREADS) atomicAdd(&rowcnt[bufA[e].row - R0], 1);
+        for (int e = tid; e < nb; e += BIG_THREADS) atomicAdd(&rowcnt[keyA[e] >> colbits], 1);
         __syncthreads();
         {
             const int c = tid < nrows ? rowcnt[tid] : 0;          // rb <= BK_RB_MAX == BIG_THREADS
@@ -698,8 +687,10 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
         const int per = ((nb + BIG_WARPS - 1) / BIG_WARPS + 31) & ~31;     // segment of a warp
         const int seg_lo = min(nb, wid * per), seg_hi = min(nb, seg_lo + per);
         for (int pass = 0; pass < npasses; pass++) {
-            const E *src = (pass & 1) ? bufB : bufA;
-            E *dst = (pass & 1) ? bufA : bufB;
+            const int *ksrc = (pass & 1) ? keyB : keyA;
+            int *kdst = (pass & 1) ? keyA : keyB;
+            const double *vsrc = (pass & 1) ? valB : valA;
+            double *vdst = (pass & 1) ? valA : valB;
             const bool last = pass == npasses - 1;
             const int shift = pass * width;
             for (int k = tid; k < nbins * BIG_WARPS; k += BIG_THREADS) cursors[k] = 0;
@@ -711,11 +702,7 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
                 for (int u = 0; u < BIG_UNROLL; u++) {
                     const int e = e0 + u * 32 + lane;
                     d[u] = -1;
-                    if (e < seg_hi) {
-                        const EntryP rc = *reinterpret_cast<const EntryP *>(&src[e]);
-                        const unsigned long long key = ((unsigned long long)(rc.row - R0) << colbits) | (unsigned)rc.col;
-                        d[u] = (int)((key >> shift) & (nbins - 1));
-                    }
+                    if (e < seg_hi) d[u] = (ksrc[e] >> shift) & (nbins - 1);
                 }
 #pragma unroll
                 for (int u = 0; u < BIG_UNROLL; u++) {
@@ -736,16 +723,18 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
             __syncthreads();
             // stable scatter: every warp walks its segment in order
             for (int e0 = seg_lo; e0 < seg_hi; e0 += 32 * BIG_UNROLL) {
-                E en[BIG_UNROLL];
-                int d[BIG_UNROLL];
+                int key[BIG_UNROLL], d[BIG_UNROLL];
+                double val[BIG_UNROLL];
 #pragma unroll
                 for (int u = 0; u < BIG_UNROLL; u++) {
                     const int e = e0 + u * 32 + lane;
                     d[u] = -1;
+                    key[u] = 0;
+                    val[u] = 0.0;
                     if (e < seg_hi) {
-                        en[u] = src[e];
-                        const unsigned long long key = ((unsigned long long)(en[u].row - R0) << colbits) | (unsigned)en[u].col;
-                        d[u] = (int)((key >> shift) & (nbins - 1));
+                        key[u] = ksrc[e];
+                        if (VALUES) val[u] = vsrc[e];
+                        d[u] = (key[u] >> shift) & (nbins - 1);
                     }
                 }
 #pragma unroll
@@ -760,10 +749,12 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
                     }
                     pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(peers & lt);
                     if (valid) {
-                        if (!last) dst[pos] = en[u];
-                        else {
-                            Ci[base + pos] = en[u].col;
-                            if constexpr (VALUES) Cx[base + pos] = en[u].val;
+                        if (!last) {
+                            kdst[pos] = key[u];
+                            if (VALUES) vdst[pos] = val[u];
+                        } else {
+                            Ci[base + pos] = key[u] & colmask;
+                            if (VALUES) Cx[base + pos] = val[u];
                         }
                     }
                     __syncwarp();
@@ -826,10 +817,13 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     while (log_rb < (warp_path ? 7 : 10) && (double)(2 << log_rb) * avg <= 0.85 * bcap) log_rb++;
     const int nbuckets = (int)(((long long)m + (1 << log_rb) - 1) >> log_rb);
     const int ntiles = ceil_div(nnz, PT_TILE);
+    // the bucket path moves one packed word (row inside the bucket, source column) per entry
+    int colbits = 1;
+    while (colbits < 31 && (1LL << colbits) < (long long)n) colbits++;
+    const bool packable = colbits + log_rb <= 31;
 
     DevBuf<int> bstart, bfill, tile_col;
     DevBuf<long long> total;
-    DevBuf<unsigned char> inter;
     if ((st = bstart.alloc((size_t)nbuckets + 1)) || (st = bfill.alloc((size_t)nbuckets + 2)) ||
         (st = tile_col.alloc((size_t)ntiles + 1)) || (st = total.alloc(1)))
         return fail(st);
@@ -839,7 +833,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
         *out = C;
         return (int)CSB200_OK;
     };
-    if (g_force_radix) return radix_path();
+    if (g_force_radix || !packable) return radix_path();
     TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 2) * sizeof(int), s));
     {
         int *wide = bfill.ptr + nbuckets + 1, h_wide = 0;
@@ -866,42 +860,46 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
         TR_CUDA(cudaStreamSynchronize(s));
         if ((long long)h_ct[1] * 8 > nnz) return radix_path();
     }
-    if ((st = inter.alloc((size_t)nnz * (has_x ? sizeof(Entry) : sizeof(EntryP)))) != CSB200_OK) return fail(st);
+    // intermediate: one packed word (row inside the bucket, source column) per entry + its value
+    DevBuf<int> ikey;
+    DevBuf<double> ival;
+    if ((st = ikey.alloc((size_t)nnz + 8)) != CSB200_OK) return fail(st);
+    if (has_x && (st = ival.alloc((size_t)nnz + 8)) != CSB200_OK) return fail(st);
     k_tile_cols<<<ceil_div(ntiles + 1, 256), 256, 0, s>>>(A->p, n, nnz, ntiles, tile_col.ptr);
     TR_LAUNCHED();
-    if (has_x) k_partition<true><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
-    else       k_partition<false><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, nnz, tile_col.ptr, log_rb, bfill.ptr, inter.ptr);
+    if (has_x) k_partition<true><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, log_rb, colbits, bfill.ptr, ikey.ptr, ival.ptr);
+    else       k_partition<false><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, nnz, tile_col.ptr, log_rb, colbits, bfill.ptr, ikey.ptr, nullptr);
     TR_LAUNCHED();
     if (warp_path) {
         constexpr int smem = WB_WARPS * WB_WARP_BYTES;
         const int grid = min(ceil_div(nbuckets, WB_WARPS), 148 * 4);
-        if (has_x) k_bucket_sort_warp<true><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-        else       k_bucket_sort_warp<false><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+        if (has_x) k_bucket_sort_warp<true><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, ival.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+        else       k_bucket_sort_warp<false><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, nullptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
         TR_LAUNCHED();
     } else {
         TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
         TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
-        if (has_x) k_bucket_sort<true><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-        else       k_bucket_sort<false><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, nbuckets, bstart.ptr, inter.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+        if (has_x) k_bucket_sort<true><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, ival.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+        else       k_bucket_sort<false><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, nullptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
         TR_LAUNCHED();
     }
     {
-        DevBuf<unsigned char> scratch;
         if (h_ct[0] > 0) {
-            // key = (local row, source column): colbits + log_rb bits, in an odd number of passes
-            int colbits = 1;
-            while (colbits < 31 && (1LL << colbits) < (long long)n) colbits++;
+            // key = the packed word (local row, source column): colbits + log_rb bits, in an odd number of passes
             const int bits = colbits + log_rb;
             const int npasses = bits <= BIG_MAX_WIDTH ? 1 : bits <= 3 * BIG_MAX_WIDTH ? 3 : 5;
             int width = (bits + npasses - 1) / npasses;
             if (width < 5) width = 5;                    // the scan wants one cursor per thread at least
-            if ((st = scratch.alloc((size_t)h_ct[1] * (has_x ? sizeof(Entry) : sizeof(EntryP)))) != CSB200_OK) return fail(st);
+            DevBuf<int> skey;
+            DevBuf<double> sval;
+            if ((st = skey.alloc((size_t)h_ct[1])) != CSB200_OK) return fail(st);
+            if (has_x && (st = sval.alloc((size_t)h_ct[1])) != CSB200_OK) return fail(st);
             const int smem = (int)((sizeof(int) * BIG_WARPS) << width);
             const int grid = min(h_ct[0], 148);
             TR_CUDA(cudaFuncSetAttribute(k_bucket_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             TR_CUDA(cudaFuncSetAttribute(k_bucket_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            if (has_x) k_bucket_big<true><<<grid, BIG_THREADS, smem, s>>>(m, log_rb, nbuckets, colbits, width, npasses, big_list.ptr, big_soff.ptr, h_ct[0], bstart.ptr, inter.ptr, scratch.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-            else       k_bucket_big<false><<<grid, BIG_THREADS, smem, s>>>(m, log_rb, nbuckets, colbits, width, npasses, big_list.ptr, big_soff.ptr, h_ct[0], bstart.ptr, inter.ptr, scratch.ptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
+            if (has_x) k_bucket_big<true><<<grid, BIG_THREADS, smem, s>>>(m, log_rb, nbuckets, colbits, width, npasses, big_list.ptr, big_soff.ptr, h_ct[0], bstart.ptr, ikey.ptr, ival.ptr, skey.ptr, sval.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
+            else       k_bucket_big<false><<<grid, BIG_THREADS, smem, s>>>(m, log_rb, nbuckets, colbits, width, npasses, big_list.ptr, big_soff.ptr, h_ct[0], bstart.ptr, ikey.ptr, nullptr, skey.ptr, nullptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
             TR_LAUNCHED();
         }
     }
