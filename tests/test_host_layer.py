@@ -64,6 +64,28 @@ def test_sentinels_need_no_gpu():
         cc.cs_gaxpy(P, [1.0], [1.0])
 
 
+def test_next_row_sentinels_need_no_gpu():
+    """cs_add :173-176, cs_norm :1655, cs_compress :654, cs_dupl :1044, cs_fkeep :1182,
+    cs_permute :1680, cs_symperm :2229, cs_amd :229 -- argument-shape errors before any device work"""
+    T = cc.cs(); T.nz = 2; T.m = T.n = 2
+    A = cc.cs(); A.nz = -1; A.m, A.n = 2, 3; A.p, A.i, A.x = [0, 0, 0, 0], [0], [0.0]
+    B = cc.cs(); B.nz = -1; B.m, B.n = 3, 3; B.p, B.i, B.x = [0, 0, 0, 0], [0], [0.0]
+    assert cc.cs_add(T, A, 1, 1) is None and cc.cs_add(A, None, 1, 1) is None and cc.cs_add(A, B, 1, 1) is None
+    assert cc.cs_norm(None) == -1 and cc.cs_norm(T) == -1
+    P = cc.cs(); P.nz = -1; P.m = P.n = 1; P.p, P.i, P.x = [0, 1], [0], None
+    assert cc.cs_norm(P) == -1
+    assert cc.cs_compress(A) is None and cc.cs_compress(None) is None
+    assert cc.cs_dupl(T) is False and cc.cs_dupl(None) is False
+    assert cc.cs_fkeep(T, cc.KEEP_NONZERO, None) == -1 and cc.cs_dropzeros(None) == -1 and cc.cs_droptol(T, 1.0) == -1
+    assert cc.cs_permute(T, None, None, True) is None and cc.cs_symperm(None, None, True) is None
+    assert cc.cs_amd_matrix(0, A) is None and cc.cs_amd_matrix(4, A) is None and cc.cs_amd_matrix(1, T) is None
+    assert cc.cs_pinv(None, 3) is None and cc.cs_pinv([2, 0, 1], 3) == [1, 2, 0]
+    with pytest.raises(TypeError):
+        cc.cs_dupl(P)
+    with pytest.raises(NotImplementedError):
+        cc.cs_fkeep(A, cc.cs_ifkeep(), None)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
