@@ -8,7 +8,8 @@ workload is BASELINE.json's headline: cs_gaxpy (y += A*x) on the 2-D 5-point
 Laplacian 4096^2 (n = 16 777 216, nnz = 83 869 696), metric "cs_gaxpy HBM GB/s" =
 algorithmic bytes (12 nnz + 4(n+1) + 8n + 16m) / time.  Other
 workloads: multiply_st27 (cs_multiply A*A, 27-point stencil 128^3, nnz(C)/s),
-transpose_lap2d, gaxpy_rmat (R-MAT 2^scale rows, merge-path kernel).
+transpose_lap2d, gaxpy_rmat (R-MAT 2^scale rows, merge-path kernel; N > 1: row blocks balanced by
+nonzeros, x all-gathered every step).
 
 N > 1 (launched by torchrun, one rank per GPU, NCCL): weak scaling -- every rank
 owns a 4096 x 4096 slab (16.7 M rows) of a 4096 x 4096N grid; per step each rank
@@ -249,7 +250,10 @@ def main():
     if a.workload == "gaxpy_lap2d":
         out = bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler)
     elif a.workload == "gaxpy_rmat":
-        out = bench_gaxpy_single(a, torch, cc, synth, "rmat", k, peak, peak_src, sampler)
+        if world == 1:
+            out = bench_gaxpy_single(a, torch, cc, synth, "rmat", k, peak, peak_src, sampler)
+        else:
+            out = bench_gaxpy_rmat_dist(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler)
     elif a.workload == "transpose_lap2d":
         out = bench_transpose(a, torch, cc, synth, k, peak, peak_src, sampler)
     elif a.workload == "multiply_st27":
@@ -446,6 +450,84 @@ def bench_gaxpy_single(a, torch, cc, synth, family, k, peak, peak_src, sampler):
             "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
                          "traffic": None, "kernel": f"k_spmv_{plan}", "peak_source": peak_src},
             "e2e": None}
+
+
+def bench_gaxpy_rmat_dist(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler):
+    """cs_gaxpy on the R-MAT matrix over N GPUs (strong scaling): contiguous row blocks of the CSR
+    view balanced by nonzeros, x owned in equal slices and all-gathered every step (NCCL), then the
+    local merge-path SpMV.  y is row-owned: no reduction."""
+    m, n, tp, ti, tx = synth.rmat_torch(k, 16)                 # same seed on every rank: the same matrix
+    nnz = int(ti.numel())
+    dA = cc.from_device(m, n, tp.data_ptr(), ti.data_ptr(), tx.data_ptr())
+    torch.cuda.synchronize()
+    del tp, ti, tx
+    torch.cuda.empty_cache()
+    dAT = cc.cs_transpose(dA, True)                            # CSC of A' == CSR view of A
+    dA.free()
+    p_ptr, _, _ = dAT.device_pointers()
+    rowptr = csd._as_tensor(p_ptr, m + 1, torch.int32, "cuda").to(torch.int64)
+    targets = torch.arange(world + 1, device="cuda", dtype=torch.int64) * nnz // world
+    bounds = torch.searchsorted(rowptr, targets).clamp_(0, m)
+    bounds[0], bounds[-1] = 0, m
+    bounds = [int(v) for v in bounds.tolist()]
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    blk = dAT.col_slice(r0, r1)                                # this rank's rows, all columns
+    nnz_local = blk.nnz
+    del rowptr
+    assert n % world == 0
+    xs = n // world
+    x_full = torch.empty(n, dtype=torch.float64, device="cuda")
+    x_own = torch.randn(xs, dtype=torch.float64, device="cuda")
+    y_own = torch.randn(r1 - r0, dtype=torch.float64, device="cuda")
+    # parity of the sharded step before anything is timed: the same rows from the whole matrix
+    dist.all_gather_into_tensor(x_full, x_own)
+    y_ref = torch.zeros(m, dtype=torch.float64, device="cuda")
+    y_ref[r0:r1] = y_own
+    dAT.gaxpy_t_dev(x_full.data_ptr(), y_ref.data_ptr())
+    y_chk = y_own.clone()
+    blk.gaxpy_t_dev(x_full.data_ptr(), y_chk.data_ptr())
+    err = float(torch.linalg.norm(y_chk - y_ref[r0:r1]) / torch.linalg.norm(y_ref[r0:r1]))
+    assert err <= 1e-12, f"sharded cs_gaxpy differs from the single-GPU result: {err:.3e}"
+    del y_ref, y_chk
+    dAT.free()
+
+    def step():
+        dist.all_gather_into_tensor(x_full, x_own)
+        blk.gaxpy_t_dev(x_full.data_ptr(), y_own.data_ptr())
+    step()
+    l0 = cc.launch_count()
+    sampler.start()
+    ms = device_timed(torch, dist, world, step, a.steps, a.warmup)
+    launches = (cc.launch_count() - l0) * a.steps // (a.steps + a.warmup)
+    kern = lambda: blk.gaxpy_t_dev(x_full.data_ptr(), y_own.data_ptr())
+    kms = device_timed(torch, dist, 1, kern, a.steps, 2) / a.steps
+    clocks = sampler.stop()
+    b_global = synth.gaxpy_bytes(m, n, nnz)
+    b_local = synth.gaxpy_bytes(r1 - r0, n, nnz_local)
+    value = b_global * a.steps / (ms * 1e-3) / 1e9
+    hx, hy = x_own.cpu().pin_memory(), y_own.cpu().pin_memory()
+
+    def e2e_step():
+        x_own.copy_(hx, non_blocking=True)
+        step()
+        hy.copy_(y_own, non_blocking=True)
+    ems = device_timed(torch, dist, world, e2e_step, min(a.steps, 200), 2)
+    esteps = min(a.steps, 200)
+    return {"metric": "cs_gaxpy HBM GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cs_gaxpy, R-MAT scale {k} ef 16 (n={n}, nnz={nnz}), row blocks balanced by nonzeros "
+                                   f"({r1 - r0} rows / {nnz_local} nnz on rank 0), x all-gathered every step",
+                       "kernel": "k_spmv_merge / k_spmv_tma by row statistics of the block",
+                       "exchange": "all-gather", "exchange_bytes_per_rank_step": 8 * (n - xs),
+                       "l2": "inputs exceed L2"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": b_local / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": b_local / (kms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "local SpMV of rank 0",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_local, "kernel_ms": kms},
+            "e2e": {"value": b_global * esteps / (ems * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 8 * xs,
+                    "d2h_bytes_per_step": 8 * (r1 - r0), "ms_per_step": ems / esteps,
+                    "call": "per rank: x slice H2D, all-gather of x, local csb200_gaxpy_t_dev, y slice D2H (row block resident)"}}
 
 
 def bench_transpose(a, torch, cc, synth, k, peak, peak_src, sampler):
