@@ -193,8 +193,14 @@ class DeviceMatrix(object):
 
 
 def force_transpose_path(path: Optional[str]):
-    """Tests / benchmarks: None or "auto" = automatic choice, "radix" = always the stable radix sort."""
-    _lib.check(_lib.lib().csb200_transpose_force_path({None: 0, "auto": 0, "radix": 1}[path]))
+    """Tests / benchmarks: None or "auto" = automatic choice, "radix" = always the stable radix sort,
+    "bucket" = automatic choice without the one-pass mirror path."""
+    _lib.check(_lib.lib().csb200_transpose_force_path({None: 0, "auto": 0, "radix": 1, "bucket": 2}[path]))
+
+
+def last_transpose_path() -> str:
+    """Which kernel path this thread's last cs_transpose took ("mirror", "bucket", "radix", "trivial")."""
+    return {1: "mirror", 2: "bucket", 3: "radix"}.get(_lib.lib().csb200_transpose_last_path(), "trivial")
 
 
 def upload(A, validate: bool = True) -> DeviceMatrix:
@@ -647,8 +653,10 @@ def gaxpy_host(m, n, Ap, Ai, Ax, x, y):
 
 def force_multiply_path(path: Optional[str]):
     """None / "auto": device-matrix products may use the blocked numeric kernel (rows of a column
-    block by block); "ordered": always the reference's discovery order."""
-    _lib.check(_lib.lib().csb200_multiply_force_path({None: 0, "auto": 0, "ordered": 1}[path]))
+    block by block); "ordered": always the reference's discovery order; "blocked_v1" / "blocked_v2" /
+    "blocked_v2p": automatic with that version of the blocked numeric kernel (A/B measurements)."""
+    code = {None: 0, "auto": 0, "ordered": 1, "blocked_v1": 2, "blocked_v2": 3, "blocked_v2p": 4}[path]
+    _lib.check(_lib.lib().csb200_multiply_force_path(code))
 
 
 def last_multiply_flops() -> int:

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "csb200_mat_free": (C.c_int, [mat_t]),
     "csb200_transpose": (C.c_int, [mat_t, C.c_int, matp]),
     "csb200_transpose_force_path": (C.c_int, [C.c_int]),
+    "csb200_transpose_last_path": (C.c_int, []),
     "csb200_transpose_host": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "csb200_gaxpy": (C.c_int, [mat_t, C.c_void_p, C.c_void_p]),

@@ -57,7 +57,9 @@ int ensure_device()
 // implemented in transpose.cu / spmv.cu / spgemm.cu
 int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out);
 extern int g_force_radix;
+int transpose_last_path();
 extern int g_multiply_ordered;
+extern int g_multiply_blocked_version;
 int spmv_run(csb200_mat *AT, const double *d_x, double *d_y);
 int spmv_build_plan(csb200_mat *AT);
 void spmv_plan_free(SpmvPlan *pl);
@@ -384,10 +386,12 @@ int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
 
 int csb200_transpose_force_path(int path)
 {
-    if (path < 0 || path > 1) return set_error(CSB200_ERR_ARG, "bad transpose path");
+    if (path < 0 || path > 2) return set_error(CSB200_ERR_ARG, "bad transpose path");
     g_force_radix = path;
     return CSB200_OK;
 }
+
+int csb200_transpose_last_path(void) { return transpose_last_path(); }
 
 int csb200_transpose_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
                           csi *Cp, csi *Ci, double *Cx)
@@ -538,8 +542,9 @@ int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B, csb200_mat
 
 int csb200_multiply_force_path(int path)
 {
-    if (path < 0 || path > 1) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
-    g_multiply_ordered = path;
+    if (path < 0 || path > 4) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
+    g_multiply_ordered = path == 1;
+    g_multiply_blocked_version = path >= 2 ? path : 0;
     return CSB200_OK;
 }
 

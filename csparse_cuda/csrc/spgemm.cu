@@ -24,6 +24,7 @@
 // column makes two lanes hit one row in a step; that case is serialised in lane
 // order, see CANON.)
 #include "common.cuh"
+#include <type_traits>
 
 namespace csb {
 
@@ -510,6 +511,186 @@ k_num_blocked(const int *__restrict__ list, int ncols,
     }
 }
 
+// ---- the blocked numeric kernel, second version ------------------------------------------------
+// Same algorithm and the same results as k_num_blocked, with the accumulate loop cut from ~62 to
+// ~35 warp instructions per A column and fewer shared-memory wavefronts (the kernel is bound by
+// instruction issue and the L1/shared data stage, not by HBM):
+//   * one 8-byte table slot {block << 7 | offset of the block's first row, mask}: one LDS.64 per
+//     probe instead of a key load plus a {mask, base} load (needs rows < 2^29);
+//   * the (first position, length, B value) of the <= 32 A columns of a chunk of B(:,j) are staged
+//     in shared memory and broadcast with one LDS.128 per A column instead of four shuffles;
+//   * PIPE: the row indices and values of the next A column are loaded while the current one is
+//     accumulated (6 CTAs per SM at 40 registers instead of 8 at 32).
+constexpr int BLK2_BASE_BITS = 7;
+static_assert((1 << BLK2_BASE_BITS) >= BLK_CAP, "offset field holds every row position");
+constexpr long long BLK2_MAX_ROWS = 1LL << (31 - BLK2_BASE_BITS + 5);
+constexpr int BLK2_PER_WARP = BLK_CAP * 8 + BLK_CAP * 4 + BLK_H * 8 + 32 * 16;
+
+template <bool VALUES, bool CANON, bool PIPE>
+__global__ void __launch_bounds__(256, PIPE ? 6 : 8)
+k_num_blocked2(const int *__restrict__ list, int ncols,
+               const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+               const csi *__restrict__ Bp, const csi *__restrict__ Bi, const double *__restrict__ Bx,
+               const int2 *__restrict__ blk_in, const int *__restrict__ nblk_in,
+               const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+{
+    constexpr int H = BLK_H, LOGH = BLK_LOGH;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *wbase = sm_raw + (size_t)wid * BLK2_PER_WARP;
+    double *vals = reinterpret_cast<double *>(wbase);                               // BLK_CAP accumulators
+    int *rows = reinterpret_cast<int *>(wbase + BLK_CAP * 8);                       // BLK_CAP row indices
+    int2 *tab = reinterpret_cast<int2 *>(wbase + BLK_CAP * 12);                     // H x {block << 7 | base, mask}
+    int4 *stage = reinterpret_cast<int4 *>(wbase + BLK_CAP * 12 + H * 8);           // 32 x {first, len, B value}
+    const int nwarps = gridDim.x * 8;
+    for (int s = lane; s < H; s += 32) tab[s] = make_int2(EMPTY, 0);
+    __syncwarp();
+
+    // one product beta * a for row i: position from the block table, accumulate in the reference's order
+    auto accumulate = [&](bool active, int i, double a, double beta) {
+        if (CANON) {
+            if (active) {                                               // distinct rows in a step
+                const int blk = i >> 5;
+                unsigned h = hash_row(blk, LOGH);
+                int2 e = tab[h];
+                while ((e.x >> BLK2_BASE_BITS) != blk) { h = (h + 1) & (H - 1); e = tab[h]; }   // present by construction
+                const int pos = (e.x & ((1 << BLK2_BASE_BITS) - 1)) + __popc((unsigned)e.y & ((1u << (i & 31)) - 1u));
+                vals[pos] = __dadd_rn(vals[pos], __dmul_rn(beta, a));
+            }
+        } else {
+            int pos = 0;
+            if (active) {
+                const int blk = i >> 5;
+                unsigned h = hash_row(blk, LOGH);
+                int2 e = tab[h];
+                while ((e.x >> BLK2_BASE_BITS) != blk) { h = (h + 1) & (H - 1); e = tab[h]; }
+                pos = (e.x & ((1 << BLK2_BASE_BITS) - 1)) + __popc((unsigned)e.y & ((1u << (i & 31)) - 1u));
+            }
+            const double prod = __dmul_rn(beta, a);
+            unsigned pend = __ballot_sync(0xffffffffu, active);          // duplicates: storage (= lane) order
+            while (pend) {
+                const int l = __ffs(pend) - 1;
+                if (lane == l) vals[pos] = __dadd_rn(vals[pos], prod);
+                pend &= pend - 1;
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    };
+
+    for (int idx = blockIdx.x * 8 + wid; idx < ncols; idx += nwarps) {
+        const int j = list[idx];
+        const int nblk = nblk_in[j];
+        const int out = Cp[j];
+        const int cnt = Cp[j + 1] - out;
+        // ---- the block table: insert (distinct blocks), offsets, row list -------------------------
+        int my_slot[BLK_STRIDE / 32];
+        int running = 0;
+#pragma unroll
+        for (int r = 0; r < BLK_STRIDE / 32; r++) {
+            my_slot[r] = -1;
+            if (r * 32 < nblk) {                                  // warp-uniform
+                const int t = r * 32 + lane;
+                const bool valid = t < nblk;
+                int2 bm = make_int2(0, 0);
+                if (valid) bm = blk_in[(size_t)j * BLK_STRIDE + t];
+                const int c = valid ? __popc((unsigned)bm.y) : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                const int first = running + inc - c;
+                const int word = (bm.x << BLK2_BASE_BITS) | first;
+                unsigned h = hash_row(bm.x, LOGH);
+                bool pend = valid;
+                while (__any_sync(0xffffffffu, pend)) {           // racing plain stores: the warp owns the table
+                    if (pend && tab[h].x == EMPTY) tab[h].x = word;
+                    __syncwarp();
+                    if (pend) {
+                        if (tab[h].x == word) { tab[h].y = bm.y; pend = false; }
+                        else h = (h + 1) & (H - 1);
+                    }
+                }
+                if (valid) {
+                    my_slot[r] = (int)h;
+                    unsigned mk = (unsigned)bm.y;
+                    int q = first;
+                    while (mk) { const int bit = __ffs(mk) - 1; rows[q++] = (bm.x << 5) + bit; mk &= mk - 1; }
+                }
+                running += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        // -0.0 is the exact additive identity (-0.0 + x == x bit for bit, also for x == -0.0), so the
+        // first product of a row lands as the reference's first-touch assignment
+        if (VALUES) for (int t = lane; t < cnt; t += 32) vals[t] = -0.0;
+        __syncwarp();
+        // ---- accumulate --------------------------------------------------------------------------
+        if (VALUES) {
+            const int pb_end = Bp[j + 1];
+            for (int pb0 = Bp[j]; pb0 < pb_end; pb0 += 32) {
+                const int my_pb = pb0 + lane;
+                int4 st = make_int4(0, 0, 0, 0);
+                if (my_pb < pb_end) {
+                    const int k = Bi[my_pb];
+                    const int ab = Ap[k], ae = Ap[k + 1];
+                    const double beta = Bx[my_pb];
+                    st = make_int4(ab, ae - ab, __double2loint(beta), __double2hiint(beta));
+                }
+                __syncwarp();                                      // the previous chunk has been consumed
+                stage[lane] = st;
+                __syncwarp();
+                const int nb = min(32, pb_end - pb0);
+                const bool long_cols = __reduce_max_sync(0xffffffffu, st.y) > 32;   // warp-uniform
+                auto run_steps = [&](auto long_tag) {              // two copies: the usual one has no tail loop
+                    constexpr bool LONG = decltype(long_tag)::value;
+                    int ni = 0;
+                    double na = 0.0;
+                    if (PIPE) {
+                        const int4 g0 = stage[0];
+                        if (lane < g0.y) { ni = Ai[g0.x + lane]; na = Ax[g0.x + lane]; }
+                    }
+                    for (int s = 0; s < nb; s++) {
+                        const int4 g = stage[s];                   // one broadcast LDS.128
+                        const double beta = __hiloint2double(g.w, g.z);
+                        if (PIPE) {
+                            const int i = ni;
+                            const double a = na;
+                            if (s + 1 < nb) {                      // the next A column's first 32 entries
+                                const int4 g2 = stage[s + 1];
+                                if (lane < g2.y) { ni = Ai[g2.x + lane]; na = Ax[g2.x + lane]; }
+                            }
+                            accumulate(lane < g.y, i, a, beta);
+                        } else {
+                            int i = 0;
+                            double a = 0.0;
+                            const bool active = lane < g.y;
+                            if (active) { i = Ai[g.x + lane]; a = Ax[g.x + lane]; }
+                            accumulate(active, i, a, beta);
+                        }
+                        if (LONG) {
+                            for (int o0 = 32; o0 < g.y; o0 += 32) {    // columns longer than a warp
+                                const bool active = o0 + lane < g.y;
+                                int i = 0;
+                                double a = 0.0;
+                                if (active) { i = Ai[g.x + o0 + lane]; a = Ax[g.x + o0 + lane]; }
+                                accumulate(active, i, a, beta);
+                            }
+                        }
+                    }
+                };
+                if (long_cols) run_steps(std::true_type{}); else run_steps(std::false_type{});
+            }
+        }
+        // ---- emit, empty the table -----------------------------------------------------------------
+        for (int t = lane; t < cnt; t += 32) {
+            Ci[out + t] = rows[t];
+            if (VALUES) Cx[out + t] = vals[t];
+        }
+#pragma unroll
+        for (int r = 0; r < BLK_STRIDE / 32; r++) if (my_slot[r] >= 0) tab[my_slot[r]].x = EMPTY;
+        __syncwarp();
+    }
+}
+
 // ---- numeric, one CTA per column, dense workspaces in global memory -----------------
 // The reference's algorithm verbatim per column: marks w[m], accumulator x[m]
 // (csparse.py:1624-1626), discovery order by a block-wide rank of the new rows.
@@ -689,6 +870,7 @@ __global__ void k_pick_blocked(int n, const int *__restrict__ nblk, int *__restr
 }
 
 int g_multiply_ordered = 0;        // csb200_multiply_force_path: 1 = always the reference's discovery order
+int g_multiply_blocked_version = 0;   // csb200_multiply_force_path 2 / 3 / 4: which blocked numeric kernel (0 = default)
 
 // ordered: the columns of C must come out in the reference's discovery order (cs_add / cs_dupl are
 // built on that); otherwise the blocked numeric kernel may emit them block by block.
@@ -796,7 +978,31 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             MM_LAUNCHED();
             MM_CUDA(cudaMemcpyAsync(&n_blocked, counts.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
             MM_CUDA(cudaStreamSynchronize(s));
-            if (n_blocked > 0) {
+            // kernel version: 2 = the first blocked kernel, 3 / 4 = k_num_blocked2 without / with the
+            // next-column prefetch (csb200_multiply_force_path); the packed table slot needs rows < 2^29
+            int version = g_multiply_blocked_version ? g_multiply_blocked_version : 3;
+            if ((long long)m > BLK2_MAX_ROWS) version = 2;
+            if (n_blocked > 0 && version >= 3) {
+                constexpr int smem = 8 * BLK2_PER_WARP;
+                const int per_sm = version == 4 ? 6 : 8;
+                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * per_sm);
+#define BLK2_LAUNCH(V, K, P)                                                                          \
+                do {                                                                                      \
+                    auto kern = k_num_blocked2<V, K, P>;                                                  \
+                    MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+                    kern<<<grid, 256, smem, s>>>(lists.ptr, n_blocked, A->p, A->i, A->x, B->p, B->i, B->x,   \
+                                                 blkbuf.ptr, nblk.ptr, C->p, C->i, C->x);                 \
+                } while (0)
+#define BLK2_PICK(P)                                                                                  \
+                do {                                                                                      \
+                    if (values) { if (canon) BLK2_LAUNCH(true, true, P); else BLK2_LAUNCH(true, false, P); }   \
+                    else        { if (canon) BLK2_LAUNCH(false, true, P); else BLK2_LAUNCH(false, false, P); } \
+                } while (0)
+                if (version == 4) BLK2_PICK(true); else BLK2_PICK(false);
+#undef BLK2_PICK
+#undef BLK2_LAUNCH
+                MM_LAUNCHED();
+            } else if (n_blocked > 0) {
                 constexpr int smem = 8 * (BLK_CAP * 12 + BLK_H * 12);
                 const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * min(8, (220 * 1024) / smem));
 #define BLK_LAUNCH(V, K)                                                                              \

@@ -779,8 +779,151 @@ k_bucket_big(int m, int log_rb, int nbuckets, int colbits, int width, int npasse
     }
 }
 
+// ---- mirror path: square matrix, strictly increasing columns, symmetric pattern -----------------
+// When every column of A is strictly increasing and (i, j) in A <=> (j, i) in A, the pattern of
+// A' is the pattern of A (Cp = Ap, Ci = Ai), and the value of output position q -- row j = Ai[q]
+// of output column i -- is A(i, j): the entry of source column j whose row is i.  Its position in
+// column j is unique (no duplicates), so the transpose is ONE pass: stream Ai, look the mirror
+// entry up, gather its value, write Ci / Cx coalesced.  24 B per entry of DRAM traffic (the
+// algorithmic figure) instead of the 52 B of the two-hop bucket sort.  Source order inside an
+// output column is ascending j (columns are visited in order, csparse.py:2308-2314), which is the
+// order of the strictly increasing column i of A: bit-identical by construction.
+// Nothing is assumed: the kernel checks every column for strict order and every entry for its
+// mirror, and raises *fail otherwise (the caller then discards C and takes the general path).
+// The lookup first tries position "same distance from the other end of the column" (exact for
+// translation-invariant stencils away from the boundary: one 4-byte gather), then a binary search.
+template <bool VALUES>
+__global__ void __launch_bounds__(TR_THREADS, 4)
+k_mirror(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+         int n, long long nnz, int ntiles, const int *__restrict__ tile_col,
+         csi *__restrict__ Ci, double *__restrict__ Cx, int *fail)
+{
+    __shared__ int sAp[PT_SMEM_COLS];
+    const int lane = threadIdx.x & 31;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // block-uniform early exit once anyone found an asymmetry; also the barrier that lets sAp be restaged
+        if (__syncthreads_or(*reinterpret_cast<volatile int *>(fail))) return;
+        const long long p_begin = (long long)t * PT_TILE;
+        const long long p_end = min(nnz, p_begin + PT_TILE);
+        const int j_first = tile_col[t];
+        const int j_last = tile_col[t + 1];
+        const int ncols = j_last - j_first + 1;
+        const bool staged = ncols + 1 <= PT_SMEM_COLS;
+        if (staged)
+            for (int k = threadIdx.x; k <= ncols; k += TR_THREADS) sAp[k] = Ap[j_first + k];
+        __syncthreads();
+
+        int rows[PT_EPT];       // row index of the entry = the source column of its mirror
+        int off[PT_EPT];        // distance from the start of the entry's own column
+        int col[PT_EPT];        // the entry's own column = the row of its mirror
+        int src[PT_EPT];        // position of the mirror entry
+        int cntk[PT_EPT / 4];
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < PT_EPT / 4; k++) {
+            const long long p = p_begin + (long long)(k * TR_THREADS + threadIdx.x) * 4;
+            cntk[k] = p < p_end ? (int)min((long long)4, p_end - p) : 0;
+            if (cntk[k] == 4) {
+                const int4 r = ldg_stream(reinterpret_cast<const int4 *>(Ai + p));
+                rows[4 * k] = r.x; rows[4 * k + 1] = r.y; rows[4 * k + 2] = r.z; rows[4 * k + 3] = r.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) rows[4 * k + e] = e < cntk[k] ? Ai[p + e] : -1;
+            }
+        }
+        // own column of every entry; strict order inside the column
+#pragma unroll
+        for (int k = 0; k < PT_EPT / 4; k++) {
+            const int p = (int)(p_begin + (long long)(k * TR_THREADS + threadIdx.x) * 4);
+            int prev = __shfl_up_sync(0xffffffffu, rows[4 * k + 3], 1);      // entry p - 1 (full group)
+            if (cntk[k] > 0) {
+                if (lane == 0 && p > 0) prev = Ai[p - 1];
+                int j;   // largest j with Ap[j] <= p
+                if (staged) j = upper_row(sAp, 0, ncols - 1, p);
+                else        j = upper_row(Ap, j_first, j_last, p) - j_first;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (e < cntk[k]) {
+                        const int pe = p + e;
+                        if (staged) { while (sAp[j + 1] <= pe) j++; }
+                        else        { while (Ap[j_first + j + 1] <= pe) j++; }
+                        const int o = pe - (staged ? sAp[j] : Ap[j_first + j]);
+                        off[4 * k + e] = o;
+                        col[4 * k + e] = j_first + j;
+                        const int r = rows[4 * k + e];
+                        if (o > 0 && prev >= r) bad = true;                    // not strictly increasing
+                        if ((unsigned)r >= (unsigned)n) bad = true;
+                        prev = r;
+                    }
+                }
+            }
+        }
+        unsigned miss = 0;      // entries whose guessed position does not hold the mirror
+        if (!bad) {
+            // guess: as far from the end of the mirror column as this entry is from its own column's
+            // start.  The column bounds are gathers (16 loads in flight), then one 4-byte probe each.
+#pragma unroll
+            for (int k = 0; k < PT_EPT; k++) {
+                src[k] = -1;
+                if (k % 4 < cntk[k / 4]) {
+                    const int ca = Ap[rows[k]], cb = Ap[rows[k] + 1];
+                    const int g = cb - 1 - off[k];
+                    src[k] = g >= ca ? g : -1;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PT_EPT; k++) {
+                if (k % 4 < cntk[k / 4]) {
+                    const int got = src[k] >= 0 ? Ai[src[k]] : -1;
+                    if (got != col[k]) miss |= 1u << k;
+                }
+            }
+        }
+        if (miss) {             // boundary columns, irregular patterns: binary search in the mirror column
+#pragma unroll
+            for (int k = 0; k < PT_EPT; k++) {
+                if (miss >> k & 1) {
+                    const int cb = Ap[rows[k] + 1];
+                    int lo = Ap[rows[k]], hi = cb;                              // first position with Ai >= col
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (Ai[mid] < col[k]) lo = mid + 1; else hi = mid;
+                    }
+                    if (lo < cb && Ai[lo] == col[k]) src[k] = lo; else bad = true;
+                }
+            }
+        }
+        if (bad) {
+            *fail = 1;
+        } else {
+            double v[PT_EPT];
+            if (VALUES) {
+#pragma unroll
+                for (int k = 0; k < PT_EPT; k++) if (k % 4 < cntk[k / 4]) v[k] = Ax[src[k]];
+            }
+#pragma unroll
+            for (int k = 0; k < PT_EPT / 4; k++) {
+                const long long p = p_begin + (long long)(k * TR_THREADS + threadIdx.x) * 4;
+                if (cntk[k] == 4) {
+                    *reinterpret_cast<int4 *>(Ci + p) = make_int4(rows[4 * k], rows[4 * k + 1], rows[4 * k + 2], rows[4 * k + 3]);
+                    if (VALUES) {
+                        *reinterpret_cast<double2 *>(Cx + p) = make_double2(v[4 * k], v[4 * k + 1]);
+                        *reinterpret_cast<double2 *>(Cx + p + 2) = make_double2(v[4 * k + 2], v[4 * k + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (e < cntk[k]) { Ci[p + e] = rows[4 * k + e]; if (VALUES) Cx[p + e] = v[4 * k + e]; }
+                }
+            }
+        }
+    }
+}
+
 // ---- host side -------------------------------------------------------------------
-int g_force_radix = 0;     // tests: send every transpose through the radix path
+int g_force_radix = 0;     // tests: 1 sends every transpose through the radix path, 2 skips the mirror path
+thread_local int t_last_path = 0;   // 1 mirror, 2 bucket sort, 3 radix sort, 0 trivial
+int transpose_last_path() { return t_last_path; }
 
 int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
 {
@@ -800,6 +943,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
 #define TR_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
         set_error(CSB200_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); return fail(CSB200_ERR_CUDA); } } while (0)
 #define TR_LAUNCHED() do { g_launches.fetch_add(1, std::memory_order_relaxed); TR_CUDA(cudaGetLastError()); } while (0)
+    t_last_path = 0;
     if (nnz == 0 || m == 0) {   // cs_spalloc leaves one zero slot (csparse.py:2401); Cp is all zero
         TR_CUDA(cudaMemsetAsync(C->p, 0, ((size_t)m + 1) * sizeof(csi), s));
         TR_CUDA(cudaMemsetAsync(C->i, 0, sizeof(csi), s));
@@ -830,10 +974,40 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     auto radix_path = [&]() {
         int st2 = stable_sort_by_key(nnz, m, A->i, nullptr, A->p, n, has_x ? A->x : nullptr, C->p, C->i, C->x);
         if (st2 != CSB200_OK) return fail(st2);
+        t_last_path = 3;
         *out = C;
         return (int)CSB200_OK;
     };
-    if (g_force_radix || !packable) return radix_path();
+    // one-pass mirror path: tried on square matrices until the handle is known not to qualify; the
+    // kernel verifies what it relies on (strictly increasing columns, symmetric pattern) and backs out
+    if (g_force_radix == 0 && m == n && A->mirror != 0) {
+        DevBuf<int> flag;
+        if ((st = flag.alloc(1)) != CSB200_OK) return fail(st);
+        TR_CUDA(cudaMemsetAsync(flag.ptr, 0, sizeof(int), s));
+        k_tile_cols<<<ceil_div(ntiles + 1, 256), 256, 0, s>>>(A->p, n, nnz, ntiles, tile_col.ptr);
+        TR_LAUNCHED();
+        int per_sm = 4;
+        if (has_x) TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mirror<true>, TR_THREADS, 0));
+        else       TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mirror<false>, TR_THREADS, 0));
+        const int grid = min(ntiles, 148 * max(per_sm, 1));      // resident CTAs striding over the tiles
+        if (has_x) k_mirror<true><<<grid, TR_THREADS, 0, s>>>(A->p, A->i, A->x, n, nnz, ntiles, tile_col.ptr, C->i, C->x, flag.ptr);
+        else       k_mirror<false><<<grid, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, n, nnz, ntiles, tile_col.ptr, C->i, nullptr, flag.ptr);
+        TR_LAUNCHED();
+        TR_CUDA(cudaMemcpyAsync(C->p, A->p, ((size_t)n + 1) * sizeof(csi), cudaMemcpyDeviceToDevice, s));
+        int h_flag = 1;
+        TR_CUDA(cudaMemcpyAsync(&h_flag, flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+        TR_CUDA(cudaStreamSynchronize(s));
+        const_cast<csb200_mat *>(A)->mirror = h_flag ? 0 : 1;
+        if (!h_flag) {
+            const_cast<csb200_mat *>(A)->canon = 1;
+            C->canon = 1;
+            C->mirror = 1;
+            t_last_path = 1;
+            *out = C;
+            return CSB200_OK;
+        }
+    }
+    if (g_force_radix == 1 || !packable) return radix_path();
     TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 2) * sizeof(int), s));
     {
         int *wide = bfill.ptr + nbuckets + 1, h_wide = 0;
@@ -905,6 +1079,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     }
 #undef TR_CUDA
 #undef TR_LAUNCHED
+    t_last_path = 2;
     *out = C;
     return CSB200_OK;
 }

@@ -86,9 +86,15 @@ CSB200_API int csb200_mat_free(csb200_mat *A);
  * p, i, x are bit-identical to the reference's.  C has values iff values != 0
  * and A has values. */
 CSB200_API int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C);
-/* which algorithm later transposes use: 0 = automatic (two-level bucket sort, stable radix sort
- * when power-law rows overflow the buckets), 1 = always the radix sort; for tests and benchmarks */
+/* which algorithm later transposes use: 0 = automatic (one-pass mirror lookup for square matrices
+ * with sorted duplicate-free columns and a symmetric pattern -- verified by the kernel itself --,
+ * else the two-level bucket sort, or the stable radix sort when power-law rows overflow the
+ * buckets), 1 = always the radix sort, 2 = automatic without the mirror path; for tests and
+ * benchmarks */
 CSB200_API int csb200_transpose_force_path(int path);
+/* the path the calling thread's last transpose took: 1 mirror, 2 bucket sort, 3 radix sort,
+ * 0 trivial (empty matrix) */
+CSB200_API int csb200_transpose_last_path(void);
 /* one-shot form on host buffers: Cp has m+1 slots, Ci/Cx nnz slots (Cx may be NULL) */
 CSB200_API int csb200_transpose_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
                           csi *Cp, csi *Ci, double *Cx);
@@ -125,7 +131,9 @@ CSB200_API int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B,
  * numeric kernel come out block by block (32-row blocks in discovery order, ascending inside a
  * block), the rest in the reference's discovery order; 1 = always the reference's discovery order
  * (then p, i, x are bit-identical to cs_multiply on canonical inputs).  The set of rows and every
- * value are the same either way. */
+ * value are the same either way.  2 / 3 / 4 = automatic with a given version of the blocked numeric
+ * kernel (first version / packed-slot version / packed-slot version with next-column prefetch),
+ * for A/B measurements and tests. */
 CSB200_API int csb200_multiply_force_path(int path);
 /* number of multiply-adds of the last csb200_multiply on this thread */
 CSB200_API int64_t csb200_multiply_last_flops(void);

@@ -19,13 +19,24 @@ def test_c3_lap2d_4096_transpose_and_gaxpy():
     """Config C3: n = 16 777 216, nnz = 83 869 696."""
     m, n, p, i, x = synth.lap2d(4096)
     assert len(i) == 83869696
+    # unsymmetric values on the symmetric pattern, so that A' != A: the one-pass mirror path and the
+    # two-hop bucket sort against the oracle
+    xr = np.random.default_rng(3).standard_normal(len(i))
+    R = orc.cs_transpose(orc.csc(m, n, p, i, xr), True)
+    dR = cc.from_arrays(m, n, p, i, xr)
+    for path, took in ((None, "mirror"), ("bucket", "bucket")):
+        cc.force_transpose_path(path)
+        try:
+            tp, ti, tx = cc.cs_transpose(dR, True).arrays()
+        finally:
+            cc.force_transpose_path(None)
+        assert cc.last_transpose_path() == took
+        assert np.array_equal(tp, R.p) and np.array_equal(ti, R.i) and np.array_equal(bits(tx), bits(R.x)), path
+    del R, xr, tx
+    dR.free()
     A = orc.csc(m, n, p, i, x)
     dA = cc.from_arrays(m, n, p, i, x)
-    dT = cc.cs_transpose(dA, True)
-    tp, ti, tx = dT.arrays()
-    R = orc.cs_transpose(A, True)
-    assert np.array_equal(tp, R.p) and np.array_equal(ti, R.i) and np.array_equal(bits(tx), bits(R.x))
-    del R
+    tp, ti, tx = cc.cs_transpose(dA, True).arrays()
     # symmetric matrix: A' == A bit for bit; and transposing twice is the identity
     assert np.array_equal(tp, p) and np.array_equal(ti, i) and np.array_equal(bits(tx), bits(x))
     xv, y0 = synth.vectors(m, n)
@@ -53,12 +64,19 @@ def test_c4_st27_multiply():
     dA = cc.from_arrays(m, n, p, i, x)
     assert R.nnz == (5 * 64 - 6) ** 3
     # default device path (blocked numeric kernel): the contract -- pattern after canonical sort, values
-    dC = cc.cs_multiply(dA, dA)
-    cp, ci, cx = dC.arrays()
-    Cz, Rz = orc.canonical(orc.csc(m, n, cp, ci, cx)), orc.canonical(R)
-    assert np.array_equal(cp, R.p) and np.array_equal(Cz.i, Rz.i)
-    assert np.array_equal(bits(Cz.x), bits(Rz.x))                          # same summation sequence: bit-equal
-    del dC, Cz, Rz
+    Rz = orc.canonical(R)
+    for path in (None, "blocked_v1", "blocked_v2p"):
+        cc.force_multiply_path(path)
+        try:
+            dC = cc.cs_multiply(dA, dA)
+        finally:
+            cc.force_multiply_path(None)
+        cp, ci, cx = dC.arrays()
+        Cz = orc.canonical(orc.csc(m, n, cp, ci, cx))
+        assert np.array_equal(cp, R.p) and np.array_equal(Cz.i, Rz.i), path
+        assert np.array_equal(bits(Cz.x), bits(Rz.x)), path                # same summation sequence: bit-equal
+        del dC, Cz
+    del Rz
     cc.force_multiply_path("ordered")
     try:
         cp, ci, cx = cc.cs_multiply(dA, dA).arrays()

@@ -37,7 +37,7 @@ def test_fuzz_transpose_gaxpy(seed):
     rng = np.random.default_rng(1000 + seed)
     m, n, d = shapes(rng)
     A = random_csc(rng, m, n, d, sort=bool(seed % 2), dups=bool(seed % 3 == 0), values=bool(seed % 5))
-    for path in (None, "radix"):
+    for path in (None, "radix", "bucket"):
         cc.force_transpose_path(path)
         try:
             C = cc.cs_transpose(to_cs(A, lists=False), True)
@@ -62,11 +62,16 @@ def test_fuzz_multiply_add(seed):
     R = orc.cs_multiply(A, B)
     assert_same_matrix(cc.cs_multiply(to_cs(A, lists=False), to_cs(B, lists=False)), R, f"ordered multiply seed {seed}")
     dA, dB = cc.upload(to_cs(A, lists=False)), cc.upload(to_cs(B, lists=False))
-    C = cc.cs_multiply(dA, dB).download(trim=True)                 # blocked numeric kernel allowed
-    assert_multiply_parity(C, R, f"device multiply seed {seed}")
-    if R.x is not None and R.nnz:
-        cz, rz = orc.canonical(as_omat(C)), orc.canonical(R)
-        assert np.array_equal(bits(cz.x), bits(rz.x)), f"multiply values seed {seed}"
+    for path in (None, "blocked_v1", "blocked_v2", "blocked_v2p"):  # every version of the blocked numeric kernel
+        cc.force_multiply_path(path)
+        try:
+            C = cc.cs_multiply(dA, dB).download(trim=True)
+        finally:
+            cc.force_multiply_path(None)
+        assert_multiply_parity(C, R, f"device multiply seed {seed} path {path}")
+        if R.x is not None and R.nnz:
+            cz, rz = orc.canonical(as_omat(C)), orc.canonical(R)
+            assert np.array_equal(bits(cz.x), bits(rz.x)), f"multiply values seed {seed} path {path}"
     # add: same shape operands
     A2 = random_csc(rng, m, k, d, sort=canon, dups=not canon, values=bool(seed % 3))
     al, be = float(rng.standard_normal()), float(rng.standard_normal())
@@ -145,3 +150,23 @@ def test_concurrent_threads_on_different_handles():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("path", [None, "blocked_v1", "blocked_v2", "blocked_v2p"])
+@pytest.mark.parametrize("canon", [True, False])
+def test_blocked_multiply_long_columns(path, canon):
+    """columns of A longer than a warp step (33..100 entries) that still give columns of C within the
+    blocked kernel's 128 rows; chunks of B(:,j) longer than 32; duplicates inside A's columns"""
+    rng = np.random.default_rng(77)
+    A = random_csc(rng, 120, 90, 0.6, sort=canon, dups=not canon)
+    B = random_csc(rng, 90, 60, 0.5, sort=canon, dups=not canon)
+    R = orc.cs_multiply(A, B)
+    dA, dB = cc.upload(to_cs(A, lists=False)), cc.upload(to_cs(B, lists=False))
+    cc.force_multiply_path(path)
+    try:
+        C = cc.cs_multiply(dA, dB).download(trim=True)
+    finally:
+        cc.force_multiply_path(None)
+    assert_multiply_parity(C, R, f"long columns path {path}")
+    cz, rz = orc.canonical(as_omat(C)), orc.canonical(R)
+    assert np.array_equal(bits(cz.x), bits(rz.x))

@@ -44,6 +44,7 @@ def report(name, nbytes, med, best, **kw):
 
 
 ONLY = None
+MUL_PATHS = (None,)
 
 
 def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
@@ -60,8 +61,16 @@ def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
     def tr():
         holder["c"] = cc.cs_transpose(dA, True)
     if ONLY != "multiply":
-        med, best = timeit(tr, 2, 5)
-        report(tag + " cs_transpose", synth.transpose_bytes(m, n, nnz), med, best)
+        for path in (None, "bucket"):
+            cc.force_transpose_path(path)
+            try:
+                med, best = timeit(tr, 2, 7)
+                took = cc.last_transpose_path()
+            finally:
+                cc.force_transpose_path(None)
+            report(f"{tag} cs_transpose[{took}]", synth.transpose_bytes(m, n, nnz), med, best)
+            if took != "mirror" and path is None:
+                break
     holder.clear()
     xv = torch.randn(n, dtype=torch.float64, device="cuda")
     yv = torch.randn(m, dtype=torch.float64, device="cuda")
@@ -74,10 +83,16 @@ def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
     if do_mul:
         def mul():
             holder["c"] = cc.cs_multiply(dA, dA)
-        med, best = timeit(mul, 1, 3)
-        C = holder["c"]
-        report(tag + " cs_multiply A*A", synth.multiply_bytes(nnz, nnz, C.nnz, n, n), med, best,
-               nnzC=C.nnz, nnzC_per_s=round(C.nnz / (med * 1e-3), 1), madds=cc.last_multiply_flops())
+        for path in MUL_PATHS:
+            cc.force_multiply_path(path)
+            try:
+                med, best = timeit(mul, 1, 5)
+            finally:
+                cc.force_multiply_path(None)
+            C = holder["c"]
+            report(f"{tag} cs_multiply A*A [{path or 'auto'}]", synth.multiply_bytes(nnz, nnz, C.nnz, n, n), med, best,
+                   nnzC=C.nnz, nnzC_per_s=round(C.nnz / (med * 1e-3), 1), madds=cc.last_multiply_flops())
+            holder.clear()
     dA.free()
 
 
@@ -88,9 +103,11 @@ if __name__ == "__main__":
     ap.add_argument("--rmat", type=int, default=20)
     ap.add_argument("--only", default=None, choices=[None, "transpose", "multiply"])
     ap.add_argument("--once", action="store_true", help="one warm-up + one timed call per op (for ncu launch lists)")
+    ap.add_argument("--mul-paths", default="auto", help="comma list of auto,blocked_v1,blocked_v2,blocked_v2p,ordered")
     a = ap.parse_args()
     ONCE = a.once
     ONLY = a.only
+    MUL_PATHS = tuple(None if t == 'auto' else t for t in a.mul_paths.split(','))
     torch.cuda.init()
     cc.set_stream(torch.cuda.current_stream().cuda_stream)
     n = 1 << 24
