@@ -51,7 +51,7 @@ def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
     nnz = len(i)
     if ONLY == "transpose":
         do_mul, plans = False, ()
-    if ONLY == "multiply":
+    if ONLY in ("multiply", "tm"):
         plans = ()
     t0 = time.time()
     dA = cc.from_arrays(m, n, p, i, x)
@@ -101,7 +101,7 @@ if __name__ == "__main__":
     ap.add_argument("--lap", type=int, default=4096)
     ap.add_argument("--st", type=int, default=128)
     ap.add_argument("--rmat", type=int, default=20)
-    ap.add_argument("--only", default=None, choices=[None, "transpose", "multiply"])
+    ap.add_argument("--only", default=None, choices=[None, "transpose", "multiply", "tm"])
     ap.add_argument("--once", action="store_true", help="one warm-up + one timed call per op (for ncu launch lists)")
     ap.add_argument("--mul-paths", default="auto", help="comma list of auto,blocked_v1,blocked_v2,blocked_v2p,ordered")
     a = ap.parse_args()
