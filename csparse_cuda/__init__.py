@@ -653,9 +653,9 @@ def gaxpy_host(m, n, Ap, Ai, Ax, x, y):
 
 def force_multiply_path(path: Optional[str]):
     """None / "auto": device-matrix products may use the blocked numeric kernel (rows of a column
-    block by block); "ordered": always the reference's discovery order; "blocked_v1" / "blocked_v2" /
-    "blocked_v2p": automatic with that version of the blocked numeric kernel (A/B measurements)."""
-    code = {None: 0, "auto": 0, "ordered": 1, "blocked_v1": 2, "blocked_v2": 3, "blocked_v2p": 4}[path]
+    block by block); "ordered": always the reference's discovery order; "blocked_v1" / "blocked_v2":
+    automatic with that version of the blocked numeric kernel (A/B measurements)."""
+    code = {None: 0, "auto": 0, "ordered": 1, "blocked_v1": 2, "blocked_v2": 3}[path]
     _lib.check(_lib.lib().csb200_multiply_force_path(code))
 
 

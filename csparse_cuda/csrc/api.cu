@@ -542,7 +542,7 @@ int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B, csb200_mat
 
 int csb200_multiply_force_path(int path)
 {
-    if (path < 0 || path > 4) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
+    if (path < 0 || path > 3) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
     g_multiply_ordered = path == 1;
     g_multiply_blocked_version = path >= 2 ? path : 0;
     return CSB200_OK;

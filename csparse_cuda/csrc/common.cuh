@@ -153,6 +153,20 @@ __device__ __forceinline__ double ldg_stream(const double *p)
     return r;
 }
 
+// 256-bit accesses (sm_100: LDG/STG.E.ENL2.256): four consecutive doubles of one thread as ONE
+// request, so that a warp whose lanes own 32 contiguous bytes each moves whole 32-byte sectors per
+// instruction (two 16-byte accesses with a 32-byte lane stride touch every sector twice, half-filled).
+// p must be 32-byte aligned.
+__device__ __forceinline__ void ldg_stream4(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void stg4(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // largest j in [lo, hi] with a[j] <= v  (a non-decreasing, a[lo] <= v assumed)
 __device__ __forceinline__ int upper_row(const int *a, int lo, int hi, int v)
 {

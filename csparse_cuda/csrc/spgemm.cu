@@ -512,22 +512,22 @@ k_num_blocked(const int *__restrict__ list, int ncols,
 }
 
 // ---- the blocked numeric kernel, second version ------------------------------------------------
-// Same algorithm and the same results as k_num_blocked, with the accumulate loop cut from ~62 to
-// ~35 warp instructions per A column and fewer shared-memory wavefronts (the kernel is bound by
-// instruction issue and the L1/shared data stage, not by HBM):
+// Same algorithm and the same results as k_num_blocked with a leaner accumulate loop (62 -> 42 warp
+// instructions and ~25 % fewer shared-memory wavefronts per A column; the kernel is bound by the
+// L1/shared data stage and instruction issue, not by HBM):
 //   * one 8-byte table slot {block << 7 | offset of the block's first row, mask}: one LDS.64 per
 //     probe instead of a key load plus a {mask, base} load (needs rows < 2^29);
 //   * the (first position, length, B value) of the <= 32 A columns of a chunk of B(:,j) are staged
-//     in shared memory and broadcast with one LDS.128 per A column instead of four shuffles;
-//   * PIPE: the row indices and values of the next A column are loaded while the current one is
-//     accumulated (6 CTAs per SM at 40 registers instead of 8 at 32).
+//     in shared memory and broadcast with one LDS.128 per A column instead of four shuffles (a
+//     shuffle costs a shared-memory wavefront too);
+//   * columns of A longer than a warp step take a separate copy of the loop.
 constexpr int BLK2_BASE_BITS = 7;
 static_assert((1 << BLK2_BASE_BITS) >= BLK_CAP, "offset field holds every row position");
 constexpr long long BLK2_MAX_ROWS = 1LL << (31 - BLK2_BASE_BITS + 5);
 constexpr int BLK2_PER_WARP = BLK_CAP * 8 + BLK_CAP * 4 + BLK_H * 8 + 32 * 16;
 
-template <bool VALUES, bool CANON, bool PIPE>
-__global__ void __launch_bounds__(256, PIPE ? 6 : 8)
+template <bool VALUES, bool CANON>
+__global__ void __launch_bounds__(256, 8)
 k_num_blocked2(const int *__restrict__ list, int ncols,
                const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
                const csi *__restrict__ Bp, const csi *__restrict__ Bi, const double *__restrict__ Bx,
@@ -546,26 +546,26 @@ k_num_blocked2(const int *__restrict__ list, int ncols,
     for (int s = lane; s < H; s += 32) tab[s] = make_int2(EMPTY, 0);
     __syncwarp();
 
-    // one product beta * a for row i: position from the block table, accumulate in the reference's order
+    // position of row i in the column: the block's slot (present by construction), then the rank of
+    // the row's bit inside the block's mask
+    auto lookup = [&](int i) -> int {
+        const int blk = i >> 5;
+        unsigned h = hash_row(blk, LOGH);
+        int2 e = tab[h];
+        while ((e.x >> BLK2_BASE_BITS) != blk) { h = (h + 1) & (H - 1); e = tab[h]; }
+        return (e.x & ((1 << BLK2_BASE_BITS) - 1)) + __popc((unsigned)e.y & ((1u << (i & 31)) - 1u));
+    };
+
+    // one product beta * a for row i, accumulated in the reference's order
     auto accumulate = [&](bool active, int i, double a, double beta) {
         if (CANON) {
             if (active) {                                               // distinct rows in a step
-                const int blk = i >> 5;
-                unsigned h = hash_row(blk, LOGH);
-                int2 e = tab[h];
-                while ((e.x >> BLK2_BASE_BITS) != blk) { h = (h + 1) & (H - 1); e = tab[h]; }   // present by construction
-                const int pos = (e.x & ((1 << BLK2_BASE_BITS) - 1)) + __popc((unsigned)e.y & ((1u << (i & 31)) - 1u));
+                const int pos = lookup(i);
                 vals[pos] = __dadd_rn(vals[pos], __dmul_rn(beta, a));
             }
         } else {
             int pos = 0;
-            if (active) {
-                const int blk = i >> 5;
-                unsigned h = hash_row(blk, LOGH);
-                int2 e = tab[h];
-                while ((e.x >> BLK2_BASE_BITS) != blk) { h = (h + 1) & (H - 1); e = tab[h]; }
-                pos = (e.x & ((1 << BLK2_BASE_BITS) - 1)) + __popc((unsigned)e.y & ((1u << (i & 31)) - 1u));
-            }
+            if (active) pos = lookup(i);
             const double prod = __dmul_rn(beta, a);
             unsigned pend = __ballot_sync(0xffffffffu, active);          // duplicates: storage (= lane) order
             while (pend) {
@@ -642,24 +642,10 @@ k_num_blocked2(const int *__restrict__ list, int ncols,
                 const bool long_cols = __reduce_max_sync(0xffffffffu, st.y) > 32;   // warp-uniform
                 auto run_steps = [&](auto long_tag) {              // two copies: the usual one has no tail loop
                     constexpr bool LONG = decltype(long_tag)::value;
-                    int ni = 0;
-                    double na = 0.0;
-                    if (PIPE) {
-                        const int4 g0 = stage[0];
-                        if (lane < g0.y) { ni = Ai[g0.x + lane]; na = Ax[g0.x + lane]; }
-                    }
                     for (int s = 0; s < nb; s++) {
                         const int4 g = stage[s];                   // one broadcast LDS.128
                         const double beta = __hiloint2double(g.w, g.z);
-                        if (PIPE) {
-                            const int i = ni;
-                            const double a = na;
-                            if (s + 1 < nb) {                      // the next A column's first 32 entries
-                                const int4 g2 = stage[s + 1];
-                                if (lane < g2.y) { ni = Ai[g2.x + lane]; na = Ax[g2.x + lane]; }
-                            }
-                            accumulate(lane < g.y, i, a, beta);
-                        } else {
+                        {
                             int i = 0;
                             double a = 0.0;
                             const bool active = lane < g.y;
@@ -870,7 +856,7 @@ __global__ void k_pick_blocked(int n, const int *__restrict__ nblk, int *__restr
 }
 
 int g_multiply_ordered = 0;        // csb200_multiply_force_path: 1 = always the reference's discovery order
-int g_multiply_blocked_version = 0;   // csb200_multiply_force_path 2 / 3 / 4: which blocked numeric kernel (0 = default)
+int g_multiply_blocked_version = 0;   // csb200_multiply_force_path 2 / 3: which blocked numeric kernel (0 = default)
 
 // ordered: the columns of C must come out in the reference's discovery order (cs_add / cs_dupl are
 // built on that); otherwise the blocked numeric kernel may emit them block by block.
@@ -978,28 +964,22 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             MM_LAUNCHED();
             MM_CUDA(cudaMemcpyAsync(&n_blocked, counts.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
             MM_CUDA(cudaStreamSynchronize(s));
-            // kernel version: 2 = the first blocked kernel, 3 / 4 = k_num_blocked2 without / with the
-            // next-column prefetch (csb200_multiply_force_path); the packed table slot needs rows < 2^29
+            // kernel version: 2 = the first blocked kernel, 3 = k_num_blocked2 (csb200_multiply_force_path);
+            // the packed table slot of the second needs rows < 2^29
             int version = g_multiply_blocked_version ? g_multiply_blocked_version : 3;
             if ((long long)m > BLK2_MAX_ROWS) version = 2;
             if (n_blocked > 0 && version >= 3) {
                 constexpr int smem = 8 * BLK2_PER_WARP;
-                const int per_sm = version == 4 ? 6 : 8;
-                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * per_sm);
-#define BLK2_LAUNCH(V, K, P)                                                                          \
+                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * 8);
+#define BLK2_LAUNCH(V, K)                                                                             \
                 do {                                                                                      \
-                    auto kern = k_num_blocked2<V, K, P>;                                                  \
+                    auto kern = k_num_blocked2<V, K>;                                                     \
                     MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
                     kern<<<grid, 256, smem, s>>>(lists.ptr, n_blocked, A->p, A->i, A->x, B->p, B->i, B->x,   \
                                                  blkbuf.ptr, nblk.ptr, C->p, C->i, C->x);                 \
                 } while (0)
-#define BLK2_PICK(P)                                                                                  \
-                do {                                                                                      \
-                    if (values) { if (canon) BLK2_LAUNCH(true, true, P); else BLK2_LAUNCH(true, false, P); }   \
-                    else        { if (canon) BLK2_LAUNCH(false, true, P); else BLK2_LAUNCH(false, false, P); } \
-                } while (0)
-                if (version == 4) BLK2_PICK(true); else BLK2_PICK(false);
-#undef BLK2_PICK
+                if (values) { if (canon) BLK2_LAUNCH(true, true); else BLK2_LAUNCH(true, false); }
+                else        { if (canon) BLK2_LAUNCH(false, true); else BLK2_LAUNCH(false, false); }
 #undef BLK2_LAUNCH
                 MM_LAUNCHED();
             } else if (n_blocked > 0) {

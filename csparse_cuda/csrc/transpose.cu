@@ -164,9 +164,7 @@ k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double
             const int4 r = ldg_stream(reinterpret_cast<const int4 *>(Ai + p));
             rows[4 * k] = r.x; rows[4 * k + 1] = r.y; rows[4 * k + 2] = r.z; rows[4 * k + 3] = r.w;
             if (VALUES) {
-                const double2 a = ldg_stream(reinterpret_cast<const double2 *>(Ax + p));
-                const double2 b = ldg_stream(reinterpret_cast<const double2 *>(Ax + p + 2));
-                vals[4 * k] = a.x; vals[4 * k + 1] = a.y; vals[4 * k + 2] = b.x; vals[4 * k + 3] = b.y;
+                ldg_stream4(Ax + p, vals[4 * k], vals[4 * k + 1], vals[4 * k + 2], vals[4 * k + 3]);
             }
         } else {
 #pragma unroll
@@ -800,9 +798,15 @@ k_mirror(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *_
 {
     __shared__ int sAp[PT_SMEM_COLS];
     const int lane = threadIdx.x & 31;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        // block-uniform early exit once anyone found an asymmetry; also the barrier that lets sAp be restaged
-        if (__syncthreads_or(*reinterpret_cast<volatile int *>(fail))) return;
+    int round = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, round++) {
+        // block-uniform early exit once anyone found an asymmetry (looked at every 8th tile: the flag
+        // is an L2 round trip); also the barrier that lets sAp be restaged
+        if ((round & 7) == 0) {
+            if (__syncthreads_or(*reinterpret_cast<volatile int *>(fail))) return;
+        } else {
+            __syncthreads();
+        }
         const long long p_begin = (long long)t * PT_TILE;
         const long long p_end = min(nnz, p_begin + PT_TILE);
         const int j_first = tile_col[t];
@@ -866,7 +870,10 @@ k_mirror(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *_
             for (int k = 0; k < PT_EPT; k++) {
                 src[k] = -1;
                 if (k % 4 < cntk[k / 4]) {
-                    const int ca = Ap[rows[k]], cb = Ap[rows[k] + 1];
+                    const unsigned rel = (unsigned)(rows[k] - j_first);     // mirror column inside the tile's own range:
+                    int ca, cb;                                              // its bounds are already in shared memory
+                    if (staged && rel < (unsigned)ncols) { ca = sAp[rel]; cb = sAp[rel + 1]; }
+                    else { ca = Ap[rows[k]]; cb = Ap[rows[k] + 1]; }
                     const int g = cb - 1 - off[k];
                     src[k] = g >= ca ? g : -1;
                 }
@@ -906,10 +913,7 @@ k_mirror(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *_
                 const long long p = p_begin + (long long)(k * TR_THREADS + threadIdx.x) * 4;
                 if (cntk[k] == 4) {
                     *reinterpret_cast<int4 *>(Ci + p) = make_int4(rows[4 * k], rows[4 * k + 1], rows[4 * k + 2], rows[4 * k + 3]);
-                    if (VALUES) {
-                        *reinterpret_cast<double2 *>(Cx + p) = make_double2(v[4 * k], v[4 * k + 1]);
-                        *reinterpret_cast<double2 *>(Cx + p + 2) = make_double2(v[4 * k + 2], v[4 * k + 3]);
-                    }
+                    if (VALUES) stg4(Cx + p, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; e++)
@@ -986,12 +990,18 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
         TR_CUDA(cudaMemsetAsync(flag.ptr, 0, sizeof(int), s));
         k_tile_cols<<<ceil_div(ntiles + 1, 256), 256, 0, s>>>(A->p, n, nnz, ntiles, tile_col.ptr);
         TR_LAUNCHED();
-        int per_sm = 4;
-        if (has_x) TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mirror<true>, TR_THREADS, 0));
-        else       TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mirror<false>, TR_THREADS, 0));
-        const int grid = min(ntiles, 148 * max(per_sm, 1));      // resident CTAs striding over the tiles
-        if (has_x) k_mirror<true><<<grid, TR_THREADS, 0, s>>>(A->p, A->i, A->x, n, nnz, ntiles, tile_col.ptr, C->i, C->x, flag.ptr);
-        else       k_mirror<false><<<grid, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, n, nnz, ntiles, tile_col.ptr, C->i, nullptr, flag.ptr);
+        // resident CTAs striding over the tiles
+        auto launch = [&](auto kern) -> int {
+            int per_sm = 4;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TR_THREADS, 0);
+            if (e != cudaSuccess) return set_error(CSB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+            const int grid = min(ntiles, 148 * max(per_sm, 1));
+            kern<<<grid, TR_THREADS, 0, s>>>(A->p, A->i, has_x ? A->x : nullptr, n, nnz, ntiles, tile_col.ptr, C->i,
+                                             has_x ? C->x : nullptr, flag.ptr);
+            return CSB200_OK;
+        };
+        st = has_x ? launch(k_mirror<true>) : launch(k_mirror<false>);
+        if (st != CSB200_OK) return fail(st);
         TR_LAUNCHED();
         TR_CUDA(cudaMemcpyAsync(C->p, A->p, ((size_t)n + 1) * sizeof(csi), cudaMemcpyDeviceToDevice, s));
         int h_flag = 1;

@@ -131,9 +131,8 @@ CSB200_API int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B,
  * numeric kernel come out block by block (32-row blocks in discovery order, ascending inside a
  * block), the rest in the reference's discovery order; 1 = always the reference's discovery order
  * (then p, i, x are bit-identical to cs_multiply on canonical inputs).  The set of rows and every
- * value are the same either way.  2 / 3 / 4 = automatic with a given version of the blocked numeric
- * kernel (first version / packed-slot version / packed-slot version with next-column prefetch),
- * for A/B measurements and tests. */
+ * value are the same either way.  2 / 3 = automatic with the first / second version of the
+ * blocked numeric kernel, for A/B measurements and tests. */
 CSB200_API int csb200_multiply_force_path(int path);
 /* number of multiply-adds of the last csb200_multiply on this thread */
 CSB200_API int64_t csb200_multiply_last_flops(void);

@@ -65,7 +65,7 @@ def test_c4_st27_multiply():
     assert R.nnz == (5 * 64 - 6) ** 3
     # default device path (blocked numeric kernel): the contract -- pattern after canonical sort, values
     Rz = orc.canonical(R)
-    for path in (None, "blocked_v1", "blocked_v2p"):
+    for path in (None, "blocked_v1"):
         cc.force_multiply_path(path)
         try:
             dC = cc.cs_multiply(dA, dA)

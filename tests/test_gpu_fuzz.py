@@ -62,7 +62,7 @@ def test_fuzz_multiply_add(seed):
     R = orc.cs_multiply(A, B)
     assert_same_matrix(cc.cs_multiply(to_cs(A, lists=False), to_cs(B, lists=False)), R, f"ordered multiply seed {seed}")
     dA, dB = cc.upload(to_cs(A, lists=False)), cc.upload(to_cs(B, lists=False))
-    for path in (None, "blocked_v1", "blocked_v2", "blocked_v2p"):  # every version of the blocked numeric kernel
+    for path in (None, "blocked_v1", "blocked_v2"):  # every version of the blocked numeric kernel
         cc.force_multiply_path(path)
         try:
             C = cc.cs_multiply(dA, dB).download(trim=True)
@@ -152,7 +152,7 @@ def test_concurrent_threads_on_different_handles():
     assert not errors, errors
 
 
-@pytest.mark.parametrize("path", [None, "blocked_v1", "blocked_v2", "blocked_v2p"])
+@pytest.mark.parametrize("path", [None, "blocked_v1", "blocked_v2"])
 @pytest.mark.parametrize("canon", [True, False])
 def test_blocked_multiply_long_columns(path, canon):
     """columns of A longer than a warp step (33..100 entries) that still give columns of C within the

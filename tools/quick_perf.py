@@ -103,7 +103,7 @@ if __name__ == "__main__":
     ap.add_argument("--rmat", type=int, default=20)
     ap.add_argument("--only", default=None, choices=[None, "transpose", "multiply", "tm"])
     ap.add_argument("--once", action="store_true", help="one warm-up + one timed call per op (for ncu launch lists)")
-    ap.add_argument("--mul-paths", default="auto", help="comma list of auto,blocked_v1,blocked_v2,blocked_v2p,ordered")
+    ap.add_argument("--mul-paths", default="auto", help="comma list of auto,blocked_v1,blocked_v2,ordered")
     a = ap.parse_args()
     ONCE = a.once
     ONLY = a.only
