@@ -17,7 +17,18 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__grid_size",
         "launch__block_size", "smsp__cycles_active.avg", "sm__inst_executed.sum",
-        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio" ]
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__t_sectors.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
 
 
 def rows_of(path):
@@ -64,7 +75,7 @@ def raw(path):
         print("| metric | value | unit |")
         print("|---|---:|---|")
         for k in hdr:
-            if any(k == m or k.startswith(m) for m in KEEP) or "dram__bytes" in k or "warp_issue_stalled" in k and "pct" in k:
+            if any(k == m for m in KEEP) or k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 print(f"| {k} | {r[k]} | {units.get(k, '')} |")
         print()
 

@@ -82,6 +82,7 @@ def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
                gflops=round(2 * nnz / (med * 1e-3) / 1e9, 1))
     if do_mul:
         def mul():
+            holder.clear()                   # one 3 GB result alive at a time (keeps the memory pool steady)
             holder["c"] = cc.cs_multiply(dA, dA)
         for path in MUL_PATHS:
             cc.force_multiply_path(path)
