@@ -632,9 +632,21 @@ def extras(a, torch, cc, synth, peak):
         m, n, p, i, x = synth.lap2d(4096)
         dA = cc.from_arrays(m, n, p, i, x)
         hold = {}
-        ms = timed(lambda: hold.__setitem__("c", cc.cs_transpose(dA, True)), 2, 5)
-        b = synth.transpose_bytes(m, n, len(i))
-        ex["cs_transpose lap2d 4096^2"] = {"ms": ms, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak}
+        def tr_paths(tag, dM, nb):
+            # automatic choice (one-pass mirror path for these symmetric-pattern stencils) and the
+            # general two-hop bucket sort on the same matrix
+            for path in (None, "bucket"):
+                cc.force_transpose_path(path)
+                try:
+                    t = timed(lambda: hold.__setitem__("c", cc.cs_transpose(dM, True)), 2, 5)
+                    took = cc.last_transpose_path()
+                finally:
+                    cc.force_transpose_path(None)
+                ex[f"cs_transpose {tag}" + ("" if path is None else " (bucket path)")] = {
+                    "ms": t, "GB/s": nb / t / 1e6, "frac_of_peak": nb / t / 1e6 / peak, "path": took}
+                hold.clear()
+
+        tr_paths("lap2d 4096^2", dA, synth.transpose_bytes(m, n, len(i)))
         hold.clear(); dA.free()
         m, n, p, i, x = synth.st27(128)
         dA = cc.from_arrays(m, n, p, i, x)
@@ -648,9 +660,7 @@ def extras(a, torch, cc, synth, peak):
                                             "frac_of_peak": b / ms / 1e6 / peak, "nnzC": nnzc,
                                             "GFLOP/s": 2 * cc.last_multiply_flops() / ms / 1e6}
         hold.clear()
-        ms = timed(lambda: hold.__setitem__("c", cc.cs_transpose(dA, True)), 2, 5)
-        b = synth.transpose_bytes(m, n, len(i))
-        ex["cs_transpose st27 128^3"] = {"ms": ms, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak}
+        tr_paths("st27 128^3", dA, synth.transpose_bytes(m, n, len(i)))
         hold.clear(); dA.free()
         m, n, tp, ti, tx = synth.rmat_torch(24, 16)
         nnz = int(ti.numel())
