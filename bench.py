@@ -617,16 +617,21 @@ def extras(a, torch, cc, synth, peak):
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def timed(fn, warm, iters):
+        # median of per-call CUDA-event times ("report median and best"): these calls
+        # allocate their GB-sized results from the stream-ordered pool, and a call that makes the pool
+        # map fresh memory costs tens of ms once -- a mean over five calls would report the allocator
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
-        e0, e1 = ev(), ev()
-        e0.record()
+        ts = []
         for _ in range(iters):
+            e0, e1 = ev(), ev()
+            e0.record()
             fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
 
     try:
         m, n, p, i, x = synth.lap2d(4096)
