@@ -616,22 +616,24 @@ def extras(a, torch, cc, synth, peak):
     ex = {}
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    def timed(fn, warm, iters):
-        # median of per-call CUDA-event times ("report median and best"): these calls
-        # allocate their GB-sized results from the stream-ordered pool, and a call that makes the pool
-        # map fresh memory costs tens of ms once -- a mean over five calls would report the allocator
+    def timed(fn, warm, iters, batches=3):
+        # ms per call: `batches` runs of `iters` back-to-back calls, one CUDA-event pair around each run
+        # (host work of a call overlaps the previous call's kernels, as in a solver loop), median over
+        # the runs.  These calls allocate their GB-sized results from the stream-ordered pool; a call
+        # that makes the pool map fresh memory costs tens of ms once, which a single mean would report.
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
-        ts = []
-        for _ in range(iters):
+        per_call = []
+        for _ in range(batches):
             e0, e1 = ev(), ev()
             e0.record()
-            fn()
+            for _ in range(iters):
+                fn()
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        return float(np.median(ts))
+            per_call.append(e0.elapsed_time(e1) / iters)
+        return float(np.median(per_call))
 
     try:
         m, n, p, i, x = synth.lap2d(4096)
