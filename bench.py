@@ -645,7 +645,11 @@ def extras(a, torch, cc, synth, peak):
             for path in (None, "bucket"):
                 cc.force_transpose_path(path)
                 try:
-                    t = timed(lambda: hold.__setitem__("c", cc.cs_transpose(dM, True)), 2, 5)
+                    # 12 warm-up calls: the bucket path's temporaries (two nnz-sized intermediates next to
+                    # the result) take the stream-ordered pool ~15 calls to stop mapping fresh memory
+                    # (tools/diag_pool.py: 7.1, 4.6, 2.0 ms per call over the first three runs of five,
+                    # 1.27 ms from then on in every mode)
+                    t = timed(lambda: hold.__setitem__("c", cc.cs_transpose(dM, True)), 12, 5)
                     took = cc.last_transpose_path()
                 finally:
                     cc.force_transpose_path(None)
