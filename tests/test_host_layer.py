@@ -136,3 +136,24 @@ def test_synthetic_generators():
     assert synth.gaxpy_bytes(16777216, 16777216, 83869696) == 1476198404
     assert synth.transpose_bytes(16777216, 16777216, 83869696) == 2147090440
     assert synth.multiply_bytes(55742968, 55742968, 254840104, 2097152, 2097152) == 4421078316
+
+
+def test_path_controls_need_no_gpu():
+    """the test / A-B switches of the C ABI only set library state: documented names map to the
+    documented codes, anything else is refused, and nothing touches a device"""
+    from csparse_cuda import _lib
+    L = _lib.lib()
+    for name in (None, "auto", "radix", "bucket"):
+        cc.force_transpose_path(name)
+    cc.force_transpose_path(None)
+    assert cc.last_transpose_path() == "trivial"                  # no transpose ran on this thread
+    with pytest.raises(KeyError):
+        cc.force_transpose_path("fastest")
+    assert L.csb200_transpose_force_path(7) != 0 and L.csb200_transpose_force_path(-1) != 0
+    for name in (None, "auto", "ordered", "blocked_v1", "blocked_v2"):
+        cc.force_multiply_path(name)
+    cc.force_multiply_path(None)
+    with pytest.raises(KeyError):
+        cc.force_multiply_path("blocked_v9")
+    assert L.csb200_multiply_force_path(9) != 0
+    assert L.csb200_transpose_force_path(0) == 0 and L.csb200_multiply_force_path(0) == 0
