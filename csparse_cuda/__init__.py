@@ -34,6 +34,7 @@ of cs_transpose / cs_multiply on device matrices stay on the device
 """
 from __future__ import annotations
 
+import array as _array
 import ctypes as C
 from typing import Optional
 
@@ -78,7 +79,15 @@ def _i32(seq, count) -> np.ndarray:
     if isinstance(seq, np.ndarray):
         a = seq[:count]
     else:
-        a = np.asarray(seq[:count] if len(seq) != count else seq)
+        part = seq[:count] if len(seq) != count else seq
+        if isinstance(part, list):
+            # a list of Python ints (the reference's own containers): array('i') converts and
+            # range-checks in one pass, 1.5x faster than np.asarray + min/max on 1e7 entries
+            try:
+                return np.frombuffer(_array.array("i", part), dtype=np.int32) if part else np.zeros(0, np.int32)
+            except (TypeError, OverflowError):
+                pass                      # floats, numpy scalars without __index__, values past int32: slow path
+        a = np.asarray(part)
     if a.size and a.dtype != np.int32:
         if a.dtype.kind not in "iu":
             a = a.astype(np.int64)
@@ -91,7 +100,13 @@ def _f64(seq, count) -> np.ndarray:
     if isinstance(seq, np.ndarray):
         a = seq[:count]
     else:
-        a = np.asarray(seq[:count] if len(seq) != count else seq, dtype=np.float64)
+        part = seq[:count] if len(seq) != count else seq
+        if isinstance(part, list) and part:
+            try:
+                return np.frombuffer(_array.array("d", part), dtype=np.float64)
+            except TypeError:
+                pass                      # entries that are not real numbers: let numpy decide
+        a = np.asarray(part, dtype=np.float64)
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
