@@ -110,6 +110,13 @@ def _f64(seq, count) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _need(seq, count, what):
+    """The reference indexes seq[0..count-1] and raises IndexError on a short container; the C ABI
+    gets raw pointers, so lengths are checked here, before any pointer crosses the boundary."""
+    if count < 0 or len(seq) < count:
+        raise IndexError(f"{what}: {len(seq)} entries, {count} needed")
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -124,6 +131,8 @@ class DeviceMatrix(object):
     nz = -1
 
     def __init__(self, handle, owner=True):
+        if not handle:
+            raise CSparseCudaError("DeviceMatrix: null csb200_mat handle (the call that should have made it failed)")
         self._h = C.c_void_p(handle)
         self._owner = owner
         m, n, nnz, hv = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int()
@@ -160,7 +169,7 @@ class DeviceMatrix(object):
 
     def col_slice(self, j0: int, j1: int) -> "DeviceMatrix":
         out = C.c_void_p()
-        st = _lib.check(_lib.lib().csb200_mat_col_slice(self._h, j0, j1, C.byref(out)), "col_slice")
+        st = _lib.check(_lib.lib().csb200_mat_col_slice(self._h, j0, j1, C.byref(out)), "col_slice", allow_arg=True)
         if st == _lib.ERR_ARG:
             raise ValueError(_lib.last_error())
         return DeviceMatrix(out.value)
@@ -225,15 +234,18 @@ def upload(A, validate: bool = True) -> DeviceMatrix:
     if not CS_CSC(A):
         raise ValueError("upload: a compressed-column cs is required")
     n = A.n
+    if A.m < 0 or n < 0:
+        raise ValueError("upload: negative dimension")
+    _need(A.p, n + 1, "upload: column pointers p")
     p = _i32(A.p, n + 1)
-    nnz = int(p[n]) if n + 1 <= len(p) else 0
+    nnz = int(p[n])
     if nnz < 0 or nnz > len(A.i) or (A.x is not None and nnz > len(A.x)):
         raise ValueError("upload: p[n] exceeds the length of i / x")
     i = _i32(A.i, nnz)
     x = None if A.x is None else _f64(A.x, nnz)
     out = C.c_void_p()
     st = _lib.check(_lib.lib().csb200_mat_upload(A.m, n, _ptr(p), _ptr(i), _ptr(x), 1 if validate else 0,
-                                                 C.byref(out)), "upload")
+                                                 C.byref(out)), "upload", allow_arg=True)
     if st == _lib.ERR_ARG:
         raise ValueError(_lib.last_error())
     return DeviceMatrix(out.value)
@@ -253,7 +265,7 @@ def from_device(m, n, p_ptr: int, i_ptr: int, x_ptr: int = 0) -> DeviceMatrix:
     pattern-only).  The arrays are copied; contents are trusted (not validated)."""
     out = C.c_void_p()
     st = _lib.check(_lib.lib().csb200_mat_from_dev(int(m), int(n), C.c_void_p(p_ptr), C.c_void_p(i_ptr),
-                                                   C.c_void_p(x_ptr or None), C.byref(out)), "from_device")
+                                                   C.c_void_p(x_ptr or None), C.byref(out)), "from_device", allow_arg=True)
     if st == _lib.ERR_ARG:
         raise ValueError(_lib.last_error())
     return DeviceMatrix(out.value)
@@ -276,6 +288,11 @@ def cs_cumsum(p, c, n):
     """
     if p is None or c is None:
         return -1
+    n = int(n)
+    if n < 0:
+        n = 0                      # range(n) is empty in the reference: only p[0] = 0 is written
+    _need(c, n, "cs_cumsum: c")
+    _need(p, n + 1, "cs_cumsum: p")
     cc = _i32(c, n).copy()
     pp = np.empty(n + 1, np.int32)
     total = C.c_int64()
@@ -324,6 +341,13 @@ def cs_gaxpy(A, x, y):
     if not has_x:
         raise TypeError("cs_gaxpy: matrix has no numerical values (A.x is None)")
     dA, tmp = _as_device(A)
+    try:
+        _need(x, dA.n, "cs_gaxpy: x")
+        _need(y, dA.m, "cs_gaxpy: y")
+    except IndexError:
+        if tmp:
+            dA.free()
+        raise
     xx = _f64(x, dA.n)
     inplace = (isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous
                and y.flags.writeable)
@@ -435,11 +459,15 @@ def cs_norm(A):
 def compress_device(T) -> "DeviceMatrix":
     """cs_compress leaving the result in HBM."""
     nz = T.nz
+    _need(T.i, nz, "cs_compress: row indices i")
+    _need(T.p, nz, "cs_compress: column indices p")
+    if T.x is not None:
+        _need(T.x, nz, "cs_compress: values x")
     ti, tj = _i32(T.i, nz), _i32(T.p, nz)
     tx = None if T.x is None else _f64(T.x, nz)
     out = C.c_void_p()
     st = _lib.check(_lib.lib().csb200_compress(T.m, T.n, nz, _ptr(ti), _ptr(tj), _ptr(tx), C.byref(out)),
-                    "cs_compress")
+                    "cs_compress", allow_arg=True)
     if st == _lib.ERR_ARG:
         raise ValueError(_lib.last_error())
     return DeviceMatrix(out.value)
@@ -474,7 +502,7 @@ def cs_dupl(A):
 def dupl_device(A) -> "DeviceMatrix":
     dA, tmp = _as_device(A)
     out = C.c_void_p()
-    st = _lib.check(_lib.lib().csb200_dupl(dA._h, C.byref(out)), "cs_dupl")
+    st = _lib.check(_lib.lib().csb200_dupl(dA._h, C.byref(out)), "cs_dupl", allow_arg=True)
     if tmp:
         dA.free()
     if st == _lib.ERR_ARG:
@@ -616,15 +644,28 @@ def cs_permute(A, pinv, q, values):
     if not CS_CSC(A):
         return None
     dA, tmp = _as_device(A)
+    try:
+        if pinv is not None:
+            _need(pinv, dA.m, "cs_permute: pinv")
+        if q is not None:
+            _need(q, dA.n, "cs_permute: q")
+    except IndexError:
+        if tmp:
+            dA.free()
+        raise
     pv = None if pinv is None else _i32(pinv, dA.m)
     qv = None if q is None else _i32(q, dA.n)
     out = C.c_void_p()
-    _lib.check(_lib.lib().csb200_permute(dA._h, _ptr(pv), _ptr(qv), 1 if values else 0, C.byref(out)), "cs_permute")
+    nzmax = max(dA.nnz, 1)                      # cs_spalloc(m, n, Ap[n], ...) (csparse.py:1681)
+    try:
+        _lib.check(_lib.lib().csb200_permute(dA._h, _ptr(pv), _ptr(qv), 1 if values else 0, C.byref(out)), "cs_permute")
+    finally:
+        if tmp:
+            dA.free()
     dC = DeviceMatrix(out.value)
     if not tmp:
         return dC
-    dA.free()
-    return dC.download(trim=False)
+    return _padded(dC, nzmax)
 
 
 def cs_symperm(A, pinv, values):
@@ -634,6 +675,10 @@ def cs_symperm(A, pinv, values):
         return None
     nzmax = max(_nnz_of(A), 1)
     dA, tmp = _as_device(A)
+    if pinv is not None and len(pinv) < dA.n:
+        if tmp:
+            dA.free()
+        raise IndexError(f"cs_symperm: pinv: {len(pinv)} entries, {dA.n} needed")
     pv = None if pinv is None else _i32(pinv, dA.n)
     out = C.c_void_p()
     _lib.check(_lib.lib().csb200_symperm(dA._h, _ptr(pv), 1 if values else 0, C.byref(out)), "cs_symperm")

@@ -95,12 +95,15 @@ def last_error() -> str:
     return msg.decode("utf-8", "replace") if msg else ""
 
 
-def check(status: int, what: str = "") -> int:
+def check(status: int, what: str = "", allow_arg: bool = False) -> int:
     """Map a csb200_status to the Python exception the host layer documents.
-    ERR_ARG is returned to the caller (it becomes the reference's sentinel)."""
-    if status == OK or status == ERR_ARG:
+    ERR_ARG raises ValueError unless ``allow_arg`` (the few callers that turn it into the
+    reference's sentinel or into their own exception ask for it back)."""
+    if status == OK or (status == ERR_ARG and allow_arg):
         return status
     msg = f"{what}: {last_error()}" if what else last_error()
+    if status == ERR_ARG:
+        raise ValueError(msg)
     if status == ERR_INDEX:
         raise ValueError(msg)
     if status == ERR_OVERFLOW:

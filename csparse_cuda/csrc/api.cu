@@ -25,6 +25,19 @@ int set_error(int status, const char *fmt, ...)
     return status;
 }
 
+int sm_count()
+{
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 148; }
+        cached[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 int ensure_device()
 {
     static std::mutex mu;
@@ -56,10 +69,7 @@ int ensure_device()
 
 // implemented in transpose.cu / spmv.cu / spgemm.cu
 int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out);
-extern int g_force_radix;
 int transpose_last_path();
-extern int g_multiply_ordered;
-extern int g_multiply_blocked_version;
 int spmv_run(csb200_mat *AT, const double *d_x, double *d_y);
 int spmv_build_plan(csb200_mat *AT);
 void spmv_plan_free(SpmvPlan *pl);
@@ -253,7 +263,8 @@ int csb200_mat_upload(csi m, csi n, const csi *p, const csi *i, const double *x,
         if (st != CSB200_OK) { csb200_mat_free(A); return st; }
         cudaMemsetAsync(bad.ptr, 0, sizeof(int), s);
         const long long work = nnz > n ? nnz : n;
-        const int blocks = (int)(work / 256 + 1 < 148 * 32 ? work / 256 + 1 : 148 * 32);
+        const long long cap_blocks = (long long)sm_count() * 32;
+        const int blocks = (int)(work / 256 + 1 < cap_blocks ? work / 256 + 1 : cap_blocks);
         k_validate<<<blocks, 256, 0, s>>>(m, n, A->p, A->i, nnz, bad.ptr);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         int h = 0;
@@ -387,7 +398,7 @@ int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
 int csb200_transpose_force_path(int path)
 {
     if (path < 0 || path > 2) return set_error(CSB200_ERR_ARG, "bad transpose path");
-    g_force_radix = path;
+    tls().force_transpose = path;
     return CSB200_OK;
 }
 
@@ -543,8 +554,8 @@ int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B, csb200_mat
 int csb200_multiply_force_path(int path)
 {
     if (path < 0 || path > 3) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
-    g_multiply_ordered = path == 1;
-    g_multiply_blocked_version = path >= 2 ? path : 0;
+    tls().multiply_ordered = path == 1;
+    tls().multiply_blocked_version = path >= 2 ? path : 0;
     return CSB200_OK;
 }
 

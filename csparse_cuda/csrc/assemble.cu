@@ -23,7 +23,6 @@ namespace csb {
 
 int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered);
 int mat_is_canonical(csb200_mat *A, int *out);
-int g_add_force_spgemm = 0;          // tests: send cs_add through the SpGEMM kernels even for canonical operands
 int mat_alloc(csi m, csi n, long long nnz, bool has_x, csb200_mat **out);
 
 // ---- small builders ------------------------------------------------------------------
@@ -304,7 +303,7 @@ int csb200_add(csb200_mat *A, csb200_mat *B, double alpha, double beta, csb200_m
     int ca = 0, cb = 0;
     CSB_TRY(mat_is_canonical(A, &ca));
     CSB_TRY(mat_is_canonical(B, &cb));
-    if (ca && cb && !g_add_force_spgemm) {
+    if (ca && cb && !tls().add_force_spgemm) {
         // both operands sorted without duplicates: membership by binary search, two passes
         DevBuf<int> cnt;
         DevBuf<long long> total;
@@ -363,7 +362,7 @@ int csb200_add(csb200_mat *A, csb200_mat *B, double alpha, double beta, csb200_m
 int csb200_add_force_path(int path)
 {
     if (path < 0 || path > 1) return set_error(CSB200_ERR_ARG, "bad cs_add path");
-    g_add_force_spgemm = path;
+    tls().add_force_spgemm = path;
     return CSB200_OK;
 }
 
@@ -491,6 +490,15 @@ int csb200_permute(const csb200_mat *A, const csi *pinv, const csi *q, int value
     k_perm_lens<<<ceil_div(n, 256), 256, 0, s>>>(n, A->p, q ? d_q.ptr : nullptr, len.ptr);
     CSB_LAUNCHED();
     CSB_TRY(launch_excl_scan(R.m->p, len.ptr, n, total.ptr, nullptr));
+    // C holds nnz(A) entries: a q that repeats columns (not a permutation) would make the copy
+    // run past it -- the reference fails with IndexError there, this returns CSB200_ERR_INDEX
+    long long h_total = 0;
+    CSB_CUDA(cudaMemcpyAsync(&h_total, total.ptr, sizeof(h_total), cudaMemcpyDeviceToHost, s));
+    CSB_CUDA(cudaStreamSynchronize(s));
+    if (h_total > nnz)
+        return set_error(CSB200_ERR_INDEX, "cs_permute: q is not a permutation (selected columns hold %lld entries, A has %lld)",
+                         h_total, nnz);
+    R.m->nnz = h_total;                                                   // fewer when q skips columns
     if (nnz / n > 12)
         k_perm_copy<32><<<ceil_div((long long)n * 32, 256), 256, 0, s>>>(n, A->p, A->i, has_x ? A->x : nullptr,
                                                                          pinv ? d_pinv.ptr : nullptr, q ? d_q.ptr : nullptr,

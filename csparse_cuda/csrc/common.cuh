@@ -16,6 +16,11 @@ struct ThreadState {
     cudaStream_t stream = nullptr;   // legacy default stream unless csb200_set_stream
     char err[640] = {0};
     int64_t last_flops = 0;
+    // path switches of the tests / benchmarks (csb200_*_force_path): per thread, like the stream
+    int force_transpose = 0;          // 1: always the radix sort, 2: automatic choice without the mirror path
+    int multiply_ordered = 0;         // 1: always the reference's discovery order
+    int multiply_blocked_version = 0; // 2 / 3: which blocked numeric kernel (0 = default)
+    int add_force_spgemm = 0;         // 1: cs_add on the SpGEMM kernels even for canonical operands
 };
 ThreadState &tls();
 extern std::atomic<int64_t> g_launches;
@@ -44,6 +49,9 @@ int set_error(int status, const char *fmt, ...);
     } while (0)
 
 inline cudaStream_t stream() { return tls().stream; }
+
+// SMs of the current device (queried once per device; grids are sized in multiples of it)
+int sm_count();
 
 // stream-ordered allocation from the device's default memory pool (cached: the
 // release threshold is raised once per device in ensure_device()).

@@ -265,7 +265,7 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
     if (npasses >= 3) CSB_TRY(bufB.alloc((size_t)nnz * recsz));
     RS_CUDA(cudaMemsetAsync(hist.ptr, 0, RS_MAX_PASSES * RS_BINS * sizeof(unsigned long long), s));
     RS_CUDA(cudaMemsetAsync(ticket.ptr, 0, RS_MAX_PASSES * sizeof(unsigned), s));
-    k_rs_hist<<<min(ceil_div(nnz, 1024 * 8), 148 * 8), 256, 0, s>>>(key, nnz, npasses, hist.ptr);
+    k_rs_hist<<<min(ceil_div(nnz, 1024 * 8), sm_count() * 8), 256, 0, s>>>(key, nnz, npasses, hist.ptr);
     CSB_LAUNCHED();
     k_rs_starts<<<1, RS_BINS, 0, s>>>(npasses, hist.ptr);
     CSB_LAUNCHED();

@@ -812,8 +812,8 @@ static int run_sym_flat(const int *list, const int *ncols_dev, int ncols, const 
     if (!ncols_dev && ncols == 0) return CSB200_OK;
     const size_t smem = (size_t)WARPS * ((size_t)(1 << LOGH) * 8 + CAP * 2);
     const int resident = (int)min((size_t)(2048 / (WARPS * 32)), (size_t)(220 * 1024) / smem);
-    const int grid = ncols_dev ? 148 * resident
-                               : (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * resident);
+    const int grid = ncols_dev ? sm_count() * resident
+                               : (int)min((long long)ceil_div(ncols, WARPS), (long long)sm_count() * resident);
     auto kern = k_sym_flat<LOGH, CAP, WARPS, OPTIMISTIC>;
     CSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, WARPS * 32, smem, stream()>>>(list, ncols_dev, ncols, A->p, A->c32_blk, A->c32_mask, A->c32_len,
@@ -829,7 +829,7 @@ static int run_num_warp(const int *list, int ncols, const csb200_mat *A, const c
     if (ncols == 0) return CSB200_OK;
     const size_t smem = (size_t)WARPS * ((size_t)(1 << LOGH) * 12 + CAP * 2);
     const int resident = (int)min((size_t)16, (size_t)(220 * 1024) / smem);
-    const int grid = (int)min((long long)ceil_div(ncols, WARPS), (long long)148 * resident);
+    const int grid = (int)min((long long)ceil_div(ncols, WARPS), (long long)sm_count() * resident);
 #define NUM_LAUNCH(V, K)                                                                          \
     do {                                                                                          \
         auto kern = k_num_warp<LOGH, CAP, WARPS, V, K>;                                           \
@@ -855,15 +855,13 @@ __global__ void k_pick_blocked(int n, const int *__restrict__ nblk, int *__restr
     if (b) size[j] = 0;
 }
 
-int g_multiply_ordered = 0;        // csb200_multiply_force_path: 1 = always the reference's discovery order
-int g_multiply_blocked_version = 0;   // csb200_multiply_force_path 2 / 3: which blocked numeric kernel (0 = default)
 
 // ordered: the columns of C must come out in the reference's discovery order (cs_add / cs_dupl are
 // built on that); otherwise the blocked numeric kernel may emit them block by block.
 int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
 {
     const csi m = A->m, n = B->n;
-    if (g_multiply_ordered) ordered = true;
+    if (tls().multiply_ordered) ordered = true;
     const bool values = A->x != nullptr && B->x != nullptr;      // csparse.py:1625
     cudaStream_t s = stream();
 
@@ -966,11 +964,11 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             MM_CUDA(cudaStreamSynchronize(s));
             // kernel version: 2 = the first blocked kernel, 3 = k_num_blocked2 (csb200_multiply_force_path);
             // the packed table slot of the second needs rows < 2^29
-            int version = g_multiply_blocked_version ? g_multiply_blocked_version : 3;
+            int version = tls().multiply_blocked_version ? tls().multiply_blocked_version : 3;
             if ((long long)m > BLK2_MAX_ROWS) version = 2;
             if (n_blocked > 0 && version >= 3) {
                 constexpr int smem = 8 * BLK2_PER_WARP;
-                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * 8);
+                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)sm_count() * 8);
 #define BLK2_LAUNCH(V, K)                                                                             \
                 do {                                                                                      \
                     auto kern = k_num_blocked2<V, K>;                                                     \
@@ -984,7 +982,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
                 MM_LAUNCHED();
             } else if (n_blocked > 0) {
                 constexpr int smem = 8 * (BLK_CAP * 12 + BLK_H * 12);
-                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)148 * min(8, (220 * 1024) / smem));
+                const int grid = (int)min((long long)ceil_div(n_blocked, 8), (long long)sm_count() * min(8, (220 * 1024) / smem));
 #define BLK_LAUNCH(V, K)                                                                              \
                 do {                                                                                      \
                     auto kern = k_num_blocked<V, K>;                                                      \

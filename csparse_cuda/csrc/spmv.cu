@@ -278,9 +278,7 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
 static int launch_spmv_tma(bool long_rows, int m, int nblocks, int R, const csi *rowptr, const csi *col,
                            const double *val, const double *x, double *y, cudaStream_t s)
 {
-    int dev = 0, sms = 0;
-    CSB_CUDA(cudaGetDevice(&dev));
-    CSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = sm_count();
     const int grid = min(nblocks, 2 * sms);          // two resident CTAs per SM
     if (long_rows) {
         CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma<TsLong>, cudaFuncAttributeMaxDynamicSharedMemorySize, TsLong::smem));
@@ -437,7 +435,7 @@ int spmv_build_plan(csb200_mat *AT)
         DevBuf<int> d_max;
         CSB_TRY(d_max.alloc(1));
         CSB_CUDA(cudaMemsetAsync(d_max.ptr, 0, sizeof(int), stream()));
-        k_max_len<<<min(ceil_div(m, 256), 148 * 8), 256, 0, stream()>>>(AT->p, m, d_max.ptr);
+        k_max_len<<<min(ceil_div(m, 256), sm_count() * 8), 256, 0, stream()>>>(AT->p, m, d_max.ptr);
         CSB_LAUNCHED();
         CSB_CUDA(cudaMemcpyAsync(&h_max, d_max.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream()));
         CSB_CUDA(cudaStreamSynchronize(stream()));
@@ -538,7 +536,7 @@ int spmv_chunk_maxcol(csb200_mat *AT, int rows, int count, const int **out)
         DevBuf<int> d;
         CSB_TRY(d.alloc(8));
         CSB_CUDA(cudaMemsetAsync(d.ptr, 0xff, 8 * sizeof(int), stream()));
-        k_chunk_maxcol<<<dim3(148, count), 256, 0, stream()>>>(AT->p, AT->i, AT->n, rows, d.ptr);
+        k_chunk_maxcol<<<dim3(sm_count(), count), 256, 0, stream()>>>(AT->p, AT->i, AT->n, rows, d.ptr);
         CSB_LAUNCHED();
         CSB_CUDA(cudaMemcpyAsync(pl->chunk_maxcol, d.ptr, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
         CSB_CUDA(cudaStreamSynchronize(stream()));

@@ -925,7 +925,6 @@ k_mirror(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *_
 }
 
 // ---- host side -------------------------------------------------------------------
-int g_force_radix = 0;     // tests: 1 sends every transpose through the radix path, 2 skips the mirror path
 thread_local int t_last_path = 0;   // 1 mirror, 2 bucket sort, 3 radix sort, 0 trivial
 int transpose_last_path() { return t_last_path; }
 
@@ -984,7 +983,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     };
     // one-pass mirror path: tried on square matrices until the handle is known not to qualify; the
     // kernel verifies what it relies on (strictly increasing columns, symmetric pattern) and backs out
-    if (g_force_radix == 0 && m == n && A->mirror != 0) {
+    if (tls().force_transpose == 0 && m == n && A->mirror != 0) {
         DevBuf<int> flag;
         if ((st = flag.alloc(1)) != CSB200_OK) return fail(st);
         TR_CUDA(cudaMemsetAsync(flag.ptr, 0, sizeof(int), s));
@@ -995,7 +994,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
             int per_sm = 4;
             cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TR_THREADS, 0);
             if (e != cudaSuccess) return set_error(CSB200_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
-            const int grid = min(ntiles, 148 * max(per_sm, 1));
+            const int grid = min(ntiles, sm_count() * max(per_sm, 1));
             kern<<<grid, TR_THREADS, 0, s>>>(A->p, A->i, has_x ? A->x : nullptr, n, nnz, ntiles, tile_col.ptr, C->i,
                                              has_x ? C->x : nullptr, flag.ptr);
             return CSB200_OK;
@@ -1017,7 +1016,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
             return CSB200_OK;
         }
     }
-    if (g_force_radix == 1 || !packable) return radix_path();
+    if (tls().force_transpose == 1 || !packable) return radix_path();
     TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 2) * sizeof(int), s));
     {
         int *wide = bfill.ptr + nbuckets + 1, h_wide = 0;
@@ -1056,7 +1055,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     TR_LAUNCHED();
     if (warp_path) {
         constexpr int smem = WB_WARPS * WB_WARP_BYTES;
-        const int grid = min(ceil_div(nbuckets, WB_WARPS), 148 * 4);
+        const int grid = min(ceil_div(nbuckets, WB_WARPS), sm_count() * 4);
         if (has_x) k_bucket_sort_warp<true><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, ival.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
         else       k_bucket_sort_warp<false><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, nullptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
         TR_LAUNCHED();
@@ -1079,7 +1078,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
             if ((st = skey.alloc((size_t)h_ct[1])) != CSB200_OK) return fail(st);
             if (has_x && (st = sval.alloc((size_t)h_ct[1])) != CSB200_OK) return fail(st);
             const int smem = (int)((sizeof(int) * BIG_WARPS) << width);
-            const int grid = min(h_ct[0], 148);
+            const int grid = min(h_ct[0], sm_count());
             TR_CUDA(cudaFuncSetAttribute(k_bucket_big<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             TR_CUDA(cudaFuncSetAttribute(k_bucket_big<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             if (has_x) k_bucket_big<true><<<grid, BIG_THREADS, smem, s>>>(m, log_rb, nbuckets, colbits, width, npasses, big_list.ptr, big_soff.ptr, h_ct[0], bstart.ptr, ikey.ptr, ival.ptr, skey.ptr, sval.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
