@@ -52,6 +52,14 @@ PROTOTYPES = {
     "csb200_gaxpy_prepare": (C.c_int, [mat_t]),
     "csb200_gaxpy_plan": (C.c_int, [mat_t, intp]),
     "csb200_gaxpy_force_plan": (C.c_int, [mat_t, C.c_int]),
+    "csb200_halo_create": (C.c_int, [C.c_int64, matp]),
+    "csb200_halo_window": (C.c_int, [C.c_void_p, matp]),
+    "csb200_halo_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "csb200_halo_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
+    "csb200_halo_connect_local": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
+    "csb200_gaxpy_halo_dev": (C.c_int, [mat_t, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "csb200_halo_status": (C.c_int, [C.c_void_p, intp]),
+    "csb200_halo_free": (C.c_int, [C.c_void_p]),
     "csb200_multiply": (C.c_int, [mat_t, mat_t, matp]),
     "csb200_multiply_ordered": (C.c_int, [mat_t, mat_t, matp]),
     "csb200_multiply_force_path": (C.c_int, [C.c_int]),

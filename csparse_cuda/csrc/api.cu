@@ -38,6 +38,73 @@ int sm_count()
     return v;
 }
 
+Arena &arena()
+{
+    static thread_local Arena a;
+    return a;
+}
+
+static int arena_grow(Arena &a, size_t bytes)
+{
+    // nothing of the block is handed out here (outermost level, offset 0); kernels of earlier
+    // calls may still be reading it
+    cudaStream_t s = stream();
+    if (a.base) {
+        cudaStreamSynchronize(a.last_stream);
+        if (a.last_stream != s) cudaStreamSynchronize(s);
+        cudaFree(a.base);
+        cudaGetLastError();
+        a.base = nullptr;
+        a.cap = 0;
+    }
+    bytes += bytes / 8 + (1 << 20);
+    bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {      // no room for a private block: the pool keeps serving
+        cudaGetLastError();
+        return CSB200_OK;
+    }
+    a.base = static_cast<char *>(p);
+    a.cap = bytes;
+    return CSB200_OK;
+}
+
+int arena_enter()
+{
+    Arena &a = arena();
+    if (a.depth > 0) return CSB200_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return CSB200_OK; }
+    cudaStream_t s = stream();
+    if (a.base && a.device != dev) {                  // the thread moved to another GPU: start over there
+        int cur = dev;
+        cudaSetDevice(a.device);
+        cudaDeviceSynchronize();
+        cudaFree(a.base);
+        cudaGetLastError();
+        cudaSetDevice(cur);
+        a.base = nullptr; a.cap = 0; a.want = 0;
+    }
+    a.device = dev;
+    if (a.base && a.last_stream != s) cudaStreamSynchronize(a.last_stream);   // reuse is ordered by the stream
+    cudaGetLastError();
+    a.off = 0;
+    a.voff = 0;
+    if (a.want > a.cap) arena_grow(a, a.want);
+    a.last_stream = s;
+    return CSB200_OK;
+}
+
+void arena_hint(size_t bytes)
+{
+    Arena &a = arena();
+    if (bytes > a.want) a.want = bytes;
+    if (a.depth == 1 && a.off == 0 && a.want > a.cap) {
+        arena_grow(a, a.want);
+        a.last_stream = stream();
+    }
+}
+
 int ensure_device()
 {
     static std::mutex mu;
@@ -206,6 +273,7 @@ int64_t csb200_launch_count(void) { return g_launches.load(std::memory_order_rel
 // ---- cs_cumsum ---------------------------------------------------------------------
 int csb200_cumsum_dev(csi *d_p, csi *d_c, csi n, int64_t *total)
 {
+    ArenaScope arena_scope;
     if (!d_p || !d_c || n < 0) return set_error(CSB200_ERR_ARG, "cs_cumsum: null array or n < 0");
     DevBuf<long long> d_total;
     CSB_TRY(d_total.alloc(1));
@@ -221,6 +289,7 @@ int csb200_cumsum_dev(csi *d_p, csi *d_c, csi n, int64_t *total)
 
 int csb200_cumsum(csi *p, csi *c, csi n, int64_t *total)
 {
+    ArenaScope arena_scope;
     if (!p || !c || n < 0) return set_error(CSB200_ERR_ARG, "cs_cumsum: null array or n < 0");
     DevBuf<csi> d_p, d_c;
     CSB_TRY(d_p.alloc((size_t)n + 1));
@@ -238,6 +307,7 @@ int csb200_cumsum(csi *p, csi *c, csi n, int64_t *total)
 int csb200_mat_upload(csi m, csi n, const csi *p, const csi *i, const double *x, int validate,
                       csb200_mat **out)
 {
+    ArenaScope arena_scope;
     if (!out) return set_error(CSB200_ERR_ARG, "null out");
     *out = nullptr;
     if (m < 0 || n < 0 || !p || (!i && p[n] > 0)) return set_error(CSB200_ERR_ARG, "mat_upload: bad arguments");
@@ -390,6 +460,7 @@ int csb200_mat_free(csb200_mat *A)
 // ---- cs_transpose ---------------------------------------------------------------------
 int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!A || !C) return set_error(CSB200_ERR_ARG, "cs_transpose: null argument");
     *C = nullptr;
     return transpose_impl(A, values != 0, C);
@@ -407,6 +478,7 @@ int csb200_transpose_last_path(void) { return transpose_last_path(); }
 int csb200_transpose_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
                           csi *Cp, csi *Ci, double *Cx)
 {
+    ArenaScope arena_scope;
     if (!Cp || !Ci) return set_error(CSB200_ERR_ARG, "cs_transpose: null output");
     csb200_mat *A = nullptr, *C = nullptr;
     CSB_TRY(csb200_mat_upload(m, n, Ap, Ai, (Ax && Cx) ? Ax : nullptr, 1, &A));
@@ -420,6 +492,7 @@ int csb200_transpose_host(csi m, csi n, const csi *Ap, const csi *Ai, const doub
 // ---- cs_gaxpy -------------------------------------------------------------------------
 int csb200_gaxpy_prepare(csb200_mat *A)
 {
+    ArenaScope arena_scope;
     if (!A) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null matrix");
     CSB_TRY(ensure_csr(A));
     return spmv_build_plan(A->csr);
@@ -427,6 +500,7 @@ int csb200_gaxpy_prepare(csb200_mat *A)
 
 int csb200_gaxpy_plan(csb200_mat *A, int *kind)
 {
+    ArenaScope arena_scope;
     if (!A || !kind) return set_error(CSB200_ERR_ARG, "null argument");
     CSB_TRY(csb200_gaxpy_prepare(A));
     *kind = spmv_plan_kind(A->csr->plan);
@@ -443,6 +517,7 @@ int csb200_gaxpy_force_plan(csb200_mat *A, int kind)
 
 int csb200_gaxpy_dev(csb200_mat *A, const double *d_x, double *d_y)
 {
+    ArenaScope arena_scope;
     if (!A || !d_x || !d_y) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null argument");
     CSB_TRY(ensure_csr(A));
     return spmv_run(A->csr, d_x, d_y);
@@ -450,12 +525,14 @@ int csb200_gaxpy_dev(csb200_mat *A, const double *d_x, double *d_y)
 
 int csb200_gaxpy_t_dev(csb200_mat *AT, const double *d_x, double *d_y)
 {
+    ArenaScope arena_scope;
     if (!AT || !d_x || !d_y) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null argument");
     return spmv_run(AT, d_x, d_y);
 }
 
 int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
 {
+    ArenaScope arena_scope;
     if (!A || !x || !y) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null argument");
     if (!A->x) return set_error(CSB200_ERR_ARG, "cs_gaxpy: matrix has no values");
     DevBuf<double> d_x, d_y;
@@ -525,6 +602,7 @@ int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
 int csb200_gaxpy_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
                       const double *x, double *y)
 {
+    ArenaScope arena_scope;
     if (!Ax) return set_error(CSB200_ERR_ARG, "cs_gaxpy: matrix has no values");
     if (!x || !y) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null vector");
     csb200_mat *A = nullptr;
@@ -537,6 +615,7 @@ int csb200_gaxpy_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *
 // ---- cs_multiply ------------------------------------------------------------------------
 int csb200_multiply(const csb200_mat *A, const csb200_mat *B, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!A || !B || !C) return set_error(CSB200_ERR_ARG, "cs_multiply: null argument");
     *C = nullptr;
     if (A->n != B->m) return set_error(CSB200_ERR_ARG, "cs_multiply: A.n != B.m");   // csparse.py:1618-1619
@@ -545,6 +624,7 @@ int csb200_multiply(const csb200_mat *A, const csb200_mat *B, csb200_mat **C)
 
 int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!A || !B || !C) return set_error(CSB200_ERR_ARG, "cs_multiply: null argument");
     *C = nullptr;
     if (A->n != B->m) return set_error(CSB200_ERR_ARG, "cs_multiply: A.n != B.m");

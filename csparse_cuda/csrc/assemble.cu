@@ -292,6 +292,7 @@ extern "C" {
 // ---- cs_add ------------------------------------------------------------------------------------
 int csb200_add(csb200_mat *A, csb200_mat *B, double alpha, double beta, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!A || !B || !C) return set_error(CSB200_ERR_ARG, "cs_add: null argument");
     *C = nullptr;
     if (A->m != B->m || A->n != B->n) return set_error(CSB200_ERR_ARG, "cs_add: dimension mismatch");
@@ -369,6 +370,7 @@ int csb200_add_force_path(int path)
 // ---- cs_norm -----------------------------------------------------------------------------------
 int csb200_norm(const csb200_mat *A, double *norm)
 {
+    ArenaScope arena_scope;
     if (!A || !norm || !A->x) return set_error(CSB200_ERR_ARG, "cs_norm: null argument or no values");
     *norm = 0.0;
     if (A->n == 0) return CSB200_OK;
@@ -388,6 +390,7 @@ int csb200_norm(const csb200_mat *A, double *norm)
 int csb200_compress_dev(csi m, csi n, csi nz, const csi *d_Ti, const csi *d_Tj, const double *d_Tx,
                         csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!C || m < 0 || n < 0 || nz < 0 || (nz > 0 && (!d_Ti || !d_Tj)))
         return set_error(CSB200_ERR_ARG, "cs_compress: bad arguments");
     *C = nullptr;
@@ -404,6 +407,7 @@ int csb200_compress_dev(csi m, csi n, csi nz, const csi *d_Ti, const csi *d_Tj, 
 
 int csb200_compress(csi m, csi n, csi nz, const csi *Ti, const csi *Tj, const double *Tx, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!C || nz < 0 || (nz > 0 && (!Ti || !Tj))) return set_error(CSB200_ERR_ARG, "cs_compress: bad arguments");
     DevBuf<csi> dI, dJ;
     DevBuf<double> dX;
@@ -425,6 +429,7 @@ int csb200_compress(csi m, csi n, csi nz, const csi *Ti, const csi *Tj, const do
 // ---- cs_dupl -----------------------------------------------------------------------------------
 int csb200_dupl(csb200_mat *A, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!A || !C || !A->x) return set_error(CSB200_ERR_ARG, "cs_dupl: null argument or no values");
     *C = nullptr;
     const csi n = A->n;
@@ -441,6 +446,7 @@ int csb200_dupl(csb200_mat *A, csb200_mat **C)
 // ---- cs_fkeep with a fixed predicate -------------------------------------------------------------
 int csb200_fkeep(const csb200_mat *A, int predicate, double tol, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!A || !C || predicate < KEEP_NONZERO || predicate > KEEP_SHORTCOL)
         return set_error(CSB200_ERR_ARG, "cs_fkeep: bad arguments");
     *C = nullptr;
@@ -471,6 +477,7 @@ int csb200_fkeep(const csb200_mat *A, int predicate, double tol, csb200_mat **C)
 // ---- cs_permute ------------------------------------------------------------------------------------
 int csb200_permute(const csb200_mat *A, const csi *pinv, const csi *q, int values, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!A || !C) return set_error(CSB200_ERR_ARG, "cs_permute: null argument");
     *C = nullptr;
     const csi m = A->m, n = A->n;
@@ -517,6 +524,7 @@ int csb200_permute(const csb200_mat *A, const csi *pinv, const csi *q, int value
 // ---- cs_symperm -------------------------------------------------------------------------------------
 int csb200_symperm(const csb200_mat *A, const csi *pinv, int values, csb200_mat **C)
 {
+    ArenaScope arena_scope;
     if (!A || !C) return set_error(CSB200_ERR_ARG, "cs_symperm: null argument");
     *C = nullptr;
     const csi n = A->n;

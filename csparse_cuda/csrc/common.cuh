@@ -54,7 +54,8 @@ inline cudaStream_t stream() { return tls().stream; }
 int sm_count();
 
 // stream-ordered allocation from the device's default memory pool (cached: the
-// release threshold is raised once per device in ensure_device()).
+// release threshold is raised once per device in ensure_device()).  Results (the p / i / x of a
+// handle) and per-handle caches come from here.
 int ensure_device();
 template <class T>
 inline int dev_alloc(T **p, size_t count)
@@ -75,13 +76,62 @@ inline void dev_free(void *p)
     if (p) cudaFreeAsync(p, stream());
 }
 
-// RAII for temporaries inside an API call
+// ---- per-thread workspace arena ------------------------------------------------------------
+// Temporaries of an API call (histograms, bucket intermediates, work lists, block tables) are
+// bump-allocated from ONE block per thread that only ever grows: a call never touches the
+// stream-ordered pool for them, so the pool sees nothing but same-sized results and the first
+// call after an upload costs what the tenth does.  Stream order makes reuse safe: the next call's
+// kernels queue behind this call's on the same stream (a thread that switches streams pays one
+// synchronize).  Requests the block cannot hold fall back to the pool for that call and raise
+// the high-water mark, so the next outermost scope grows the block once.
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, off = 0;
+    size_t voff = 0;          // like off, but also counting the requests that overflowed to the pool
+    size_t want = 0;          // high-water mark of voff: what the block should hold
+    int depth = 0;
+    int device = -1;
+    cudaStream_t last_stream = nullptr;
+};
+Arena &arena();
+int arena_enter();            // ArenaScope's constructor: grows the block at the outermost level if needed
+void arena_hint(size_t bytes);   // "this call will need about this much": grows right away when nothing is in use
+struct ArenaScope {
+    size_t saved_off, saved_voff;
+    ArenaScope() { Arena &a = arena(); arena_enter(); saved_off = a.off; saved_voff = a.voff; a.depth++; }
+    ~ArenaScope()
+    {
+        Arena &a = arena();
+        a.depth--;
+        a.off = saved_off;
+        a.voff = saved_voff;
+    }
+};
+
+// RAII for temporaries inside an API call: from the arena when a scope is open and the block has
+// room, else from the pool (freed stream-ordered on destruction)
 template <class T>
 struct DevBuf {
     T *ptr = nullptr;
-    ~DevBuf() { dev_free(ptr); }
-    int alloc(size_t count) { return dev_alloc(&ptr, count); }
-    T *release() { T *r = ptr; ptr = nullptr; return r; }
+    bool pooled = false;
+    ~DevBuf() { if (pooled) dev_free(ptr); }
+    int alloc(size_t count)
+    {
+        if (count == 0) count = 1;
+        const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        Arena &a = arena();
+        if (a.depth > 0) {
+            a.voff += bytes;
+            if (a.voff > a.want) a.want = a.voff;
+            if (a.base && a.off + bytes <= a.cap) {
+                ptr = reinterpret_cast<T *>(a.base + a.off);
+                a.off += bytes;
+                return CSB200_OK;
+            }
+        }
+        pooled = true;
+        return dev_alloc(&ptr, count);
+    }
     operator T *() const { return ptr; }
 };
 

@@ -253,6 +253,8 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
     const int ntiles = ceil_div(nnz, RS_TILE);
     const size_t recsz = VALUES ? sizeof(RsRec) : sizeof(RsRecP);
 
+    arena_hint((size_t)nnz * 4 + (npasses >= 3 ? 2 : npasses >= 2 ? 1 : 0) * (size_t)nnz * recsz +
+               (size_t)ntiles * RS_BINS * 8 + (1 << 16));
     DevBuf<unsigned long long> hist, status;
     DevBuf<unsigned> ticket;
     DevBuf<unsigned char> bufA, bufB;

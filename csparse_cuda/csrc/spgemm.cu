@@ -874,6 +874,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
     int canon = 1;
     if ((st = mat_is_canonical(A, &canon)) != CSB200_OK) return fail(st);
 
+    arena_hint((size_t)(n > 0 ? n : 1) * (8 * 4 + BLK_STRIDE * sizeof(int2)) + (1 << 16));
     DevBuf<int> ub, cnt, lists, counts, marks, marks_num, nblk, pick;
     DevBuf<int2> blkbuf;
     DevBuf<double> acc;

@@ -17,6 +17,7 @@
 //                  equal tiles per CTA and equal runs per thread, carry-out of
 //                  the unfinished row fixed up by k_merge_fixup (deterministic).
 #include "common.cuh"
+#include <string.h>
 
 struct SpmvPlan {
     int kind = 0;            // 1 stream (TMA-staged), 2 merge, 3 stream (plain loads)
@@ -164,16 +165,102 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <class SH>
+// ---- fused halo exchange (multi-GPU row-block sharding) ----------------
+// Each rank owns a slice of x inside a local window [lo halo | own | hi halo].  Instead of an NCCL
+// send/recv per step, the ONE persistent SpMV launch pulls the two halos from the neighbours'
+// windows over NVLink (peer-mapped pointers): CTA 0 tells the neighbours "my x of this epoch is
+// final", waits for theirs, copies the halo lines, raises a local flag and acknowledges the pull.
+// Row blocks that read halo entries are moved to the END of the persistent sweep and wait for the
+// flag (set long before they are reached); the launch ends only when both neighbours have pulled,
+// so the caller may overwrite x as soon as the kernel has completed on its stream.
+// Comm block (ints): [0] x ready, set by the lo neighbour  [1] x ready, set by the hi neighbour
+//                    [2] pulled, set by the lo neighbour   [3] pulled, set by the hi neighbour
+//                    [4] halo landed (local)               [5] a wait timed out (diagnostic)
+struct HaloArgs {
+    int *comm;
+    int *peer_comm[2];
+    const double *peer_x[2];
+    double *dst[2];
+    int cnt[2];
+    int epoch;
+    int top_blocks, bot_blocks;
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p >= epoch; gives up after ~2 s of SM clocks (a dead neighbour must not hang the GPU)
+__device__ __forceinline__ void halo_wait(const int *p, int epoch, int *err)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < epoch) {
+        if (clock64() - t0 > 4000000000LL) { *err = 1; break; }
+        __nanosleep(64);
+    }
+}
+// executed by `nthreads` threads (ids tid) that can meet on named barrier 1
+template <int NTHREADS>
+__device__ __forceinline__ void halo_pull(const HaloArgs &h, int tid)
+{
+    if (tid == 0) {
+        if (h.peer_comm[0]) st_release_sys(h.peer_comm[0] + 1, h.epoch);     // I am its hi neighbour
+        if (h.peer_comm[1]) st_release_sys(h.peer_comm[1] + 0, h.epoch);     // I am its lo neighbour
+        if (h.peer_comm[0]) halo_wait(h.comm + 0, h.epoch, h.comm + 5);
+        if (h.peer_comm[1]) halo_wait(h.comm + 1, h.epoch, h.comm + 5);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+#pragma unroll
+    for (int side = 0; side < 2; side++)
+        if (h.peer_x[side])
+            for (int k = tid; k < h.cnt[side]; k += NTHREADS) h.dst[side][k] = ld_relaxed_sys(h.peer_x[side] + k);
+    __threadfence();
+    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+    if (tid == 0) {
+        st_release_sys(h.comm + 4, h.epoch);
+        if (h.peer_comm[0]) st_release_sys(h.peer_comm[0] + 3, h.epoch);
+        if (h.peer_comm[1]) st_release_sys(h.peer_comm[1] + 2, h.epoch);
+    }
+}
+__device__ __forceinline__ void halo_wait_acks(const HaloArgs &h)
+{
+    if (h.peer_comm[0]) halo_wait(h.comm + 2, h.epoch, h.comm + 5);
+    if (h.peer_comm[1]) halo_wait(h.comm + 3, h.epoch, h.comm + 5);
+}
+
+// stand-alone forms for plans without the fused kernel (merge path): pull before, acks after
+__global__ void __launch_bounds__(512) k_halo_pull(HaloArgs h) { halo_pull<512>(h, threadIdx.x); }
+__global__ void k_halo_acks(HaloArgs h) { halo_wait_acks(h); }
+
+template <class SH, bool HALO>
 __global__ void __launch_bounds__(TS_THREADS, 2)
 k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi *__restrict__ col,
-           const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+           const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y, HaloArgs halo)
 {
     constexpr int TS_TILE = SH::tile, TS_STAGES = SH::stages, TS_STAGE_BYTES = SH::stage_bytes;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TS_STAGES * TS_STAGE_BYTES);
     const int tid = threadIdx.x;
     const int niter = (nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // HALO: interior row blocks first, the blocks that read halo entries last
+    const int n_int = HALO ? nblocks - halo.top_blocks - halo.bot_blocks : nblocks;
+    auto block_of = [&](int q) -> int {
+        if (!HALO || q < n_int) return (HALO ? halo.top_blocks : 0) + q;
+        const int qb = q - n_int;
+        return qb < halo.top_blocks ? qb : n_int + qb;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < TS_STAGES; s++) {
@@ -190,7 +277,7 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
             for (int it = 0; it < niter; it++) {
                 const int stage = it % TS_STAGES;
                 if (it >= TS_STAGES) mbar_wait(smem_u32(&bars[TS_STAGES + stage]), ((it / TS_STAGES) - 1) & 1);
-                const int blk = blockIdx.x + it * gridDim.x;
+                const int blk = block_of(blockIdx.x + it * gridDim.x);
                 const int r0 = blk * R;
                 const int nrows = min(R, m - r0);
                 const int start = rowptr[r0], end = rowptr[r0 + nrows];
@@ -213,9 +300,18 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
 
     // ---------------- consumers ----------------
     const int lane = tid & 31;
+    if (HALO && blockIdx.x == 0) halo_pull<TS_CONSUMERS>(halo, tid);
+    bool halo_seen = false;
     for (int it = 0; it < niter; it++) {
         const int stage = it % TS_STAGES;
-        const int blk = blockIdx.x + it * gridDim.x;
+        const int q = blockIdx.x + it * gridDim.x;
+        const int blk = block_of(q);
+        const bool edge = HALO && q >= n_int;          // this block reads halo entries: they must have landed
+        if (edge && !halo_seen) {
+            if (tid == 0) halo_wait(halo.comm + 4, halo.epoch, halo.comm + 5);
+            asm volatile("bar.sync 1, %0;" ::"n"(TS_CONSUMERS) : "memory");
+            halo_seen = true;
+        }
         const int r0 = blk * R;
         const int nrows = min(R, m - r0);
         double yv = 0.0;
@@ -235,17 +331,20 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
                 const double2 v1 = *reinterpret_cast<const double2 *>(sval + k + 2);
                 const int g = a0 + k;                         // global index of the first of four entries
                 if (g >= start && g + 3 < end) {
-                    const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+                    double x0, x1, x2, x3;
+                    if (edge) { x0 = __ldcg(x + c.x); x1 = __ldcg(x + c.y); x2 = __ldcg(x + c.z); x3 = __ldcg(x + c.w); }   // L2: the halo landed during this launch
+                    else      { x0 = __ldg(x + c.x); x1 = __ldg(x + c.y); x2 = __ldg(x + c.z); x3 = __ldg(x + c.w); }
                     double2 o0, o1;
                     o0.x = __dmul_rn(v0.x, x0); o0.y = __dmul_rn(v0.y, x1);
                     o1.x = __dmul_rn(v1.x, x2); o1.y = __dmul_rn(v1.y, x3);
                     *reinterpret_cast<double2 *>(sval + k) = o0;
                     *reinterpret_cast<double2 *>(sval + k + 2) = o1;
                 } else {                                      // ragged ends: entries of neighbouring blocks / padding
-                    if (g >= start && g < end) sval[k] = __dmul_rn(v0.x, __ldg(x + c.x));
-                    if (g + 1 >= start && g + 1 < end) sval[k + 1] = __dmul_rn(v0.y, __ldg(x + c.y));
-                    if (g + 2 >= start && g + 2 < end) sval[k + 2] = __dmul_rn(v1.x, __ldg(x + c.z));
-                    if (g + 3 >= start && g + 3 < end) sval[k + 3] = __dmul_rn(v1.y, __ldg(x + c.w));
+                    auto ldx = [&](const double *p) { return edge ? __ldcg(p) : __ldg(p); };
+                    if (g >= start && g < end) sval[k] = __dmul_rn(v0.x, ldx(x + c.x));
+                    if (g + 1 >= start && g + 1 < end) sval[k + 1] = __dmul_rn(v0.y, ldx(x + c.y));
+                    if (g + 2 >= start && g + 2 < end) sval[k + 2] = __dmul_rn(v1.x, ldx(x + c.z));
+                    if (g + 3 >= start && g + 3 < end) sval[k + 3] = __dmul_rn(v1.y, ldx(x + c.w));
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TS_CONSUMERS) : "memory");
@@ -262,7 +361,8 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
             for (int row = tid >> 5; row < nrows; row += TS_CONSUMERS / 32) {
                 const int b = srp[row], e = srp[row + 1];
                 double s = 0.0;
-                for (int k = b + lane; k < e; k += 32) s = __dadd_rn(s, __dmul_rn(val[k], __ldg(x + col[k])));
+                for (int k = b + lane; k < e; k += 32)
+                    s = __dadd_rn(s, __dmul_rn(val[k], edge ? __ldcg(x + col[k]) : __ldg(x + col[k])));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_down_sync(0xffffffffu, s, o));
                 if (lane == 0 && e > b) y[r0 + row] = __dadd_rn(y[r0 + row], s);
@@ -273,20 +373,25 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[TS_STAGES + stage]));
     }
+    // the neighbours have read my x of this epoch: the caller may overwrite it after this launch
+    if (HALO && blockIdx.x == 0 && tid == 0) halo_wait_acks(halo);
 }
 
 static int launch_spmv_tma(bool long_rows, int m, int nblocks, int R, const csi *rowptr, const csi *col,
-                           const double *val, const double *x, double *y, cudaStream_t s)
+                           const double *val, const double *x, double *y, cudaStream_t s, const HaloArgs *halo = nullptr)
 {
     const int sms = sm_count();
     const int grid = min(nblocks, 2 * sms);          // two resident CTAs per SM
-    if (long_rows) {
-        CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma<TsLong>, cudaFuncAttributeMaxDynamicSharedMemorySize, TsLong::smem));
-        k_spmv_tma<TsLong><<<grid, TS_THREADS, TsLong::smem, s>>>(m, nblocks, R, rowptr, col, val, x, y);
-    } else {
-        CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma<TsShort>, cudaFuncAttributeMaxDynamicSharedMemorySize, TsShort::smem));
-        k_spmv_tma<TsShort><<<grid, TS_THREADS, TsShort::smem, s>>>(m, nblocks, R, rowptr, col, val, x, y);
-    }
+    HaloArgs h{};
+    if (halo) h = *halo;
+#define TMA_LAUNCH(SH, HALO)                                                                                  \
+    do {                                                                                                      \
+        CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma<SH, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH::smem)); \
+        k_spmv_tma<SH, HALO><<<grid, TS_THREADS, SH::smem, s>>>(m, nblocks, R, rowptr, col, val, x, y, h);       \
+    } while (0)
+    if (long_rows) { if (halo) TMA_LAUNCH(TsLong, true); else TMA_LAUNCH(TsLong, false); }
+    else           { if (halo) TMA_LAUNCH(TsShort, true); else TMA_LAUNCH(TsShort, false); }
+#undef TMA_LAUNCH
     CSB_LAUNCHED();
     return CSB200_OK;
 }
@@ -562,3 +667,188 @@ int spmv_run_rows(csb200_mat *AT, const double *d_x, double *d_y, int ra, int rb
 namespace csb {
 int spmv_plan_kind(const SpmvPlan *pl) { return pl ? pl->kind : 0; }
 }
+
+// ---- the halo object: x window + comm block of one rank, peer-mapped views of its neighbours' ----
+struct csb200_halo {
+    double *window = nullptr;       // cudaMalloc (IPC-exportable), `count` doubles
+    int *comm = nullptr;            // 8 ints
+    long long count = 0;
+    int device = 0;
+    int epoch = 0;
+    // per side (0 = lo neighbour, 1 = hi neighbour)
+    void *peer_window_base[2] = {nullptr, nullptr};   // mapping to close (IPC) or null (same-process peer)
+    void *peer_comm_base[2] = {nullptr, nullptr};
+    const double *peer_x[2] = {nullptr, nullptr};
+    int *peer_comm[2] = {nullptr, nullptr};
+    long long local_first[2] = {0, 0};
+    int cnt[2] = {0, 0};
+};
+
+using namespace csb;
+
+static HaloArgs halo_args(csb200_halo *h, int top_blocks, int bot_blocks)
+{
+    HaloArgs a{};
+    a.comm = h->comm;
+    for (int s = 0; s < 2; s++) {
+        a.peer_comm[s] = h->peer_comm[s];
+        a.peer_x[s] = h->peer_x[s];
+        a.dst[s] = h->window + h->local_first[s];
+        a.cnt[s] = h->cnt[s];
+    }
+    a.epoch = h->epoch;
+    a.top_blocks = top_blocks;
+    a.bot_blocks = bot_blocks;
+    return a;
+}
+
+extern "C" {
+
+int csb200_halo_create(int64_t count, csb200_halo **out)
+{
+    if (!out || count < 0) return set_error(CSB200_ERR_ARG, "halo_create: bad arguments");
+    *out = nullptr;
+    CSB_TRY(ensure_device());
+    csb200_halo *h = new csb200_halo();
+    h->count = count;
+    cudaGetDevice(&h->device);
+    cudaError_t e = cudaMalloc((void **)&h->window, (size_t)(count > 0 ? count : 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->comm, 8 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->window, 0, (size_t)(count > 0 ? count : 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(h->comm, 0, 8 * sizeof(int));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(h->window); cudaFree(h->comm);
+        delete h;
+        return set_error(e == cudaErrorMemoryAllocation ? CSB200_ERR_NOMEM : CSB200_ERR_CUDA, "halo_create: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return CSB200_OK;
+}
+
+int csb200_halo_window(csb200_halo *h, double **d_window)
+{
+    if (!h || !d_window) return set_error(CSB200_ERR_ARG, "halo_window: null argument");
+    *d_window = h->window;
+    return CSB200_OK;
+}
+
+int csb200_halo_export(csb200_halo *h, void *handles)
+{
+    if (!h || !handles) return set_error(CSB200_ERR_ARG, "halo_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two 64-byte handles");
+    cudaIpcMemHandle_t hw, hc;
+    CSB_CUDA(cudaIpcGetMemHandle(&hw, h->window));
+    CSB_CUDA(cudaIpcGetMemHandle(&hc, h->comm));
+    memcpy(handles, &hw, 64);
+    memcpy(static_cast<char *>(handles) + 64, &hc, 64);
+    return CSB200_OK;
+}
+
+static int halo_set_side(csb200_halo *h, int side, const double *pw, int *pc, int64_t peer_first, int64_t count, int64_t local_first)
+{
+    if (count < 0 || count > 0x7fffffff || local_first < 0 || local_first + count > h->count || peer_first < 0)
+        return set_error(CSB200_ERR_ARG, "halo_connect: range outside the window");
+    h->peer_x[side] = pw + peer_first;
+    h->peer_comm[side] = pc;
+    h->local_first[side] = local_first;
+    h->cnt[side] = (int)count;
+    return CSB200_OK;
+}
+
+int csb200_halo_connect(csb200_halo *h, int side, const void *peer_handles, int64_t peer_first, int64_t count,
+                        int64_t local_first)
+{
+    if (!h || !peer_handles || side < 0 || side > 1) return set_error(CSB200_ERR_ARG, "halo_connect: bad arguments");
+    cudaIpcMemHandle_t hw, hc;
+    memcpy(&hw, peer_handles, 64);
+    memcpy(&hc, static_cast<const char *>(peer_handles) + 64, 64);
+    void *pw = nullptr, *pc = nullptr;
+    CSB_CUDA(cudaIpcOpenMemHandle(&pw, hw, cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaIpcOpenMemHandle(&pc, hc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaIpcCloseMemHandle(pw);
+        return set_error(CSB200_ERR_CUDA, "halo_connect: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    }
+    h->peer_window_base[side] = pw;
+    h->peer_comm_base[side] = pc;
+    return halo_set_side(h, side, static_cast<const double *>(pw), static_cast<int *>(pc), peer_first, count, local_first);
+}
+
+int csb200_halo_connect_local(csb200_halo *h, int side, csb200_halo *peer, int64_t peer_first, int64_t count,
+                              int64_t local_first)
+{
+    if (!h || !peer || side < 0 || side > 1) return set_error(CSB200_ERR_ARG, "halo_connect_local: bad arguments");
+    if (peer->device != h->device) {
+        int can = 0;
+        CSB_CUDA(cudaDeviceCanAccessPeer(&can, h->device, peer->device));
+        if (!can) return set_error(CSB200_ERR_CUDA, "halo_connect_local: no peer access between devices %d and %d", h->device, peer->device);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(h->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        cudaSetDevice(cur);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return set_error(CSB200_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    return halo_set_side(h, side, peer->window, peer->comm, peer_first, count, local_first);
+}
+
+// y[0..AT.n) += AT' * window, the halos pulled from the neighbours inside the same launch.
+// top_rows / bot_rows: rows at the two ends of the block that read halo entries.
+int csb200_gaxpy_halo_dev(csb200_mat *AT, csb200_halo *h, double *d_y, csi top_rows, csi bot_rows)
+{
+    if (!AT || !h || !d_y || top_rows < 0 || bot_rows < 0) return set_error(CSB200_ERR_ARG, "cs_gaxpy: null argument");
+    if (!AT->x) return set_error(CSB200_ERR_ARG, "cs_gaxpy: matrix has no values");
+    if (AT->m > h->count) return set_error(CSB200_ERR_ARG, "cs_gaxpy: the x window is shorter than the block's column range");
+    ArenaScope arena_scope;
+    CSB_TRY(spmv_build_plan(AT));
+    const int m = AT->n;
+    h->epoch++;
+    SpmvPlan *pl = AT->plan;
+    cudaStream_t s = stream();
+    if (m > 0 && AT->nnz > 0 && pl->kind == 1) {
+        const int R = pl->rows_per_cta;
+        const int nblocks = ceil_div(m, R);
+        int tb = ceil_div(top_rows, R), bb = ceil_div(bot_rows, R);
+        if (tb + bb > nblocks) { tb = nblocks; bb = 0; }
+        const HaloArgs a = halo_args(h, tb, bb);
+        return launch_spmv_tma(pl->long_rows, m, nblocks, R, AT->p, AT->i, AT->x, h->window, d_y, s, &a);
+    }
+    const HaloArgs a = halo_args(h, 0, 0);
+    k_halo_pull<<<1, 512, 0, s>>>(a);
+    CSB_LAUNCHED();
+    CSB_TRY(spmv_run(AT, h->window, d_y));
+    k_halo_acks<<<1, 1, 0, s>>>(a);
+    CSB_LAUNCHED();
+    return CSB200_OK;
+}
+
+int csb200_halo_status(csb200_halo *h, int *timed_out)
+{
+    if (!h || !timed_out) return set_error(CSB200_ERR_ARG, "halo_status: null argument");
+    int v = 0;
+    CSB_CUDA(cudaMemcpyAsync(&v, h->comm + 5, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    CSB_CUDA(cudaStreamSynchronize(stream()));
+    *timed_out = v;
+    return CSB200_OK;
+}
+
+int csb200_halo_free(csb200_halo *h)
+{
+    if (!h) return CSB200_OK;
+    cudaDeviceSynchronize();
+    for (int s = 0; s < 2; s++) {
+        if (h->peer_window_base[s]) cudaIpcCloseMemHandle(h->peer_window_base[s]);
+        if (h->peer_comm_base[s]) cudaIpcCloseMemHandle(h->peer_comm_base[s]);
+    }
+    cudaFree(h->window);
+    cudaFree(h->comm);
+    cudaGetLastError();
+    delete h;
+    return CSB200_OK;
+}
+
+}  // extern "C"

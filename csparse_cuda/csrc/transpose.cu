@@ -969,6 +969,8 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     while (colbits < 31 && (1LL << colbits) < (long long)n) colbits++;
     const bool packable = colbits + log_rb <= 31;
 
+    // temporaries of the bucket path: one packed word + one value per entry, bucket tables, tile table
+    arena_hint((size_t)nnz * 12 + (size_t)nbuckets * 24 + (size_t)ntiles * 4 + (1 << 16));
     DevBuf<int> bstart, bfill, tile_col;
     DevBuf<long long> total;
     if ((st = bstart.alloc((size_t)nbuckets + 1)) || (st = bfill.alloc((size_t)nbuckets + 2)) ||

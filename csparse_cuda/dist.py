@@ -122,7 +122,7 @@ class ShardedGaxpy:
 
     def __init__(self, block: RowBlock, m_global: int, n_global: int, row_bounds, x_bounds=None,
                  make_local: Callable = None, local_spmv: Callable = None, device="cpu", group=None,
-                 force_gather: bool = False):
+                 force_gather: bool = False, fused: bool = False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
@@ -150,7 +150,15 @@ class ShardedGaxpy:
         self.plan = plan_exchange(self.rank, self.world, self.x_bounds, windows, n_global, force_gather)
         pl = self.plan
         self.c0, self.c1 = int(self.x_bounds[self.rank]), int(self.x_bounds[self.rank + 1])
-        self.x_window = torch.zeros(pl.win_hi - pl.win_lo, dtype=torch.float64, device=device)
+        # fused: the halos are pulled over NVLink inside the one SpMV launch (csb200_gaxpy_halo_dev)
+        # from peer-mapped windows; otherwise batched NCCL / gloo send-recv fills a torch tensor
+        self.fused = bool(fused) and pl.mode == "halo" and self.world > 1
+        self.halo = None
+        if self.fused:
+            self.halo = FusedHalo(pl.win_hi - pl.win_lo, device)
+            self.x_window = self.halo.window
+        else:
+            self.x_window = torch.zeros(pl.win_hi - pl.win_lo, dtype=torch.float64, device=device)
         self.own = slice(self.c0 - pl.win_lo, self.c1 - pl.win_lo)       # my slice inside the window
         col_local = (block.col.astype(np.int64) - pl.win_lo).astype(np.int32)
         self.local_spmv = local_spmv
@@ -174,7 +182,16 @@ class ShardedGaxpy:
             if top < bot and (len(lo_rows) == 0 or lo_rows.max() < bot) and (len(hi_rows) == 0 or hi_rows.min() >= top):
                 self.split = (top, bot)
         ncl = pl.win_hi - pl.win_lo
-        if self.split:
+        if self.fused:
+            # one handle for the whole block; the kernel runs the rows [top, bot) first and the rows
+            # that read halo entries last (all of them when the block does not split)
+            top, bot = self.split if self.split else (nrows, nrows)
+            self.top_rows, self.bot_rows = top, nrows - bot
+            self.handle = make_local(block.rowptr, col_local, block.val, ncl)
+            self.h_top = self.h_bot = None
+            self.halo.connect(self, group)
+            self.exchanged_bytes = 8 * (pl.lo_need[self.rank] + pl.hi_need[self.rank])
+        elif self.split:
             top, bot = self.split
             rp = block.rowptr
 
@@ -251,6 +268,10 @@ class ShardedGaxpy:
     def step(self, x_own, y_own):
         """One distributed cs_gaxpy: exchange x, then y_own += A_block * x_window.  In halo
         mode the interior rows run while the halos are in flight."""
+        if self.fused:
+            self._place(x_own)
+            self.halo.step(self.handle, y_own, self.top_rows, self.bot_rows)
+            return y_own
         if self.split:
             top, bot = self.split
             works = self._exchange_start(x_own)
@@ -265,6 +286,73 @@ class ShardedGaxpy:
         xw = self.exchange(x_own)
         self.local_spmv(self.handle, xw, y_own)
         return y_own
+
+
+# ---- fused halo exchange: peer-mapped x windows (libcsparse_b200.so, csb200_halo_*) -------------
+
+class FusedHalo:
+    """The rank's x window in IPC-exportable device memory plus the flag block the persistent SpMV
+    kernel uses to pull the neighbours' halo lines over NVLink (csparse_cuda/csrc/spmv.cu).  The
+    128-byte IPC handles are exchanged once with torch.distributed; per step there is no
+    collective and no extra launch."""
+
+    def __init__(self, count: int, device):
+        import ctypes as C
+        import torch
+        from . import _lib
+        self._lib, self._C = _lib, C
+        h = C.c_void_p()
+        _lib.check(_lib.lib().csb200_halo_create(int(count), C.byref(h)), "halo_create")
+        self._h = h
+        w = C.c_void_p()
+        _lib.check(_lib.lib().csb200_halo_window(self._h, C.byref(w)), "halo_window")
+        self.window = _as_tensor(w.value, max(int(count), 1), torch.float64, device)[: int(count)]
+        self.count = int(count)
+
+    def connect(self, sh: "ShardedGaxpy", group=None):
+        """All ranks exchange (IPC handles, offset and length of the own slice inside the window);
+        each then maps the two neighbours' windows."""
+        import torch
+        C, _lib, dist = self._C, self._lib, sh.dist
+        buf = (C.c_ubyte * 128)()
+        _lib.check(_lib.lib().csb200_halo_export(self._h, buf), "halo_export")
+        mine = torch.zeros(128 + 16, dtype=torch.uint8)
+        mine[:128] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+        own_off, own_len = sh.own.start, sh.own.stop - sh.own.start
+        mine[128:] = torch.frombuffer(bytearray(np.array([own_off, own_len], dtype=np.int64).tobytes()), dtype=torch.uint8)
+        dev = sh.device
+        allb = [torch.zeros_like(mine).to(dev) for _ in range(sh.world)]
+        dist.all_gather(allb, mine.to(dev), group=group)
+        allb = [b.cpu().numpy() for b in allb]
+        pl, r = sh.plan, sh.rank
+        for side, nb in ((0, r - 1), (1, r + 1)):
+            if nb < 0 or nb >= sh.world:
+                continue
+            need = pl.lo_need[r] if side == 0 else pl.hi_need[r]
+            if need == 0:
+                continue
+            off, length = (int(v) for v in np.frombuffer(allb[nb][128:].tobytes(), dtype=np.int64))
+            peer_first = off + length - need if side == 0 else off          # its tail / its head
+            local_first = 0 if side == 0 else self.count - need
+            handles = (C.c_ubyte * 128).from_buffer_copy(allb[nb][:128].tobytes())
+            _lib.check(_lib.lib().csb200_halo_connect(self._h, side, handles, peer_first, need, local_first),
+                       "halo_connect")
+        dist.barrier(group=group)
+
+    def step(self, handle, y_own, top_rows: int, bot_rows: int):
+        C, _lib = self._C, self._lib
+        _lib.check(_lib.lib().csb200_gaxpy_halo_dev(handle._h, self._h, C.c_void_p(y_own.data_ptr()),
+                                                    int(top_rows), int(bot_rows)), "gaxpy_halo_dev")
+
+    def timed_out(self) -> bool:
+        v = self._C.c_int()
+        self._lib.check(self._lib.lib().csb200_halo_status(self._h, self._C.byref(v)), "halo_status")
+        return bool(v.value)
+
+    def free(self):
+        if self._h:
+            self._lib.lib().csb200_halo_free(self._h)
+            self._h = None
 
 
 # ---- CUDA bindings for the local kernels -----------------------------------------------
@@ -293,80 +381,96 @@ def multiply_column_bounds(Ap: np.ndarray, Bp: np.ndarray, Bi: np.ndarray, parts
     return balanced_bounds(col_prefix, parts)
 
 
-def sharded_multiply(dA, dB, bounds, rank: int, gather: Optional[str] = "all", group=None, device="cuda",
+def gather_columns(cp, ci, cx, bounds, rank: int, world: int, mode: str = "root", group=None, device="cpu"):
+    """The final gather of a column-sharded product ("no collective beyond the final
+    gather").  Every rank holds its block C(:, J_rank) as (cp rebased to 0, ci, cx or None);
+    returns (Cp, Ci, Cx) of the whole matrix on rank 0 (mode "root"; None elsewhere) or on every
+    rank (mode "all").  The only small collective is the all-gather of the world nnz counts; the
+    pieces then travel ONCE, point to point, straight into their final offsets of the destination
+    arrays -- no padding, no staging copy (NCCL send/recv over NVLink on the GPU box, gloo here).
+    """
+    import torch
+    import torch.distributed as dist
+    if mode not in ("root", "all"):
+        raise ValueError("gather mode must be 'root' or 'all'")
+    nnz_local = int(ci.numel())
+    n_total = int(bounds[-1])
+    has_x = cx is not None
+    if world == 1:
+        return cp.clone(), ci.clone(), (cx.clone() if has_x else None)
+    cnt = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(cnt, torch.tensor([nnz_local], dtype=torch.int64, device=device), group=group)
+    nnz_all = [int(v) for v in cnt.tolist()]
+    offs = np.concatenate(([0], np.cumsum(nnz_all))).astype(np.int64)
+    if int(offs[-1]) > 0x7FFFFFFF:
+        raise OverflowError("gathered nnz(C) does not fit int32")
+    cp_glob = (cp[:-1] + int(offs[rank])).contiguous()          # my column pointers in global numbering
+    receivers = [0] if mode == "root" else list(range(world))
+    Cp = Ci = Cx = None
+    if rank in receivers:
+        Cp = torch.empty(n_total + 1, dtype=torch.int32, device=device)
+        Ci = torch.empty(int(offs[-1]), dtype=torch.int32, device=device)
+        Cx = torch.empty(int(offs[-1]), dtype=torch.float64, device=device) if has_x else None
+        Cp[n_total] = int(offs[-1])
+    ops = []
+    for dst in receivers:
+        if dst == rank:
+            for g in range(world):
+                j0, j1, o0, o1 = int(bounds[g]), int(bounds[g + 1]), int(offs[g]), int(offs[g + 1])
+                if g == rank:
+                    Cp[j0:j1] = cp_glob
+                    Ci[o0:o1] = ci
+                    if has_x:
+                        Cx[o0:o1] = cx
+                    continue
+                if j1 > j0:
+                    ops.append(dist.P2POp(dist.irecv, Cp[j0:j1], g, group=group))
+                if o1 > o0:
+                    ops.append(dist.P2POp(dist.irecv, Ci[o0:o1], g, group=group))
+                    if has_x:
+                        ops.append(dist.P2POp(dist.irecv, Cx[o0:o1], g, group=group))
+        else:
+            if cp_glob.numel():
+                ops.append(dist.P2POp(dist.isend, cp_glob, dst, group=group))
+            if nnz_local:
+                ops.append(dist.P2POp(dist.isend, ci.contiguous(), dst, group=group))
+                if has_x:
+                    ops.append(dist.P2POp(dist.isend, cx.contiguous(), dst, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return (Cp, Ci, Cx) if rank in receivers else None
+
+
+def sharded_multiply(dA, dB, bounds, rank: int, gather: Optional[str] = "root", group=None, device="cuda",
                      dB_local=None):
-    """C(:, J_rank) = A * B(:, J_rank) on this rank; then the final gather.
+    """C(:, J_rank) = A * B(:, J_rank) on this rank (A replicated, no communication), then the
+    final gather.
 
     ``dB_local`` may hold the pre-sliced column block B(:, J_rank) (slice once, multiply many
-    times).  Returns (local DeviceMatrix, gathered) where gathered is None, or a tuple of
-    torch tensors (Cp, Ci, Cx) holding the whole product (on every rank for gather="all").
+    times).  ``gather``: None leaves C column-distributed; "root" assembles the whole product on
+    rank 0; "all" on every rank.  Returns (local DeviceMatrix, gathered) where gathered is None or
+    a tuple of torch tensors (Cp, Ci, Cx).
     """
-    import os
-    import time
     import torch
     import torch.distributed as dist
     import csparse_cuda as cc
-    trace = os.environ.get("CSPARSE_DIST_TRACE") == "1"
-    marks = []
-
-    def mark(name):
-        if trace:
-            torch.cuda.synchronize()
-            marks.append((name, time.perf_counter()))
-    mark("start")
     j0, j1 = int(bounds[rank]), int(bounds[rank + 1])
     dBl = dB_local if dB_local is not None else dB.col_slice(j0, j1)
-    mark("col_slice")
     dCl = cc.cs_multiply(dA, dBl)
-    mark("multiply")
     if dB_local is None:
         dBl.free()
     if gather is None:
         return dCl, None
+    if gather is True:
+        gather = "root"
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     p_ptr, i_ptr, x_ptr = dCl.device_pointers()
     # wrap the result's device arrays as torch tensors without copying
     cp = _as_tensor(p_ptr, dCl.n + 1, torch.int32, device)
     ci = _as_tensor(i_ptr, max(dCl.nnz, 1), torch.int32, device)[: dCl.nnz]
     cx = _as_tensor(x_ptr, max(dCl.nnz, 1), torch.float64, device)[: dCl.nnz] if dCl.has_values else None
-    if world == 1:
-        return dCl, (cp.clone(), ci.clone(), None if cx is None else cx.clone())
-    cnt = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(cnt, torch.tensor([dCl.nnz], dtype=torch.int64, device=device), group=group)
-    nnz_all = [int(v) for v in cnt.tolist()]
-    offs = np.concatenate(([0], np.cumsum(nnz_all)))
-    n_total = int(bounds[-1])
-    widths = [int(bounds[g + 1] - bounds[g]) for g in range(world)]
-    Cp = torch.empty(n_total + 1, dtype=torch.int32, device=device)
-    Ci = torch.empty(int(offs[-1]), dtype=torch.int32, device=device)
-    Cx = torch.empty(int(offs[-1]), dtype=torch.float64, device=device) if cx is not None else None
-
-    def gather_ragged(dst, src, sizes, starts):
-        """all-gather of unequal pieces: equal-sized padded all_gather_into_tensor, then placement"""
-        mx = max(max(sizes), 1)
-        if len(set(sizes)) == 1 and dst.numel() == world * mx:
-            dist.all_gather_into_tensor(dst, src.contiguous(), group=group)
-            return
-        pad = torch.empty(world * mx, dtype=dst.dtype, device=device)
-        mine = torch.empty(mx, dtype=dst.dtype, device=device)
-        mine[: src.numel()] = src
-        dist.all_gather_into_tensor(pad, mine, group=group)
-        for g in range(world):
-            dst[starts[g]: starts[g] + sizes[g]] = pad[g * mx: g * mx + sizes[g]]
-
-    mark("alloc")
-    gather_ragged(Cp[:n_total], (cp[:-1] + int(offs[rank])), widths, [int(b) for b in bounds[:-1]])
-    Cp[n_total] = int(offs[-1])
-    mark("gather p")
-    gather_ragged(Ci, ci, nnz_all, [int(o) for o in offs[:-1]])
-    mark("gather i")
-    if Cx is not None:
-        gather_ragged(Cx, cx, nnz_all, [int(o) for o in offs[:-1]])
-    mark("gather x")
-    if trace and rank == 0:
-        print("sharded_multiply trace (ms):",
-              ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])), flush=True)
-    return dCl, (Cp, Ci, Cx)
+    return dCl, gather_columns(cp, ci, cx, bounds, rank, world, gather, group, device)
 
 
 def _as_tensor(ptr: int, count: int, dtype, device):

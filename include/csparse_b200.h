@@ -37,6 +37,7 @@ extern "C" {
 
 typedef int32_t csi;
 typedef struct csb200_mat csb200_mat;
+typedef struct csb200_halo csb200_halo;
 
 typedef enum {
     CSB200_OK = 0,
@@ -117,6 +118,30 @@ CSB200_API int csb200_gaxpy_prepare(csb200_mat *A);
 CSB200_API int csb200_gaxpy_plan(csb200_mat *A, int *kind);
 /* force a plan (0 = automatic); for tests and benchmarks */
 CSB200_API int csb200_gaxpy_force_plan(csb200_mat *A, int kind);
+
+/* ---- cs_gaxpy across GPUs: row blocks of the CSR view, x halos over NVLink ----
+ * The reference has no distributed code; these are the in-library form of its cs_gaxpy
+ * (csparse.py:1199-1213) for a matrix whose rows are split across one process per GPU.  A halo
+ * object owns the rank's x window [lo halo | own slice | hi halo] (device memory) and a small
+ * flag block; its IPC handles are exchanged once (128 bytes per rank, by whatever transport the
+ * host has -- torch.distributed in csparse_cuda/dist.py), after which every step is ONE kernel
+ * launch per rank: the persistent SpMV pulls the halo lines from the neighbours' windows through
+ * peer-mapped pointers, runs the interior row blocks meanwhile and the edge row blocks last. */
+CSB200_API int csb200_halo_create(int64_t count, csb200_halo **out);       /* window of `count` doubles, zeroed */
+CSB200_API int csb200_halo_window(csb200_halo *h, double **d_window);
+CSB200_API int csb200_halo_export(csb200_halo *h, void *handles);          /* 128 bytes out */
+/* side 0 = the rank below, 1 = the rank above: window[local_first .. +count) is pulled from the
+ * peer's window[peer_first .. +count) every step */
+CSB200_API int csb200_halo_connect(csb200_halo *h, int side, const void *peer_handles, int64_t peer_first,
+                        int64_t count, int64_t local_first);
+/* the same for a peer living in this process (tests; one process driving several GPUs) */
+CSB200_API int csb200_halo_connect_local(csb200_halo *h, int side, csb200_halo *peer, int64_t peer_first,
+                              int64_t count, int64_t local_first);
+/* y[0..AT.n) += AT' * window; top_rows / bot_rows = rows at the two ends of the block that read
+ * halo entries (0, 0 with no neighbours).  Every rank must call it the same number of times. */
+CSB200_API int csb200_gaxpy_halo_dev(csb200_mat *AT, csb200_halo *h, double *d_y, csi top_rows, csi bot_rows);
+CSB200_API int csb200_halo_status(csb200_halo *h, int *timed_out);         /* 1: a neighbour never showed up (2 s) */
+CSB200_API int csb200_halo_free(csb200_halo *h);
 
 /* ---- cs_multiply (csparse.py:1608-1642, cs_scatter :1961-1989) ------------ */
 /* C = A*B: symbolic per-column count (shared-memory hash sets, dense spill for

@@ -107,3 +107,59 @@ def test_sharded_gaxpy_world2(kind, mode):
         assert err <= 1e-12, res
         if mode == "halo":
             assert nbytes == 8 * 24             # one grid line of the 24 x 24 Laplacian per neighbour
+
+
+def _col_block(B, j0, j1):
+    b, e = int(B.p[j0]), int(B.p[j1])
+    return orc.csc(B.m, j1 - j0, (B.p[j0:j1 + 1] - b).astype(np.int32), B.i[b:e].copy(), B.x[b:e].copy())
+
+
+def _worker_mul(rank, world, port, kind, q):
+    """Column-sharded cs_multiply: every rank forms C(:, J_rank) = A * B(:, J_rank) (here with the
+    oracle standing in for the local GPU product) and the final gather assembles C -- on rank 0
+    ("root") and on every rank ("all").  The gathered (Cp, Ci, Cx) must equal the whole product."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m, n, p, i, x = synth.st27(6) if kind == "st27" else synth.rmat(8, 5)
+        A = orc.csc(m, n, p, i, x)
+        bounds = csd.multiply_column_bounds(p, p, i, world)
+        if kind == "rmat":
+            bounds = np.array([0, 0, n][: world + 1] if world == 2 else bounds)   # an EMPTY block on rank 0
+        j0, j1 = int(bounds[rank]), int(bounds[rank + 1])
+        Cl = orc.cs_multiply(A, _col_block(A, j0, j1))
+        nl = int(Cl.p[Cl.n])
+        cp, ci, cx = torch.from_numpy(Cl.p.copy()), torch.from_numpy(Cl.i[:nl].copy()), torch.from_numpy(Cl.x[:nl].copy())
+        Cref = orc.cs_multiply(A, A)
+        nr = int(Cref.p[Cref.n])
+        ok = True
+        for mode in ("root", "all"):
+            got = csd.gather_columns(cp, ci, cx, bounds, rank, world, mode, None, "cpu")
+            if mode == "root" and rank != 0:
+                ok &= got is None
+                continue
+            Cp, Ci, Cx = (t.numpy() for t in got)
+            ok &= np.array_equal(Cp, Cref.p) and np.array_equal(Ci, Cref.i[:nr])
+            ok &= np.array_equal(Cx.view(np.int64), Cref.x[:nr].view(np.int64))
+        # pattern-only pieces travel without a value array
+        got = csd.gather_columns(cp, ci, None, bounds, rank, world, "all", None, "cpu")
+        ok &= got[2] is None and np.array_equal(got[1].numpy(), Cref.i[:nr])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["st27", "rmat"])
+def test_sharded_multiply_gather_world2(kind):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_mul, args=(r, 2, port, kind, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res

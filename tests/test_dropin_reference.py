@@ -1,0 +1,179 @@
+"""Drop-in test against the REAL reference module ("the strongest drop-in check").
+
+csparse.cs_cumsum / cs_transpose / cs_multiply / cs_gaxpy are monkey-patched with csparse_cuda's
+and the reference's OWN in-library callers are run on the fixtures:
+
+    cs_compress   csparse.py:665    cs_cumsum, result used as insertion cursors
+    cs_symperm    csparse.py:2242   cs_cumsum
+    cs_counts     csparse.py:719    cs_transpose (ata = True)
+    cs_scc        csparse.py:2003   cs_transpose; cs_dfs flips entries of the returned p list to
+                                    negative values as visit marks (:2025-2029, CS_MARK :143)
+    cs_dmperm     csparse.py:846    cs_transpose in _cs_bfs, cs_maxtrans (:1565); seed 0
+    cs_qrsol      csparse.py:1899   cs_transpose for m < n (order 0)
+
+Every result must equal the un-patched run's, list for list (cs_transpose / cs_cumsum are
+bit-exact, so everything downstream is).  The reference module is the unmodified csparse.py,
+looked up in $CSPARSE_REFERENCE, /root/reference (build container) or baseline/_ref (the
+`pip install --target baseline/_ref` copy that travels to the GPU box; git-ignored); the test
+skips when none is present.  It needs a GPU because the patched-in functions have no CPU path.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden_util import Golden
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    cands = [os.environ.get("CSPARSE_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")]
+    for d in cands:
+        if d and os.path.exists(os.path.join(d, "csparse.py")):
+            return os.path.join(d, "csparse.py")
+    return None
+
+
+@pytest.fixture(scope="module")
+def ref():
+    path = _find_reference()
+    if path is None:
+        pytest.skip("reference csparse.py not present (CSPARSE_REFERENCE, /root/reference, baseline/_ref)")
+    spec = importlib.util.spec_from_file_location("csparse_reference_module", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def ref_cs(ref, name):
+    """The fixture's compressed-column matrix as a list-backed object of the reference's own class."""
+    g = Golden(name).A()
+    nnz = int(g.p[g.n])
+    A = ref.cs()
+    A.m, A.n, A.nz, A.nzmax = g.m, g.n, -1, max(nnz, 1)
+    A.p = [int(v) for v in g.p[: g.n + 1]]
+    A.i = [int(v) for v in g.i[:nnz]]
+    A.x = [float(v) for v in g.x[:nnz]]
+    return A
+
+
+def triplet_of(ref, A):
+    T = ref.cs()
+    nnz = A.p[A.n]
+    T.m, T.n, T.nz, T.nzmax = A.m, A.n, nnz, max(nnz, 1)
+    T.p = [j for j in range(A.n) for _ in range(A.p[j], A.p[j + 1])]
+    T.i = list(A.i[:nnz])
+    T.x = list(A.x[:nnz])
+    # reversed entry order: columns of the result come out unsorted, ties keep their input order
+    T.p.reverse(); T.i.reverse(); T.x.reverse()
+    return T
+
+
+def fields(obj, names):
+    return {k: getattr(obj, k) for k in names}
+
+
+CS_FIELDS = ("m", "n", "nz", "nzmax", "p", "i", "x")
+SMALL = ["t1", "ash219", "bcsstk01", "fs_183_1", "ibm32a", "ibm32b", "lp_afiro", "west0067", "mbeacxc"]
+SQUARE = ["t1", "bcsstk01", "fs_183_1", "west0067"]
+
+
+def both(ref, monkeypatch, fn):
+    """fn(ref) with the reference as it is, then with the GPU functions patched in."""
+    import csparse_cuda as cc
+    plain = fn(ref)
+    with monkeypatch.context() as mp:
+        for name in ("cs_cumsum", "cs_transpose", "cs_multiply", "cs_gaxpy"):
+            mp.setattr(ref, name, getattr(cc, name))
+        swapped = fn(ref)
+    return plain, swapped
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_cs_compress_calls_gpu_cumsum(ref, monkeypatch, name):
+    def run(r):
+        return fields(r.cs_compress(triplet_of(r, ref_cs(r, name))), CS_FIELDS)
+    plain, swapped = both(ref, monkeypatch, run)
+    assert swapped == plain
+
+
+@pytest.mark.parametrize("name", SQUARE)
+def test_cs_symperm_calls_gpu_cumsum(ref, monkeypatch, name):
+    def run(r):
+        A = ref_cs(r, name)
+        pinv = list(np.random.default_rng(5).permutation(A.n).tolist())
+        return fields(r.cs_symperm(A, pinv, True), CS_FIELDS)
+    plain, swapped = both(ref, monkeypatch, run)
+    assert swapped == plain
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_cs_counts_calls_gpu_transpose(ref, monkeypatch, name):
+    def run(r):
+        A = ref_cs(r, name)
+        parent = r.cs_etree(A, True)
+        post = r.cs_post(parent, A.n)
+        return r.cs_counts(A, parent, post, True)
+    plain, swapped = both(ref, monkeypatch, run)
+    assert swapped == plain
+
+
+@pytest.mark.parametrize("name", SQUARE)
+def test_cs_scc_mutates_the_returned_p(ref, monkeypatch, name):
+    """cs_scc marks nodes by flipping AT.p[j] to a negative value and back (csparse.py:2025-2029):
+    the list cs_transpose returns must be a mutable list of signed ints."""
+    def run(r):
+        D = r.cs_scc(ref_cs(r, name))
+        return fields(D, ("p", "r", "nb"))
+    plain, swapped = both(ref, monkeypatch, run)
+    assert swapped == plain
+
+
+@pytest.mark.parametrize("name", ["t1", "bcsstk01", "fs_183_1", "ibm32a", "ibm32b", "west0067", "ash219", "lp_afiro"])
+def test_cs_dmperm_calls_gpu_transpose(ref, monkeypatch, name):
+    def run(r):
+        D = r.cs_dmperm(ref_cs(r, name), 0)
+        return fields(D, ("p", "q", "r", "s", "nb", "rr", "cc"))
+    plain, swapped = both(ref, monkeypatch, run)
+    assert swapped == plain
+
+
+@pytest.mark.parametrize("name", ["lp_afiro", "ibm32b", "ash219", "t1"])
+def test_cs_qrsol_order0(ref, monkeypatch, name):
+    """m < n (lp_afiro, ibm32b) goes through cs_transpose (csparse.py:1899); the others do not and
+    pin that patching leaves them alone."""
+    def run(r):
+        A = ref_cs(r, name)
+        b = [1.0 + 0.01 * k for k in range(max(A.m, A.n))]
+        ok = r.cs_qrsol(0, A, b)
+        return ok, b
+    plain, swapped = both(ref, monkeypatch, run)
+    assert swapped[0] == plain[0]
+    assert np.array_equal(np.array(swapped[1]).view(np.int64), np.array(plain[1]).view(np.int64))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_the_four_functions_equal_the_reference(ref, name):
+    """Direct calls, reference containers in, against the reference's own output: p, i, x lists of
+    cs_transpose and cs_multiply (host operands: discovery order included), y of cs_gaxpy, cs_cumsum."""
+    import csparse_cuda as cc
+    A = ref_cs(ref, name)
+    AT_ref = ref.cs_transpose(A, True)
+    AT = cc.cs_transpose(A, True)
+    assert fields(AT, CS_FIELDS) == fields(AT_ref, CS_FIELDS)
+    C_ref = ref.cs_multiply(A, AT_ref)
+    C = cc.cs_multiply(A, AT)
+    assert fields(C, CS_FIELDS) == fields(C_ref, CS_FIELDS)
+    x = [0.5 + 0.25 * k for k in range(A.n)]
+    y_ref = [1.0] * A.m
+    y = [1.0] * A.m
+    assert ref.cs_gaxpy(A, x, y_ref) is True and cc.cs_gaxpy(A, x, y) is True
+    assert np.linalg.norm(np.array(y) - np.array(y_ref)) <= 1e-12 * np.linalg.norm(np.array(y_ref))
+    c1, c2 = [A.p[j + 1] - A.p[j] for j in range(A.n)], [A.p[j + 1] - A.p[j] for j in range(A.n)]
+    p1, p2 = [7] * (A.n + 3), [7] * (A.n + 3)
+    assert cc.cs_cumsum(p1, c1, A.n) == ref.cs_cumsum(p2, c2, A.n)
+    assert p1 == p2 and c1 == c2
