@@ -58,39 +58,53 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region, for the GPUs of this job
+    (rank 0 samples all of them: eight ranks each starting their own nvidia-smi took longer to
+    produce a first line than the timed region lasted)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, indices, enabled: bool = True):
+        self.indices = [indices] if isinstance(indices, int) else list(indices)
+        self.enabled, self.proc, self.lines, self.mark = enabled, None, [], 0
 
-    def start(self):
+    def launch(self):
+        """Start nvidia-smi early (before the warm-up): its start-up takes a second or more."""
+        if not self.enabled or self.proc:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "20"],
+                                          "-i", ",".join(str(i) for i in self.indices), "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def start(self):
+        """Mark the beginning of the timed region: only samples taken from here on count."""
+        self.launch()
+        if self.proc:
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:     # first line = nvidia-smi is up
+                time.sleep(0.02)
+        self.mark = len(self.lines)
+
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if not self.enabled:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled on rank 0 only"], "samples": 0}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        lines = self.lines[self.mark:]
+        self.mark = len(self.lines)
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in lines:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -102,7 +116,16 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpus_sampled": len(self.indices)}
+
+    def close(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            self.proc = None
 
 
 # ------------------------------------------------------------------------------------
@@ -245,7 +268,8 @@ def main():
     peak, peak_src = peaks()
     k = a.k or default_k(a.workload)
     out = {}
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(list(range(world)) if world > 1 else local, enabled=(rank == 0))
+    sampler.launch()
 
     if a.workload == "gaxpy_lap2d":
         out = bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler)
@@ -259,6 +283,9 @@ def main():
     elif a.workload == "multiply_st27":
         out = bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler)
 
+    if world > 1 and a.workload == "gaxpy_lap2d" and not a.no_extra:
+        # the other sharded configurations of BASELINE.json on the same N GPUs, every rank taking part
+        out["extra"] = extras_dist(a, torch, dist, cc, synth, csd, world, rank, peak, peak_src, out)
     if rank == 0:
         if world == 1 and a.workload == "gaxpy_lap2d" and not a.no_extra:
             out["extra"] = extras(a, torch, cc, synth, peak)
@@ -272,9 +299,52 @@ def main():
                                    "sample": f"{passes} x {desc} in {dt:.1f} s; oracle/csparse_oracle.c, 1 thread "
                                              f"(host has {os.cpu_count()} logical CPUs; the reference is single-threaded)"}
         print(json.dumps(out), flush=True)
+    sampler.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def extras_dist(a, torch, dist, cc, synth, csd, world, rank, peak, peak_src, headline):
+    """N > 1: driver-visible lines for the sharded configurations the default workload does not
+    cover -- BASELINE.json configs 3 (strong-scaled: the fixed 4096^2 matrix split over N GPUs), 4
+    (cs_multiply st27 128^3 by column blocks of B; C left distributed, and gathered to rank 0) and 5
+    (cs_gaxpy R-MAT 2^24, x all-gathered).  Every rank runs them; a failure on any rank is reported
+    instead of sinking the headline, and a watchdog ends a rank that waits for a peer that gave up."""
+    import copy
+    ex = {}
+    deadline = threading.Timer(420.0, lambda: (print(json.dumps(dict(headline, extra=dict(ex, error="extras timed out"))),
+                                                   flush=True) if rank == 0 else None, os._exit(0)))
+    deadline.daemon = True
+    deadline.start()
+    quiet = ClockSampler(0, enabled=False)
+
+    def keep(name, r, keys):
+        if rank == 0:
+            ex[name] = {k: r.get(k) for k in keys if k in r}
+
+    try:
+        b = copy.copy(a)
+        b.scaling, b.steps, b.warmup = "strong", min(a.steps, 200), max(a.warmup, 3)
+        r = bench_gaxpy_lap2d(b, torch, dist, cc, synth, csd, world, rank, 4096, peak, peak_src, quiet)
+        keep("cs_gaxpy lap2d 4096^2, strong-scaled over N GPUs", r,
+             ("value", "unit", "ms_per_step", "scaling", "n_gpus", "steps", "config", "roofline", "e2e"))
+        torch.cuda.empty_cache()
+        b = copy.copy(a)
+        b.steps, b.warmup = min(a.steps, 50), max(a.warmup, 3)
+        r = bench_gaxpy_rmat_dist(b, torch, dist, cc, synth, csd, world, rank, 24, peak, peak_src, quiet)
+        keep("cs_gaxpy rmat 2^24, row blocks balanced by nonzeros, x all-gathered", r,
+             ("value", "unit", "ms_per_step", "scaling", "n_gpus", "steps", "config", "roofline", "e2e"))
+        torch.cuda.empty_cache()
+        b = copy.copy(a)
+        b.steps, b.warmup = 10, 3
+        r = bench_multiply(b, torch, dist, cc, synth, csd, world, rank, 128, peak, peak_src, quiet)
+        keep("cs_multiply st27 128^3 A*A, column blocks of B", r,
+             ("value", "unit", "ms_per_step", "scaling", "n_gpus", "steps", "config", "roofline"))
+    except Exception as e:  # secondary numbers never sink the headline
+        ex["error"] = f"rank {rank}: {e!r}"
+    deadline.cancel()
+    return ex
 
 
 def pinned(torch, arr):
@@ -574,7 +644,7 @@ def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_sr
 
         def step():
             hold.clear()
-            hold["c"] = csd.sharded_multiply(dA, dA, bounds, rank, gather="all", device="cuda", dB_local=dBl)
+            hold["c"] = csd.sharded_multiply(dA, dA, bounds, rank, gather="root", device="cuda", dB_local=dBl)
     steps, warm = min(a.steps, 10), max(min(a.warmup, 3), 2)
     l0 = cc.launch_count()
     sampler.start()
@@ -590,7 +660,12 @@ def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_sr
         step()                                     # leave a gathered product for the checks below
     launches = (cc.launch_count() - l0) * steps // (steps + warm)
     nnzc = (5 * k - 6) ** 3
-    got = hold["c"].nnz if world == 1 else int(hold["c"][1][1].numel())
+    if world == 1:
+        got = hold["c"].nnz
+    elif rank == 0:
+        got = int(hold["c"][1][1].numel())              # the gathered Ci on rank 0
+    else:
+        got = nnzc
     assert got == nnzc, (got, nnzc)
     value = nnzc * steps / (ms * 1e-3)
     b = synth.multiply_bytes(nnz, nnz, nnzc, n, n)
@@ -601,7 +676,7 @@ def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_sr
             "config": {"workload": f"cs_multiply A*A, 27-point stencil {k}^3 (n={n}, nnz={nnz}, nnz(C)={nnzc}), "
                                    f"column blocks of B, A replicated", "l2": "inputs + output exceed L2",
                        "gflops": 2 * cc.last_multiply_flops() * world * steps / (ms * 1e-3) / 1e9 if world == 1 else None,
-                       "gather": "none (N = 1)" if world == 1 else "all-gather of the whole product onto every rank, inside the timed step",
+                       "gather": "none (N = 1)" if world == 1 else "the whole product gathered to rank 0 (point-to-point pieces into their final offsets), inside the timed step",
                        "nnz(C)/s with C left column-distributed": None if ms_local is None else nnzc * steps / (ms_local * 1e-3),
                        "ms_per_step with C left column-distributed": None if ms_local is None else ms_local / steps},
             "clocks": clocks, "gpu_launches": int(launches),

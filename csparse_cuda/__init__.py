@@ -218,8 +218,10 @@ class DeviceMatrix(object):
 
 def force_transpose_path(path: Optional[str]):
     """Tests / benchmarks: None or "auto" = automatic choice, "radix" = always the stable radix sort,
-    "bucket" = automatic choice without the one-pass mirror path."""
-    _lib.check(_lib.lib().csb200_transpose_force_path({None: 0, "auto": 0, "radix": 1, "bucket": 2}[path]))
+    "bucket" = automatic choice without the one-pass mirror path, "bucket_noslab" = the same with the
+    whole partition before the whole sort (no L2-resident slabs; A/B measurements)."""
+    _lib.check(_lib.lib().csb200_transpose_force_path({None: 0, "auto": 0, "radix": 1, "bucket": 2,
+                                                       "bucket_noslab": 3}[path]))
 
 
 def last_transpose_path() -> str:
@@ -714,9 +716,16 @@ def gaxpy_host(m, n, Ap, Ai, Ax, x, y):
 def force_multiply_path(path: Optional[str]):
     """None / "auto": device-matrix products may use the blocked numeric kernel (rows of a column
     block by block); "ordered": always the reference's discovery order; "blocked_v1" / "blocked_v2":
-    automatic with that version of the blocked numeric kernel (A/B measurements)."""
-    code = {None: 0, "auto": 0, "ordered": 1, "blocked_v1": 2, "blocked_v2": 3}[path]
+    automatic with that version of the blocked numeric kernel (A/B measurements); "no_templates":
+    automatic without the pattern-class templates; "templates": templates tried at any size."""
+    code = {None: 0, "auto": 0, "ordered": 1, "blocked_v1": 2, "blocked_v2": 3, "no_templates": 4,
+            "templates": 5}[path]
     _lib.check(_lib.lib().csb200_multiply_force_path(code))
+
+
+def last_multiply_templated() -> int:
+    """Columns the last cs_multiply on this thread formed from pattern-class templates."""
+    return int(_lib.lib().csb200_multiply_last_templated())
 
 
 def last_multiply_flops() -> int:

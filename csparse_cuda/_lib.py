@@ -64,6 +64,7 @@ PROTOTYPES = {
     "csb200_multiply_ordered": (C.c_int, [mat_t, mat_t, matp]),
     "csb200_multiply_force_path": (C.c_int, [C.c_int]),
     "csb200_multiply_last_flops": (C.c_int64, []),
+    "csb200_multiply_last_templated": (C.c_int64, []),
     "csb200_add": (C.c_int, [mat_t, mat_t, C.c_double, C.c_double, matp]),
     "csb200_add_force_path": (C.c_int, [C.c_int]),
     "csb200_norm": (C.c_int, [mat_t, f64p]),

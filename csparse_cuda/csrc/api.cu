@@ -453,6 +453,7 @@ int csb200_mat_free(csb200_mat *A)
     dev_free(A->c32_blk);
     dev_free(A->c32_mask);
     dev_free(A->c32_len);
+    dev_free(A->cls);
     delete A;
     return CSB200_OK;
 }
@@ -468,7 +469,7 @@ int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
 
 int csb200_transpose_force_path(int path)
 {
-    if (path < 0 || path > 2) return set_error(CSB200_ERR_ARG, "bad transpose path");
+    if (path < 0 || path > 3) return set_error(CSB200_ERR_ARG, "bad transpose path");
     tls().force_transpose = path;
     return CSB200_OK;
 }
@@ -633,12 +634,14 @@ int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B, csb200_mat
 
 int csb200_multiply_force_path(int path)
 {
-    if (path < 0 || path > 3) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
+    if (path < 0 || path > 5) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
     tls().multiply_ordered = path == 1;
-    tls().multiply_blocked_version = path >= 2 ? path : 0;
+    tls().multiply_blocked_version = (path == 2 || path == 3) ? path : 0;
+    tls().multiply_templates = path == 4 ? 1 : path == 5 ? 2 : 0;
     return CSB200_OK;
 }
 
 int64_t csb200_multiply_last_flops(void) { return tls().last_flops; }
+int64_t csb200_multiply_last_templated(void) { return tls().last_templated; }
 
 }  // extern "C"

@@ -17,9 +17,11 @@ struct ThreadState {
     char err[640] = {0};
     int64_t last_flops = 0;
     // path switches of the tests / benchmarks (csb200_*_force_path): per thread, like the stream
-    int force_transpose = 0;          // 1: always the radix sort, 2: automatic choice without the mirror path
+    int force_transpose = 0;          // 1: always the radix sort, 2: automatic choice without the mirror path, 3: 2 without slabs
     int multiply_ordered = 0;         // 1: always the reference's discovery order
     int multiply_blocked_version = 0; // 2 / 3: which blocked numeric kernel (0 = default)
+    int multiply_templates = 0;       // pattern-class path: 0 automatic, 1 off, 2 on at any size
+    int64_t last_templated = 0;       // columns the last cs_multiply of this thread formed from class templates
     int add_force_spgemm = 0;         // 1: cs_add on the SpGEMM kernels even for canonical operands
 };
 ThreadState &tls();
@@ -174,6 +176,11 @@ struct csb200_mat {
     csi *c32_blk = nullptr;
     unsigned *c32_mask = nullptr;
     csi *c32_len = nullptr;
+    // cs_multiply's pattern classes (spgemm_tpl.cuh): cls[k] = class of column k's pattern relative to
+    // k, or -1; cls_state -1 not computed, 0 too many classes (unstructured), 1 usable
+    csi *cls = nullptr;
+    int cls_state = -1;
+    int cls_count = 0;
 };
 
 // ---- device helpers -----------------------------------------------------------

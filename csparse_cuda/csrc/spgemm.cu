@@ -25,6 +25,7 @@
 // order, see CANON.)
 #include "common.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace csb {
 
@@ -109,6 +110,10 @@ __device__ __forceinline__ int warp_find_or_insert(int *keys, int hmask, int i, 
     }
     return (int)h;
 }
+
+}  // namespace csb
+#include "spgemm_tpl.cuh"
+namespace csb {
 
 // ---- compressed columns for the symbolic phase ------------------------------------------
 // Column k of A as pairs (block = row >> 5, mask = bits of the rows present in that block),
@@ -757,10 +762,11 @@ __global__ void k_canon(const csi *__restrict__ Ap, const csi *__restrict__ Ai, 
     }
 }
 
-__global__ void k_col_sizes(int n, const csi *__restrict__ Cp, int *__restrict__ sz)
+// exact column sizes for the numeric classes; columns with a template (cb[j] >= 0) are k_num_tpl's
+__global__ void k_col_sizes(int n, const csi *__restrict__ Cp, int *__restrict__ sz, const int *__restrict__ cb)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) sz[j] = Cp[j + 1] - Cp[j];
+    if (j < n) sz[j] = (cb && cb[j] >= 0) ? 0 : Cp[j + 1] - Cp[j];
 }
 
 int mat_is_canonical(csb200_mat *A, int *out)
@@ -784,6 +790,36 @@ int mat_is_canonical(csb200_mat *A, int *out)
 }
 
 // ---- host side ---------------------------------------------------------------------------
+// pattern classes of A's columns (spgemm_tpl.cuh), once per handle: A->cls[k] = class or -1
+static int ensure_classes(csb200_mat *A)
+{
+    if (A->cls_state >= 0) return CSB200_OK;
+    A->cls_state = 0;
+    if (A->n == 0 || A->nnz == 0) return CSB200_OK;
+    cudaStream_t s = stream();
+    DevBuf<unsigned char> tb;
+    CSB_TRY(tb.alloc(CLS_TABLE_BYTES));
+    int *ca = nullptr;
+    CSB_TRY(dev_alloc(&ca, (size_t)A->n));
+    const ClsTable t = cls_table_at(tb.ptr);
+    const int grid = ceil_div((long long)A->n * 32, 256);
+    k_cls_init<<<CLS_SLOTS / 256, 256, 0, s>>>(t);
+    k_cls_hash_a<<<min(ceil_div(A->n, CLS_WARPS), sm_count() * 8), CLS_WARPS * 32, 0, s>>>(A->n, A->p, A->i, t, ca);
+    k_cls_compact<<<1, 1024, 0, s>>>(t);
+    k_cls_verify_a<<<grid, 256, 0, s>>>(A->n, A->p, A->i, t, ca);
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    int info[4] = {0, 1, 0, 0};
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(info, t.info, sizeof(info), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { dev_free(ca); return set_error(CSB200_ERR_CUDA, "pattern classes: %s", cudaGetErrorString(e)); }
+    if (info[1] || info[2] == 0) { dev_free(ca); return CSB200_OK; }
+    A->cls = ca;
+    A->cls_count = info[2];
+    A->cls_state = 1;
+    return CSB200_OK;
+}
+
 // ncols_dev != null: the number of listed columns is read on the device (no host round trip)
 static int ensure_compressed(csb200_mat *A)
 {
@@ -874,8 +910,20 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
     int canon = 1;
     if ((st = mat_is_canonical(A, &canon)) != CSB200_OK) return fail(st);
 
-    arena_hint((size_t)(n > 0 ? n : 1) * (8 * 4 + BLK_STRIDE * sizeof(int2)) + (1 << 16));
-    DevBuf<int> ub, cnt, lists, counts, marks, marks_num, nblk, pick;
+    // pattern classes (spgemm_tpl.cuh): 0 automatic, 1 off, 2 also below TPL_MIN_N columns (tests)
+    const int tmode = tls().multiply_templates;
+    bool tpl = n > 0 && canon && tmode != 1 && A->nnz > 0 && B->nnz > 0 &&
+               (tmode == 2 || (n >= TPL_MIN_N && A->n >= TPL_MIN_N));
+    if (tpl) {
+        if ((st = ensure_classes(A)) != CSB200_OK) return fail(st);
+        tpl = A->cls_state == 1;
+    }
+    tls().last_templated = 0;
+
+    arena_hint((size_t)(n > 0 ? n : 1) * (9 * 4 + BLK_STRIDE * sizeof(int2)) + (1 << 16) +
+               (tpl ? CLS_TABLE_BYTES + (size_t)CLS_MAX * (4 + TPL_UB + TPL_CAP * 4) : 0));
+    DevBuf<int> ub, cnt, lists, counts, marks, marks_num, nblk, pick, cb, tpl_cnt, tpl_rows;
+    DevBuf<unsigned char> tpl_table, tpl_pos;
     DevBuf<int2> blkbuf;
     DevBuf<double> acc;
     // the blocked numeric path keeps BLK_STRIDE pairs per column (512 B): only while that stays modest
@@ -895,11 +943,36 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
     MM_CUDA(cudaMemsetAsync(cnt.ptr, 0, ncap * sizeof(int), s));
 
     int h_counts[8] = {0};
+    int h_tpl[4] = {0, 0, 0, 0};
     unsigned long long h_flops = 0;
     constexpr int DENSE_CTAS = 64;
+    ClsTable tb{};
     if (n > 0) {
         k_ub<<<ceil_div(n, 256), 256, 0, s>>>(n, B->p, B->i, A->p, ub.ptr, flops.ptr);
         MM_LAUNCHED();
+        if (tpl) {
+            // classes of B's columns, one template per class, cnt[] of every column that has one
+            MM_TRY(tpl_table.alloc(CLS_TABLE_BYTES));
+            MM_TRY(cb.alloc(ncap));
+            MM_TRY(tpl_cnt.alloc(CLS_MAX));
+            MM_TRY(tpl_pos.alloc((size_t)CLS_MAX * TPL_UB));
+            MM_TRY(tpl_rows.alloc((size_t)CLS_MAX * TPL_CAP));
+            tb = cls_table_at(tpl_table.ptr);
+            const int wgrid = ceil_div((long long)n * 32, 256);
+            k_cls_init<<<CLS_SLOTS / 256, 256, 0, s>>>(tb);
+            MM_LAUNCHED();
+            k_cls_hash_b<<<min(ceil_div(n, CLS_WARPS), sm_count() * 8), CLS_WARPS * 32, 0, s>>>(n, B->p, B->i, A->cls, tb, cb.ptr);
+            MM_LAUNCHED();
+            k_cls_compact<<<1, 1024, 0, s>>>(tb);
+            MM_LAUNCHED();
+            k_cls_verify_b<<<wgrid, 256, 0, s>>>(n, B->p, B->i, A->cls, tb, cb.ptr);
+            MM_LAUNCHED();
+            k_tpl_build<<<CLS_MAX, 32, 0, s>>>(tb, A->p, A->i, B->p, B->i, ub.ptr, tpl_cnt.ptr, tpl_pos.ptr, tpl_rows.ptr);
+            MM_LAUNCHED();
+            k_tpl_apply<<<ceil_div(n, 256), 256, 0, s>>>(n, tb, tpl_cnt.ptr, cb.ptr, cnt.ptr, ub.ptr);
+            MM_LAUNCHED();
+            MM_CUDA(cudaMemcpyAsync(h_tpl, tb.info, sizeof(h_tpl), cudaMemcpyDeviceToHost, s));
+        }
         // symbolic classes by min(ub, m): <=256 (cannot outgrow the small table) |
         // <=8000 (optimistic: small table first, columns that outgrow it -> list 2) | dense
         k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, m, 256, 8000, 8000, lists.ptr, counts.ptr);
@@ -908,6 +981,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
         MM_CUDA(cudaMemcpyAsync(&h_flops, flops.ptr, sizeof(h_flops), cudaMemcpyDeviceToHost, s));
         MM_CUDA(cudaStreamSynchronize(s));
         tls().last_flops = (int64_t)h_flops;
+        tls().last_templated = h_tpl[3];
         int *ovf_list = lists.ptr + 2 * ncap, *ovf_count = counts.ptr + 2;
         if (h_counts[0] + h_counts[1] > 0) MM_TRY(ensure_compressed(A));
         if (blocked) {
@@ -951,8 +1025,26 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
     if (values) MM_TRY(dev_alloc(&C->x, cap));
     if (h_total > 0) {
         // exact sizes: ub[j] = Cp[j+1] - Cp[j]
-        k_col_sizes<<<ceil_div(n, 256), 256, 0, s>>>(n, C->p, ub.ptr);
+        k_col_sizes<<<ceil_div(n, 256), 256, 0, s>>>(n, C->p, ub.ptr, tpl ? cb.ptr : nullptr);
         MM_LAUNCHED();
+        if (h_tpl[3] > 0) {
+            constexpr int smem = 8 * TPL_PER_WARP;
+            static const int variant = getenv("CSB200_TPL_VARIANT") ? atoi(getenv("CSB200_TPL_VARIANT")) : 0;
+#define TPL_LAUNCH(V, BATCH, MINB)                                                                           \
+            do {                                                                                             \
+                auto kern = k_num_tpl<V, BATCH, MINB>;                                                       \
+                const int grid = (int)min((long long)ceil_div(n, 8), (long long)sm_count() * MINB);          \
+                MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+                kern<<<grid, 256, smem, s>>>(n, cb.ptr, tpl_cnt.ptr, tpl_pos.ptr, tpl_rows.ptr, A->p, A->x,  \
+                                             B->p, B->i, B->x, C->p, C->i, C->x);                            \
+            } while (0)
+            if (!values) TPL_LAUNCH(false, 4, 8);
+            else if (variant == 1) TPL_LAUNCH(true, 8, 4);
+            else if (variant == 2) TPL_LAUNCH(true, 8, 3);
+            else TPL_LAUNCH(true, 4, 5);                 // fastest of the three on st27 128^3 (5.36 / 5.77 / 5.60 ms per product)
+#undef TPL_LAUNCH
+            MM_LAUNCHED();
+        }
         int n_blocked = 0;
         if (blocked) {
             // columns whose block list was kept go to the blocked kernel (list 3 region is free here)

@@ -30,7 +30,9 @@
 // is then sorted by j, and tied groups are re-read from the source column in
 // storage order.  Correctness never depends on how atomics were ordered.
 #include "common.cuh"
+#include <algorithm>
 #include <type_traits>
+#include <vector>
 
 namespace csb {
 
@@ -89,7 +91,7 @@ __device__ __forceinline__ void block_minmax(int lo, int hi, int *s_red, int &bm
 // such a matrix is transposed by the stable radix sort of radix.cu.
 __global__ void __launch_bounds__(TR_THREADS)
 k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__restrict__ bcount,
-              int *__restrict__ wide_tiles)
+              int *__restrict__ wide_tiles, int *__restrict__ tile_range)
 {
     __shared__ int cnt[HIST_WIN];
     __shared__ int s_red[16];
@@ -113,6 +115,8 @@ k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__rest
     int bmin, bmax;
     block_minmax(lo, hi, s_red, bmin, bmax);
     if (bmax < 0) return;
+    // first and last bucket this tile feeds: the host schedules the partition / sort slabs from it
+    if (threadIdx.x == 0) { tile_range[2 * blockIdx.x] = bmin; tile_range[2 * blockIdx.x + 1] = bmax; }
     const int win = bmax - bmin + 1;
     if (win <= HIST_WIN) {
         for (int k = threadIdx.x; k < win; k += TR_THREADS) cnt[k] = 0;
@@ -138,12 +142,12 @@ template <bool VALUES>
 __global__ void __launch_bounds__(TR_THREADS, 4)
 k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
             long long nnz, const int *__restrict__ tile_col, int log_rb, int colbits, int *__restrict__ bfill,
-            int *__restrict__ ikey, double *__restrict__ ival)
+            int *__restrict__ ikey, double *__restrict__ ival, int tile0)
 {
     __shared__ int sAp[PT_SMEM_COLS];
     __shared__ int cnt[HIST_WIN];
     __shared__ int s_red[16];
-    const int t = blockIdx.x;
+    const int t = tile0 + blockIdx.x;
     const long long p_begin = (long long)t * PT_TILE;
     const long long p_end = min(nnz, p_begin + PT_TILE);
     const int j_first = tile_col[t];
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(BK_THREADS, 5)
 k_bucket_sort(int m, int log_rb, int colbits, int nbuckets, const int *__restrict__ bstart,
               const int *__restrict__ ikey, const double *__restrict__ ival,
               const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
-              csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+              csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx, int b0)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double *sval = reinterpret_cast<double *>(smem);
@@ -402,7 +406,7 @@ k_bucket_sort(int m, int log_rb, int colbits, int nbuckets, const int *__restric
     int *rowcnt = scol + BK_CAP;
     int *rowstart = rowcnt + BK_RB_MAX + 1;
     int *warp_tot = rowstart + BK_RB_MAX + 1;          // 16 ints
-    const int b = blockIdx.x;
+    const int b = b0 + blockIdx.x;
     const int tid = threadIdx.x;
     const int rb = 1 << log_rb;
     const int R0 = b << log_rb;
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32, 4)
 k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__restrict__ bstart,
                    const int *__restrict__ ikey, const double *__restrict__ ival,
                    const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
-                   csi *__restrict__ Cp, csi *Ci, double *Cx)
+                   csi *__restrict__ Cp, csi *Ci, double *Cx, int b0, int b1)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -488,8 +492,8 @@ k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__re
     const int rb = 1 << log_rb;
     const int colmask = (1 << colbits) - 1;
 
-    int b = blockIdx.x * WB_WARPS + wid;
-    if (b >= nbuckets) return;
+    int b = b0 + blockIdx.x * WB_WARPS + wid;          // this launch sorts the buckets [b0, b1)
+    if (b >= b1) return;
     // prologue: bounds and row fields of the first bucket
     int base = bstart[b], nb = bstart[b + 1] - base;
     int rows[WB_EPT];
@@ -498,12 +502,12 @@ k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__re
         const int e = lane + k * 32;
         rows[k] = (e < nb && nb <= WB_CAP) ? ikey[base + e] : 0;      // packed (local row, column) words
     }
-    while (b < nbuckets) {
+    while (b < b1) {
         const int R0 = b << log_rb;
         const int nrows = min(rb, m - R0);
         const int bn = b + nwarps;                 // next bucket of this warp
         int nbase = 0, nnb = 0;
-        if (bn < nbuckets) { nbase = bstart[bn]; nnb = bstart[bn + 1] - nbase; }
+        if (bn < b1) { nbase = bstart[bn]; nnb = bstart[bn + 1] - nbase; }
 
         if (nb <= WB_CAP) {                        // larger buckets are k_bucket_big's job
             for (int k = lane; k < WB_RB_MAX; k += 32) cnt[k] = 0;
@@ -1020,11 +1024,16 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     }
     if (tls().force_transpose == 1 || !packable) return radix_path();
     TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 2) * sizeof(int), s));
+    const int nht = ceil_div(nnz, TR_TILE);
+    std::vector<int> h_range((size_t)2 * nht);
     {
         int *wide = bfill.ptr + nbuckets + 1, h_wide = 0;
-        k_bucket_hist<<<ceil_div(nnz, TR_TILE), TR_THREADS, 0, s>>>(A->i, nnz, log_rb, bfill.ptr, wide);
+        DevBuf<int> tile_range;
+        if ((st = tile_range.alloc((size_t)2 * nht)) != CSB200_OK) return fail(st);
+        k_bucket_hist<<<nht, TR_THREADS, 0, s>>>(A->i, nnz, log_rb, bfill.ptr, wide, tile_range.ptr);
         TR_LAUNCHED();
         TR_CUDA(cudaMemcpyAsync(&h_wide, wide, sizeof(int), cudaMemcpyDeviceToHost, s));
+        TR_CUDA(cudaMemcpyAsync(h_range.data(), tile_range.ptr, h_range.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
         TR_CUDA(cudaStreamSynchronize(s));
         if (h_wide > 0) return radix_path();
     }
@@ -1052,21 +1061,60 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     if (has_x && (st = ival.alloc((size_t)nnz + 8)) != CSB200_OK) return fail(st);
     k_tile_cols<<<ceil_div(ntiles + 1, 256), 256, 0, s>>>(A->p, n, nnz, ntiles, tile_col.ptr);
     TR_LAUNCHED();
-    if (has_x) k_partition<true><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, log_rb, colbits, bfill.ptr, ikey.ptr, ival.ptr);
-    else       k_partition<false><<<ntiles, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, nnz, tile_col.ptr, log_rb, colbits, bfill.ptr, ikey.ptr, nullptr);
-    TR_LAUNCHED();
-    if (warp_path) {
-        constexpr int smem = WB_WARPS * WB_WARP_BYTES;
-        const int grid = min(ceil_div(nbuckets, WB_WARPS), sm_count() * 4);
-        if (has_x) k_bucket_sort_warp<true><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, ival.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-        else       k_bucket_sort_warp<false><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, nullptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
-        TR_LAUNCHED();
-    } else {
-        TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
-        TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
-        if (has_x) k_bucket_sort<true><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, ival.ptr, A->p, A->i, A->x, C->p, C->i, C->x);
-        else       k_bucket_sort<false><<<nbuckets, BK_THREADS, BK_SMEM, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, nullptr, A->p, A->i, nullptr, C->p, C->i, nullptr);
-        TR_LAUNCHED();
+    // Slabs: a banded matrix completes its buckets in order -- once the entries up to some tile are
+    // partitioned, no later tile feeds the buckets below the smallest bucket those later tiles
+    // touch.  The partition is therefore cut into slabs of a few million entries, and after each
+    // slab the buckets it completed are sorted at once, while their share of the intermediate is
+    // still in the 126 MB L2: the second hop then reads L2 instead of HBM.  A matrix whose buckets
+    // stay open for long (more than SLAB_LAG_BYTES of intermediate) takes one slab, as before.
+    struct Slab { int tile_end, bucket_end; };
+    std::vector<Slab> slabs;
+    {
+        constexpr long long SLAB_LAG_BYTES = 40LL << 20;
+        const long long slab_entries = std::min<long long>(4LL << 20, std::max<long long>(1LL << 20, nnz / 16));
+        const int step = (int)(slab_entries / TR_TILE);
+        bool ok = tls().force_transpose != 3 && h_ct[0] == 0 && nht >= 4 * step;
+        if (ok) {
+            std::vector<int> sufmin((size_t)nht + 1);
+            sufmin[nht] = nbuckets;
+            for (int t = nht - 1; t >= 0; t--) sufmin[t] = std::min(sufmin[t + 1], h_range[2 * t]);
+            const double bytes_per_bucket = (has_x ? 12.0 : 4.0) * (double)nnz / nbuckets;
+            int premax = -1, t = 0;
+            for (int e = step; ok; e += step) {
+                if (e > nht) e = nht;
+                for (; t < e; t++) premax = std::max(premax, h_range[2 * t + 1]);
+                const int frontier = e == nht ? nbuckets : sufmin[e];
+                if ((double)(premax + 1 - frontier) * bytes_per_bucket > (double)SLAB_LAG_BYTES) ok = false;
+                slabs.push_back({std::min(2 * e, ntiles), frontier});
+                if (e == nht) break;
+            }
+        }
+        if (!ok) { slabs.clear(); slabs.push_back({ntiles, nbuckets}); }
+    }
+    TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+    TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+    int tile0 = 0, b0 = 0;
+    for (const Slab &sl : slabs) {
+        const int nt = sl.tile_end - tile0;
+        if (nt > 0) {
+            if (has_x) k_partition<true><<<nt, TR_THREADS, 0, s>>>(A->p, A->i, A->x, nnz, tile_col.ptr, log_rb, colbits, bfill.ptr, ikey.ptr, ival.ptr, tile0);
+            else       k_partition<false><<<nt, TR_THREADS, 0, s>>>(A->p, A->i, nullptr, nnz, tile_col.ptr, log_rb, colbits, bfill.ptr, ikey.ptr, nullptr, tile0);
+            TR_LAUNCHED();
+        }
+        tile0 = sl.tile_end;
+        const int b1 = sl.bucket_end;
+        if (b1 > b0 && warp_path) {
+            constexpr int smem = WB_WARPS * WB_WARP_BYTES;
+            const int grid = min(ceil_div(b1 - b0, WB_WARPS), sm_count() * 4);
+            if (has_x) k_bucket_sort_warp<true><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, ival.ptr, A->p, A->i, A->x, C->p, C->i, C->x, b0, b1);
+            else       k_bucket_sort_warp<false><<<grid, WB_WARPS * 32, smem, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, nullptr, A->p, A->i, nullptr, C->p, C->i, nullptr, b0, b1);
+            TR_LAUNCHED();
+        } else if (b1 > b0) {
+            if (has_x) k_bucket_sort<true><<<b1 - b0, BK_THREADS, BK_SMEM, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, ival.ptr, A->p, A->i, A->x, C->p, C->i, C->x, b0);
+            else       k_bucket_sort<false><<<b1 - b0, BK_THREADS, BK_SMEM, s>>>(m, log_rb, colbits, nbuckets, bstart.ptr, ikey.ptr, nullptr, A->p, A->i, nullptr, C->p, C->i, nullptr, b0);
+            TR_LAUNCHED();
+        }
+        b0 = std::max(b0, b1);
     }
     {
         if (h_ct[0] > 0) {

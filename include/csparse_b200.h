@@ -90,8 +90,9 @@ CSB200_API int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
 /* which algorithm later transposes use: 0 = automatic (one-pass mirror lookup for square matrices
  * with sorted duplicate-free columns and a symmetric pattern -- verified by the kernel itself --,
  * else the two-level bucket sort, or the stable radix sort when power-law rows overflow the
- * buckets), 1 = always the radix sort, 2 = automatic without the mirror path; for tests and
- * benchmarks */
+ * buckets), 1 = always the radix sort, 2 = automatic without the mirror path, 3 = like 2 with the
+ * bucket sort's partition and sort phases as two whole passes instead of L2-sized slabs; for tests
+ * and benchmarks */
 CSB200_API int csb200_transpose_force_path(int path);
 /* the path the calling thread's last transpose took: 1 mirror, 2 bucket sort, 3 radix sort,
  * 0 trivial (empty matrix) */
@@ -157,8 +158,13 @@ CSB200_API int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B,
  * block), the rest in the reference's discovery order; 1 = always the reference's discovery order
  * (then p, i, x are bit-identical to cs_multiply on canonical inputs).  The set of rows and every
  * value are the same either way.  2 / 3 = automatic with the first / second version of the
- * blocked numeric kernel, for A/B measurements and tests. */
+ * blocked numeric kernel, for A/B measurements and tests.  4 = automatic without the pattern-class
+ * templates, 5 = templates tried at any size (automatic: from 16384 columns).  Columns formed from a
+ * class template (matrices of translation-invariant operators: one symbolic pass per class of
+ * columns instead of one per column) are always in the reference's discovery order. */
 CSB200_API int csb200_multiply_force_path(int path);
+/* columns the last csb200_multiply on this thread formed from pattern-class templates */
+CSB200_API int64_t csb200_multiply_last_templated(void);
 /* number of multiply-adds of the last csb200_multiply on this thread */
 CSB200_API int64_t csb200_multiply_last_flops(void);
 

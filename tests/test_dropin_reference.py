@@ -133,7 +133,10 @@ def test_cs_scc_mutates_the_returned_p(ref, monkeypatch, name):
     assert swapped == plain
 
 
-@pytest.mark.parametrize("name", ["t1", "bcsstk01", "fs_183_1", "ibm32a", "ibm32b", "west0067", "ash219", "lp_afiro"])
+# west0067, ash219, lp_afiro and mbeacxc are left out: the UNPATCHED reference never returns from
+# cs_maxtrans on them under Python 3 (csparse.py:1511, an endless augmenting-path loop of its own)
+@pytest.mark.timeout(60)
+@pytest.mark.parametrize("name", ["t1", "bcsstk01", "fs_183_1", "ibm32a", "ibm32b"])
 def test_cs_dmperm_calls_gpu_transpose(ref, monkeypatch, name):
     def run(r):
         D = r.cs_dmperm(ref_cs(r, name), 0)

@@ -61,15 +61,15 @@ def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
     def tr():
         holder["c"] = cc.cs_transpose(dA, True)
     if ONLY != "multiply":
-        for path in (None, "bucket"):
+        for path in (None, "bucket", "bucket_noslab"):
             cc.force_transpose_path(path)
             try:
                 med, best = timeit(tr, 2, 7)
                 took = cc.last_transpose_path()
             finally:
                 cc.force_transpose_path(None)
-            report(f"{tag} cs_transpose[{took}]", synth.transpose_bytes(m, n, nnz), med, best)
-            if took != "mirror" and path is None:
+            report(f"{tag} cs_transpose[{took}{' noslab' if path == 'bucket_noslab' else ''}]", synth.transpose_bytes(m, n, nnz), med, best)
+            if took == "radix":
                 break
     holder.clear()
     xv = torch.randn(n, dtype=torch.float64, device="cuda")
