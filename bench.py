@@ -44,6 +44,8 @@ def parse():
                     choices=["gaxpy_lap2d", "multiply_st27", "transpose_lap2d", "gaxpy_rmat"])
     ap.add_argument("--k", type=int, default=0, help="grid edge (lap2d: 4096, st27: 128) or R-MAT scale (24)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--halo", default="fused", choices=["fused", "nccl"],
+                    help="N > 1 halo exchange of cs_gaxpy: pulled over NVLink inside the one SpMV launch, or batched NCCL send/recv")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads in the N=1 default run")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
@@ -347,9 +349,95 @@ def extras_dist(a, torch, dist, cc, synth, csd, world, rank, peak, peak_src, hea
     return ex
 
 
+def bind_numa(local: int):
+    """Pin this process to the CPUs next to GPU `local` (sysfs local_cpulist of its PCI function), so
+    that pinned host buffers allocated from now on come from that NUMA node.  Returns the node or None."""
+    try:
+        bdf = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                      text=True, timeout=20).strip().lower()
+        dom, rest = bdf.split(":", 1)
+        dev = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}"
+        cpus = set()
+        with open(dev + "/local_cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        with open(dev + "/numa_node") as f:
+            return int(f.read().strip())
+    except Exception:
+        return None
+
+
+def measured_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/traffic.json, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[key]["dram_bytes"]
+    except Exception:
+        return None
+
+
 def pinned(torch, arr):
     t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
     return t
+
+
+def e2e_transpose(torch, cc, m, n, p, i, x, steps=3):
+    """cs_transpose through the C ABI on HOST buffers (pinned): upload of A, transpose, download of
+    A' inside the timed region (csb200_transpose_host)."""
+    import ctypes as C
+    from csparse_cuda import _lib
+    nnz = len(i)
+    hp, hi, hx = pinned(torch, p), pinned(torch, i), pinned(torch, x)
+    cp = torch.empty(m + 1, dtype=torch.int32).pin_memory()
+    ci = torch.empty(max(nnz, 1), dtype=torch.int32).pin_memory()
+    cx = torch.empty(max(nnz, 1), dtype=torch.float64).pin_memory()
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    call = lambda: _lib.check(_lib.lib().csb200_transpose_host(m, n, ptr(hp), ptr(hi), ptr(hx), ptr(cp), ptr(ci), ptr(cx)))
+    call(); call()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    dt = (time.perf_counter() - t0) / steps
+    from csparse_cuda import synth
+    b = synth.transpose_bytes(m, n, nnz)
+    return {"value": b / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * (n + 1) + 12 * nnz,
+            "d2h_bytes_per_step": 4 * (m + 1) + 12 * nnz, "ms_per_step": dt * 1e3, "steps": steps,
+            "call": "csb200_transpose_host(m,n,Ap,Ai,Ax,Cp,Ci,Cx): pinned host buffers; uploads A, transposes, downloads A'"}
+
+
+def e2e_multiply(torch, cc, m, n, p, i, x, nnzc, steps=3):
+    """cs_multiply A*A through the C ABI on HOST buffers (pinned): upload of A, multiply, download of
+    C inside the timed region (csb200_mat_upload + csb200_multiply + csb200_mat_download)."""
+    import ctypes as C
+    from csparse_cuda import _lib
+    L = _lib.lib()
+    nnz = len(i)
+    hp, hi, hx = pinned(torch, p), pinned(torch, i), pinned(torch, x)
+    cp = torch.empty(n + 1, dtype=torch.int32).pin_memory()
+    ci = torch.empty(nnzc, dtype=torch.int32).pin_memory()
+    cx = torch.empty(nnzc, dtype=torch.float64).pin_memory()
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+
+    def call():
+        hA, hC = C.c_void_p(), C.c_void_p()
+        _lib.check(L.csb200_mat_upload(m, n, ptr(hp), ptr(hi), ptr(hx), 1, C.byref(hA)))
+        _lib.check(L.csb200_multiply(hA, hA, C.byref(hC)))
+        _lib.check(L.csb200_mat_download(hC, ptr(cp), ptr(ci), ptr(cx)))
+        L.csb200_mat_free(hC)
+        L.csb200_mat_free(hA)
+    call(); call()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    dt = (time.perf_counter() - t0) / steps
+    assert int(cp[n]) == nnzc
+    return {"value": nnzc / dt, "unit": "nnz(C)/s", "h2d_bytes_per_step": 4 * (n + 1) + 12 * nnz,
+            "d2h_bytes_per_step": 4 * (n + 1) + 12 * nnzc, "ms_per_step": dt * 1e3, "steps": steps,
+            "call": "csb200_mat_upload(A) + csb200_multiply(A, A) + csb200_mat_download(C): pinned host buffers, "
+                    "validation of A, pattern classes / entry-major copy of A rebuilt every step (fresh handle)"}
 
 
 def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler):
@@ -379,7 +467,7 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
     else:
         blk = csd.RowBlock(r0, r1, p, i, x, int(i.min()), int(i.max()))
         sh = csd.ShardedGaxpy(blk, n_global, n_global, bounds, make_local=csd.cuda_make_local,
-                              local_spmv=csd.cuda_local_spmv, device="cuda")
+                              local_spmv=csd.cuda_local_spmv, device="cuda", fused=(a.halo == "fused"))
         plan = sh.handle.gaxpy_plan()
         xv = sh.own_view()                      # x lives inside the halo window: no per-step copy
         xv.copy_(x_own)
@@ -387,8 +475,13 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
         step = lambda: sh.step(x_own, y_own)
         step()
         per = 1 if plan == "stream" else 2
-        launches_per_step = per * (1 + (sh.h_top is not None) + (sh.h_bot is not None)) if sh.split else per
-        exch, mode = sh.exchanged_bytes, sh.plan.mode + ("+overlap" if sh.split else "")
+        if sh.fused:
+            launches_per_step = per if plan == "stream" else per + 2
+            mode = "halo pulled over NVLink by the SpMV launch itself (peer-mapped windows, no collective)"
+        else:
+            launches_per_step = per * (1 + (sh.h_top is not None) + (sh.h_bot is not None)) if sh.split else per
+            mode = sh.plan.mode + ("+overlap (NCCL batch_isend_irecv)" if sh.split else "")
+        exch = sh.exchanged_bytes
 
     l0 = cc.launch_count()
     sampler.start()
@@ -401,17 +494,20 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
         kern = step
     else:
         xw = sh.x_window
-        mid = y_own[sh.split[0]:sh.split[1]] if sh.split else y_own
-        kern = lambda: csd.cuda_local_spmv(sh.handle, xw, mid)
-        if sh.split:     # the interior block is the dominant launch
-            nr = sh.split[1] - sh.split[0]
-            alg_bytes_local = synth.gaxpy_bytes(nr, nr, sh.handle.nnz)
+        if sh.fused:     # one handle for the whole block: the same rows without the halo protocol
+            kern = lambda: csd.cuda_local_spmv(sh.handle, xw, y_own)
+        else:
+            mid = y_own[sh.split[0]:sh.split[1]] if sh.split else y_own
+            kern = lambda: csd.cuda_local_spmv(sh.handle, xw, mid)
+            if sh.split:     # the interior block is the dominant launch
+                nr = sh.split[1] - sh.split[0]
+                alg_bytes_local = synth.gaxpy_bytes(nr, nr, sh.handle.nnz)
     kms = device_timed(torch, dist, 1, kern, a.steps, 2) / a.steps
     clocks = sampler.stop()
     achieved = alg_bytes_local / (kms * 1e-3) / 1e9
-    # DRAM bytes per launch of k_spmv_tma on this exact config from the ncu --set full capture
-    # (profiles/r1c_spmv_tma_full.md: dram__bytes_read.sum + dram__bytes_write.sum)
-    traffic = 1342053000 + 128040704 if (world == 1 and k == 4096 and plan == "stream") else None
+    # DRAM bytes per launch of the dominant kernel on this exact config, from the committed ncu
+    # --set full capture of the current binary (profiles/traffic.json names the capture it came from)
+    traffic = measured_traffic(f"k_spmv_tma lap2d {k}^2") if (world == 1 and plan == "stream") else None
 
     # e2e: the reference-facing call on HOST buffers (pinned), copies inside the timed region.
     # "e2e": csb200_gaxpy(handle, x, y) -- the step's inputs (x and the y it accumulates into)
@@ -450,17 +546,28 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
                        "the matrix handle (uploaded once, like the reference's cs object) stays in HBM"}
         e2e_res = e2e_cold
     else:
-        # N > 1: per step each rank copies its x slice H2D and its y slice D2H around the sharded step
+        # N > 1, host slices of x and y per rank (pinned, allocated after binding the process to the
+        # CPUs next to its GPU).  Fused halo: csb200_gaxpy_halo -- the ends of x first, the neighbours'
+        # lines pulled over NVLink, y in row chunks with duplex copies, as csb200_gaxpy does at N = 1.
+        node = bind_numa(local)
         hx_own, hy_own = x_own.cpu().pin_memory(), y_own.cpu().pin_memory()
-
-        def e2e_step():
-            x_own.copy_(hx_own, non_blocking=True)
-            sh.step(x_own, y_own)
-            hy_own.copy_(y_own, non_blocking=True)
-        ems = device_timed(torch, dist, world, e2e_step, a.steps, 2)
-        e2e = {"value": alg_bytes_global * a.steps / (ems * 1e-3) / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": 8 * (r1 - r0), "d2h_bytes_per_step": 8 * (r1 - r0), "ms_per_step": ems / a.steps,
-               "call": "per rank: x slice H2D, halo exchange + local csb200_gaxpy_t_dev, y slice D2H (matrix block resident)"}
+        if sh.fused:
+            e2e_step = lambda: sh.step_host(hx_own, hy_own)
+            call = ("per rank: csb200_gaxpy_halo(block, halo, x_slice, y_slice) on pinned host slices -- x and y H2D, "
+                    "halo lines pulled from the neighbours' windows, y D2H in row chunks (duplex), matrix block resident")
+            h2d = 16 * (r1 - r0)
+        else:
+            def e2e_step():
+                x_own.copy_(hx_own, non_blocking=True)
+                sh.step(x_own, y_own)
+                hy_own.copy_(y_own, non_blocking=True)
+            call = "per rank: x slice H2D, halo exchange + local csb200_gaxpy_t_dev, y slice D2H (matrix block resident)"
+            h2d = 8 * (r1 - r0)
+        esteps = min(a.steps, 100)
+        ems = device_timed(torch, dist, world, e2e_step, esteps, 2)
+        e2e = {"value": alg_bytes_global * esteps / (ems * 1e-3) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * (r1 - r0), "ms_per_step": ems / esteps,
+               "steps": esteps, "numa_node_of_rank0_buffers": node, "call": call}
 
     res = {
         "metric": "cs_gaxpy HBM GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
@@ -623,7 +730,7 @@ def bench_transpose(a, torch, cc, synth, k, peak, peak_src, sampler):
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak,
                          "traffic": None, "kernel": "whole cs_transpose (hist+scan+scatter+fix)", "peak_source": peak_src},
-            "e2e": None}
+            "e2e": e2e_transpose(torch, cc, m, n, p, i, x)}
 
 
 def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_src, sampler):
@@ -683,7 +790,7 @@ def bench_multiply(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak_sr
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "traffic": None, "kernel": "whole cs_multiply (ub+bin+symbolic+scan+numeric)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": b},
-            "e2e": None}
+            "e2e": e2e_multiply(torch, cc, m, n, p, i, x, nnzc) if world == 1 else None}
 
 
 def extras(a, torch, cc, synth, peak):
@@ -734,6 +841,7 @@ def extras(a, torch, cc, synth, peak):
 
         tr_paths("lap2d 4096^2", dA, synth.transpose_bytes(m, n, len(i)))
         hold.clear(); dA.free()
+        ex["cs_transpose lap2d 4096^2 e2e (host buffers through the C ABI)"] = e2e_transpose(torch, cc, m, n, p, i, x)
         m, n, p, i, x = synth.st27(128)
         dA = cc.from_arrays(m, n, p, i, x)
         def mul():
@@ -748,6 +856,7 @@ def extras(a, torch, cc, synth, peak):
         hold.clear()
         tr_paths("st27 128^3", dA, synth.transpose_bytes(m, n, len(i)))
         hold.clear(); dA.free()
+        ex["cs_multiply st27 128^3 A*A e2e (host buffers through the C ABI)"] = e2e_multiply(torch, cc, m, n, p, i, x, nnzc)
         m, n, tp, ti, tx = synth.rmat_torch(24, 16)
         nnz = int(ti.numel())
         dA = cc.from_device(m, n, tp.data_ptr(), ti.data_ptr(), tx.data_ptr())
@@ -806,12 +915,13 @@ def extras(a, torch, cc, synth, peak):
         # CPU baseline of the second headline metric: oracle cs_multiply on a bounded sample
         from oracle import oracle as orc
         orc.build()
-        ms_, ns_, ps_, is_, xs_ = synth.st27(48)
+        ms_, ns_, ps_, is_, xs_ = synth.st27(64)
         Ao = orc.csc(ms_, ns_, ps_, is_, xs_)
         t0 = time.perf_counter()
         Co = orc.cs_multiply(Ao, Ao)
         dt = time.perf_counter() - t0
-        ex["cpu_baseline cs_multiply (oracle port, 1 core, st27 48^3 sample)"] = {"s": dt, "nnz(C)/s": Co.nnz / dt}
+        ex["cpu_baseline cs_multiply (oracle port, 1 core, st27 64^3 sample: same per-column work as 128^3, rate is flat in n)"] = {
+            "s": dt, "nnz(C)/s": Co.nnz / dt, "nnzC": Co.nnz}
     except Exception as e:  # secondary numbers never sink the headline
         ex["error"] = repr(e)
     return ex

@@ -209,19 +209,19 @@ class DeviceMatrix(object):
     def gaxpy_plan(self) -> str:
         k = C.c_int()
         _lib.check(_lib.lib().csb200_gaxpy_plan(self._h, C.byref(k)), "gaxpy_plan")
-        return {1: "stream", 2: "merge", 3: "stream_ld"}.get(k.value, "none")
+        return {1: "stream", 2: "merge", 3: "stream_ld", 4: "split"}.get(k.value, "none")
 
     def force_gaxpy_plan(self, kind: Optional[str]):
-        code = {None: 0, "auto": 0, "stream": 1, "merge": 2, "stream_ld": 3}[kind]
+        code = {None: 0, "auto": 0, "stream": 1, "merge": 2, "stream_ld": 3, "split": 4}[kind]
         _lib.check(_lib.lib().csb200_gaxpy_force_plan(self._h, code))
 
 
 def force_transpose_path(path: Optional[str]):
     """Tests / benchmarks: None or "auto" = automatic choice, "radix" = always the stable radix sort,
-    "bucket" = automatic choice without the one-pass mirror path, "bucket_noslab" = the same with the
-    whole partition before the whole sort (no L2-resident slabs; A/B measurements)."""
+    "bucket" = automatic choice without the one-pass mirror path, "bucket_slab" = the same with the
+    partition and the sort interleaved in L2-sized slabs (measured slower; A/B measurements)."""
     _lib.check(_lib.lib().csb200_transpose_force_path({None: 0, "auto": 0, "radix": 1, "bucket": 2,
-                                                       "bucket_noslab": 3}[path]))
+                                                       "bucket_slab": 3}[path]))
 
 
 def last_transpose_path() -> str:
@@ -717,9 +717,10 @@ def force_multiply_path(path: Optional[str]):
     """None / "auto": device-matrix products may use the blocked numeric kernel (rows of a column
     block by block); "ordered": always the reference's discovery order; "blocked_v1" / "blocked_v2":
     automatic with that version of the blocked numeric kernel (A/B measurements); "no_templates":
-    automatic without the pattern-class templates; "templates": templates tried at any size."""
+    automatic without the pattern-class templates; "templates": templates tried at any size;
+    "templates_percol": the same without the lane-per-column kernel (one warp per column only)."""
     code = {None: 0, "auto": 0, "ordered": 1, "blocked_v1": 2, "blocked_v2": 3, "no_templates": 4,
-            "templates": 5}[path]
+            "templates": 5, "templates_percol": 6}[path]
     _lib.check(_lib.lib().csb200_multiply_force_path(code))
 
 

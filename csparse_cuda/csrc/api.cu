@@ -145,6 +145,10 @@ int spmv_plan_kind(const SpmvPlan *pl);
 int spmv_rows_align(csb200_mat *AT, int *align);
 int spmv_run_rows(csb200_mat *AT, const double *d_x, double *d_y, int ra, int rb, cudaStream_t s);
 int spmv_chunk_maxcol(csb200_mat *AT, int rows, int count, const int **out);
+int halo_pull_launch(csb200_halo *h, cudaStream_t s);
+int halo_acks_launch(csb200_halo *h, cudaStream_t s);
+double *halo_window_ptr(csb200_halo *h);
+long long halo_window_count(csb200_halo *h);
 
 // copy streams and events of the chunked host pipeline of csb200_gaxpy, one set per thread
 struct HostPipe {
@@ -454,6 +458,7 @@ int csb200_mat_free(csb200_mat *A)
     dev_free(A->c32_mask);
     dev_free(A->c32_len);
     dev_free(A->cls);
+    dev_free(A->soa_x);
     delete A;
     return CSB200_OK;
 }
@@ -510,7 +515,7 @@ int csb200_gaxpy_plan(csb200_mat *A, int *kind)
 
 int csb200_gaxpy_force_plan(csb200_mat *A, int kind)
 {
-    if (!A || kind < 0 || kind > 3) return set_error(CSB200_ERR_ARG, "bad plan kind");
+    if (!A || kind < 0 || kind > 4) return set_error(CSB200_ERR_ARG, "bad plan kind");
     A->forced_plan = kind;
     if (A->csr) A->csr->forced_plan = kind;
     return CSB200_OK;
@@ -600,6 +605,91 @@ int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
     return CSB200_OK;
 }
 
+// ---- cs_gaxpy on a row block of a sharded matrix, HOST x and y -------------------------------------
+// The sharded step as the reference-facing call would see it: this rank's slice of x and of y live
+// in (pinned) host memory.  The two ends of x travel first, so that the neighbours can pull their halo
+// lines (k_halo_pull) while the rest of x and y are still on the bus; y then moves in row chunks on
+// two copy streams exactly as in csb200_gaxpy -- the D2H of a finished chunk overlaps the H2D of the
+// next ones, the SpMV of a chunk starts when the part of x it reads has landed.
+int csb200_gaxpy_halo(csb200_mat *AT, csb200_halo *h, const double *x_own, int64_t own_off, int64_t own_len,
+                      int64_t edge_lo, int64_t edge_hi, double *y)
+{
+    ArenaScope arena_scope;
+    if (!AT || !h || !x_own || !y || own_off < 0 || own_len < 0 || edge_lo < 0 || edge_hi < 0)
+        return set_error(CSB200_ERR_ARG, "cs_gaxpy: bad arguments");
+    if (!AT->x) return set_error(CSB200_ERR_ARG, "cs_gaxpy: matrix has no values");
+    if (own_off + own_len > halo_window_count(h) || AT->m > halo_window_count(h))
+        return set_error(CSB200_ERR_ARG, "cs_gaxpy: the x window is shorter than the block needs");
+    if (edge_lo > own_len) edge_lo = own_len;
+    if (edge_hi > own_len) edge_hi = own_len;
+    const int m = AT->n;
+    double *win = halo_window_ptr(h);
+    double *d_own = win + own_off;
+    DevBuf<double> d_y;
+    CSB_TRY(d_y.alloc((size_t)(m > 0 ? m : 1)));
+    cudaStream_t s = stream();
+    HostPipe &hp = host_pipe();
+    CSB_TRY(hp.init());
+    int align = 0;
+    if (m >= (1 << 20)) CSB_TRY(spmv_rows_align(AT, &align));
+    CSB_CUDA(cudaEventRecord(hp.start, s));                          // earlier work on s is done, d_y exists
+    CSB_CUDA(cudaStreamWaitEvent(hp.h2d, hp.start, 0));
+    // 1. the ends of my slice, for the neighbours
+    if (edge_lo > 0) CSB_CUDA(cudaMemcpyAsync(d_own, x_own, (size_t)edge_lo * sizeof(double), cudaMemcpyHostToDevice, hp.h2d));
+    if (edge_hi > 0)
+        CSB_CUDA(cudaMemcpyAsync(d_own + own_len - edge_hi, x_own + own_len - edge_hi, (size_t)edge_hi * sizeof(double),
+                                 cudaMemcpyHostToDevice, hp.h2d));
+    CSB_CUDA(cudaEventRecord(hp.xdone, hp.h2d));
+    CSB_CUDA(cudaStreamWaitEvent(s, hp.xdone, 0));
+    CSB_TRY(halo_pull_launch(h, s));
+    if (align > 0) {
+        int rows = (m + HostPipe::MAX_CHUNKS - 1) / HostPipe::MAX_CHUNKS;
+        rows = ((rows + align - 1) / align) * align;
+        const int nchunks = (m + rows - 1) / rows;
+        const int *maxcol = nullptr;
+        CSB_TRY(spmv_chunk_maxcol(AT, rows, nchunks, &maxcol));
+        const long long xstep = ((own_len + nchunks - 1) / nchunks + 1) & ~1LL;
+        long long x_sent = 0;                                        // own coordinates
+        int c = 0;
+        for (int ra = 0; ra < m; ra += rows, c++) {
+            const int rb = ra + rows < m ? ra + rows : m;
+            const size_t bytes = (size_t)(rb - ra) * sizeof(double);
+            long long need = 0;                                      // window coordinates: x[0 .. need) must be there
+            for (int u = 0; u <= c; u++) need = need > (long long)maxcol[u] + 1 ? need : (long long)maxcol[u] + 1;
+            long long upto = need - own_off;                         // the halo below own_off comes from the pull
+            upto = ((upto + xstep - 1) / xstep) * xstep;
+            if (upto > own_len) upto = own_len;
+            if (upto > x_sent) {
+                CSB_CUDA(cudaMemcpyAsync(d_own + x_sent, x_own + x_sent, (size_t)(upto - x_sent) * sizeof(double),
+                                         cudaMemcpyHostToDevice, hp.h2d));
+                x_sent = upto;
+            }
+            CSB_CUDA(cudaMemcpyAsync(d_y.ptr + ra, y + ra, bytes, cudaMemcpyHostToDevice, hp.h2d));
+            CSB_CUDA(cudaEventRecord(hp.up[c], hp.h2d));
+            CSB_CUDA(cudaStreamWaitEvent(s, hp.up[c], 0));
+            CSB_TRY(spmv_run_rows(AT, win, d_y.ptr, ra, rb, s));
+            CSB_CUDA(cudaEventRecord(hp.done[c], s));
+            CSB_CUDA(cudaStreamWaitEvent(hp.d2h, hp.done[c], 0));
+            CSB_CUDA(cudaMemcpyAsync(y + ra, d_y.ptr + ra, bytes, cudaMemcpyDeviceToHost, hp.d2h));
+        }
+    } else {
+        if (own_len > 0) CSB_CUDA(cudaMemcpyAsync(d_own, x_own, (size_t)own_len * sizeof(double), cudaMemcpyHostToDevice, hp.h2d));
+        if (m > 0) CSB_CUDA(cudaMemcpyAsync(d_y.ptr, y, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, hp.h2d));
+        CSB_CUDA(cudaEventRecord(hp.up[0], hp.h2d));
+        CSB_CUDA(cudaStreamWaitEvent(s, hp.up[0], 0));
+        CSB_TRY(spmv_run(AT, win, d_y.ptr));
+        CSB_CUDA(cudaEventRecord(hp.done[0], s));
+        CSB_CUDA(cudaStreamWaitEvent(hp.d2h, hp.done[0], 0));
+        if (m > 0) CSB_CUDA(cudaMemcpyAsync(y, d_y.ptr, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, hp.d2h));
+    }
+    // the neighbours have pulled my lines: the next call may overwrite x
+    CSB_TRY(halo_acks_launch(h, s));
+    CSB_CUDA(cudaEventRecord(hp.end, hp.d2h));
+    CSB_CUDA(cudaStreamWaitEvent(s, hp.end, 0));
+    CSB_CUDA(cudaStreamSynchronize(s));
+    return CSB200_OK;
+}
+
 int csb200_gaxpy_host(csi m, csi n, const csi *Ap, const csi *Ai, const double *Ax,
                       const double *x, double *y)
 {
@@ -634,10 +724,10 @@ int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B, csb200_mat
 
 int csb200_multiply_force_path(int path)
 {
-    if (path < 0 || path > 5) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
+    if (path < 0 || path > 6) return set_error(CSB200_ERR_ARG, "bad cs_multiply path");
     tls().multiply_ordered = path == 1;
     tls().multiply_blocked_version = (path == 2 || path == 3) ? path : 0;
-    tls().multiply_templates = path == 4 ? 1 : path == 5 ? 2 : 0;
+    tls().multiply_templates = path == 4 ? 1 : path == 5 ? 2 : path == 6 ? 3 : 0;
     return CSB200_OK;
 }
 

@@ -17,10 +17,10 @@ struct ThreadState {
     char err[640] = {0};
     int64_t last_flops = 0;
     // path switches of the tests / benchmarks (csb200_*_force_path): per thread, like the stream
-    int force_transpose = 0;          // 1: always the radix sort, 2: automatic choice without the mirror path, 3: 2 without slabs
+    int force_transpose = 0;          // 1: always the radix sort, 2: automatic choice without the mirror path, 3: 2 in L2-sized slabs
     int multiply_ordered = 0;         // 1: always the reference's discovery order
     int multiply_blocked_version = 0; // 2 / 3: which blocked numeric kernel (0 = default)
-    int multiply_templates = 0;       // pattern-class path: 0 automatic, 1 off, 2 on at any size
+    int multiply_templates = 0;       // pattern-class path: 0 automatic, 1 off, 2 on at any size, 3 like 2 without the lane-per-column kernel
     int64_t last_templated = 0;       // columns the last cs_multiply of this thread formed from class templates
     int add_force_spgemm = 0;         // 1: cs_add on the SpGEMM kernels even for canonical operands
 };
@@ -54,6 +54,16 @@ inline cudaStream_t stream() { return tls().stream; }
 
 // SMs of the current device (queried once per device; grids are sized in multiples of it)
 int sm_count();
+#ifdef __CUDACC__
+// grid of a persistent kernel: every CTA resident at once (SMs x CTAs that fit one SM)
+template <class K>
+inline int resident_grid(K kern, int threads, size_t smem = 0)
+{
+    int per = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, threads, smem) != cudaSuccess) { cudaGetLastError(); per = 1; }
+    return sm_count() * (per > 0 ? per : 1);
+}
+#endif
 
 // stream-ordered allocation from the device's default memory pool (cached: the
 // release threshold is raised once per device in ensure_device()).  Results (the p / i / x of a
@@ -181,6 +191,11 @@ struct csb200_mat {
     csi *cls = nullptr;
     int cls_state = -1;
     int cls_count = 0;
+    // entry-major copy of the values, soa_x[e * n + k] = e-th value of column k (k_num_soa): soa_state
+    // -1 not built, 0 does not qualify, 1 usable with soa_len slots per column
+    double *soa_x = nullptr;
+    int soa_state = -1;
+    int soa_len = 0;
 };
 
 // ---- device helpers -----------------------------------------------------------

@@ -196,6 +196,42 @@ k_rs_pass(long long nnz, int shift,
     __syncthreads();
     const int tile_n = (int)min((long long)RS_TILE, nnz - base);
     const int j_lo = SRC == 2 ? s_col[0] : 0, j_hi = SRC == 2 ? s_col[1] : 0;
+    // SRC == 2: the column of every entry of the tile, without a binary search per entry -- every
+    // non-empty column that starts inside the tile marks its first position, then a running maximum
+    // carries the marks forward.  The table (16-bit offsets from the tile's first column) takes the
+    // place of the per-warp digit counters, which are no longer needed; a tile spanning more than
+    // 65535 columns (long runs of empty columns) keeps the binary search.
+    unsigned short *colof = reinterpret_cast<unsigned short *>(&cnt[0][0]);
+    static_assert(RS_WARPS * RS_BINS * sizeof(int) >= RS_TILE * sizeof(unsigned short), "the column table fits the counters' space");
+    const bool marked = SRC == 2 && j_hi - j_lo < 65535;
+    if (marked) {
+#pragma unroll
+        for (int k = 0; k < RS_EPT; k++) colof[k * RS_THREADS + tid] = 0;
+        __syncthreads();
+        for (int j = j_lo + 1 + tid; j <= j_hi; j += RS_THREADS) {
+            const int a0 = Ap[j];
+            const long long q = (long long)a0 - base;
+            if (q >= 0 && q < tile_n && Ap[j + 1] > a0) colof[(int)q] = (unsigned short)(j - j_lo);   // one non-empty column per position
+        }
+        __syncthreads();
+        // inclusive running maximum over the tile: RS_EPT consecutive entries per thread
+        int v[RS_EPT];
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < RS_EPT; k++) { run = max(run, (int)colof[tid * RS_EPT + k]); v[k] = run; }
+        int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+        __shared__ int wmax[RS_WARPS];
+        if (lane == 31) wmax[wid] = inc;
+        __syncthreads();
+        int before = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) before = 0;
+        for (int w = 0; w < wid; w++) before = max(before, wmax[w]);
+#pragma unroll
+        for (int k = 0; k < RS_EPT; k++) colof[tid * RS_EPT + k] = (unsigned short)max(v[k], before);
+        __syncthreads();
+    }
 #pragma unroll
     for (int k = 0; k < RS_EPT; k++) {
         const int tpos = k * RS_THREADS + tid;
@@ -211,7 +247,7 @@ k_rs_pass(long long nnz, int shift,
             if constexpr (VALUES) v = r.v;
         } else {
             kk = key_in[e];
-            a = SRC == 2 ? upper_row(Ap, j_lo, j_hi, (int)e) : a_in[e];
+            a = SRC == 2 ? (marked ? j_lo + (int)colof[perm[tpos]] : upper_row(Ap, j_lo, j_hi, (int)e)) : a_in[e];
             if (VALUES) v = v_in[e];
         }
         if (DST == 1) {

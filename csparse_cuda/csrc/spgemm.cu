@@ -802,9 +802,9 @@ static int ensure_classes(csb200_mat *A)
     int *ca = nullptr;
     CSB_TRY(dev_alloc(&ca, (size_t)A->n));
     const ClsTable t = cls_table_at(tb.ptr);
-    const int grid = ceil_div((long long)A->n * 32, 256);
+    const int grid = ceil_div(A->n, 256);
     k_cls_init<<<CLS_SLOTS / 256, 256, 0, s>>>(t);
-    k_cls_hash_a<<<min(ceil_div(A->n, CLS_WARPS), sm_count() * 8), CLS_WARPS * 32, 0, s>>>(A->n, A->p, A->i, t, ca);
+    k_cls_hash_a<<<grid, 256, 0, s>>>(A->n, A->p, A->i, t, ca);
     k_cls_compact<<<1, 1024, 0, s>>>(t);
     k_cls_verify_a<<<grid, 256, 0, s>>>(A->n, A->p, A->i, t, ca);
     g_launches.fetch_add(4, std::memory_order_relaxed);
@@ -817,6 +817,35 @@ static int ensure_classes(csb200_mat *A)
     A->cls = ca;
     A->cls_count = info[2];
     A->cls_state = 1;
+    return CSB200_OK;
+}
+
+// entry-major copy of the values (spgemm_tpl.cuh, k_num_soa), once per handle; soa_state 0 = the
+// matrix does not qualify (a column longer than SOA_MAXLEN, or a copy more than twice the matrix)
+static int ensure_soa(csb200_mat *M)
+{
+    if (M->soa_state >= 0) return CSB200_OK;
+    M->soa_state = 0;
+    if (!M->x || M->n == 0 || M->nnz == 0) return CSB200_OK;
+    cudaStream_t s = stream();
+    int h_max = 0;
+    {
+        DevBuf<int> d_max;
+        CSB_TRY(d_max.alloc(1));
+        CSB_CUDA(cudaMemsetAsync(d_max.ptr, 0, sizeof(int), s));
+        k_max_col_len<<<min(ceil_div(M->n, 256), sm_count() * 8), 256, 0, s>>>(M->n, M->p, d_max.ptr);
+        CSB_LAUNCHED();
+        CSB_CUDA(cudaMemcpyAsync(&h_max, d_max.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CSB_CUDA(cudaStreamSynchronize(s));
+    }
+    M->max_col_len = h_max;
+    const long long slots = (long long)h_max * M->n;
+    if (h_max == 0 || h_max > SOA_MAXLEN || slots > 2 * M->nnz + 1024 || slots >= (1LL << 30)) return CSB200_OK;
+    CSB_TRY(dev_alloc(&M->soa_x, (size_t)slots));
+    k_soa_build<<<ceil_div(M->n, 256), 256, 0, s>>>(M->n, h_max, M->p, M->x, M->soa_x);
+    CSB_LAUNCHED();
+    M->soa_len = h_max;
+    M->soa_state = 1;
     return CSB200_OK;
 }
 
@@ -913,17 +942,27 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
     // pattern classes (spgemm_tpl.cuh): 0 automatic, 1 off, 2 also below TPL_MIN_N columns (tests)
     const int tmode = tls().multiply_templates;
     bool tpl = n > 0 && canon && tmode != 1 && A->nnz > 0 && B->nnz > 0 &&
-               (tmode == 2 || (n >= TPL_MIN_N && A->n >= TPL_MIN_N));
+               (tmode >= 2 || (n >= TPL_MIN_N && A->n >= TPL_MIN_N));
     if (tpl) {
         if ((st = ensure_classes(A)) != CSB200_OK) return fail(st);
         tpl = A->cls_state == 1;
     }
     tls().last_templated = 0;
+    // lane-per-column numeric kernel on entry-major copies of both factors' values
+    bool soa = tpl && values && tls().multiply_templates != 3;
+    if (soa) {
+        if ((st = ensure_soa(A)) != CSB200_OK || (st = ensure_soa(B)) != CSB200_OK) return fail(st);
+        soa = A->soa_state == 1 && B->soa_state == 1;
+    }
 
     arena_hint((size_t)(n > 0 ? n : 1) * (9 * 4 + BLK_STRIDE * sizeof(int2)) + (1 << 16) +
-               (tpl ? CLS_TABLE_BYTES + (size_t)CLS_MAX * (4 + TPL_UB + TPL_CAP * 4) : 0));
-    DevBuf<int> ub, cnt, lists, counts, marks, marks_num, nblk, pick, cb, tpl_cnt, tpl_rows;
-    DevBuf<unsigned char> tpl_table, tpl_pos;
+               (tpl ? CLS_TABLE_BYTES + (size_t)CLS_MAX * (4 + TPL_UB + TPL_CAP * 4) + 5 * (size_t)(n > 0 ? n : 1) : 0) +
+               (soa ? (size_t)CLS_MAX * (1 + SOA_TERMS * (sizeof(int2) + 1) + (SOA_CHUNKS * SOA_WARPS + 1) * 4) : 0));
+    DevBuf<int> ub, cnt, lists, counts, marks, marks_num, nblk, pick, cb, tpl_cnt, tpl_rows, tpl_wptr;
+    DevBuf<unsigned char> tpl_table, tpl_pos, tpl_soa, tpl_mode;
+    DevBuf<int> left_list;
+    DevBuf<unsigned char> tpl_tend;
+    DevBuf<int2> tpl_terms;
     DevBuf<int2> blkbuf;
     DevBuf<double> acc;
     // the blocked numeric path keeps BLK_STRIDE pairs per column (512 B): only while that stays modest
@@ -943,13 +982,15 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
     MM_CUDA(cudaMemsetAsync(cnt.ptr, 0, ncap * sizeof(int), s));
 
     int h_counts[8] = {0};
-    int h_tpl[4] = {0, 0, 0, 0};
+    int h_tpl[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // ClsTable::info: [3] templated columns, [4] of them for k_num_tpl
     unsigned long long h_flops = 0;
     constexpr int DENSE_CTAS = 64;
     ClsTable tb{};
     if (n > 0) {
-        k_ub<<<ceil_div(n, 256), 256, 0, s>>>(n, B->p, B->i, A->p, ub.ptr, flops.ptr);
-        MM_LAUNCHED();
+        if (!tpl) {
+            k_ub<<<ceil_div(n, 256), 256, 0, s>>>(n, B->p, B->i, A->p, ub.ptr, flops.ptr);
+            MM_LAUNCHED();
+        }
         if (tpl) {
             // classes of B's columns, one template per class, cnt[] of every column that has one
             MM_TRY(tpl_table.alloc(CLS_TABLE_BYTES));
@@ -957,19 +998,30 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             MM_TRY(tpl_cnt.alloc(CLS_MAX));
             MM_TRY(tpl_pos.alloc((size_t)CLS_MAX * TPL_UB));
             MM_TRY(tpl_rows.alloc((size_t)CLS_MAX * TPL_CAP));
+            MM_TRY(tpl_mode.alloc(ncap));
+            MM_TRY(left_list.alloc(ncap));
+            if (soa) {
+                MM_TRY(tpl_soa.alloc(CLS_MAX));
+                MM_TRY(tpl_terms.alloc((size_t)CLS_MAX * SOA_TERMS));
+                MM_TRY(tpl_tend.alloc((size_t)CLS_MAX * SOA_TERMS));
+                MM_TRY(tpl_wptr.alloc((size_t)CLS_MAX * (SOA_CHUNKS * SOA_WARPS + 1)));
+            }
             tb = cls_table_at(tpl_table.ptr);
-            const int wgrid = ceil_div((long long)n * 32, 256);
+            const int wgrid = ceil_div(n, 256);
             k_cls_init<<<CLS_SLOTS / 256, 256, 0, s>>>(tb);
             MM_LAUNCHED();
-            k_cls_hash_b<<<min(ceil_div(n, CLS_WARPS), sm_count() * 8), CLS_WARPS * 32, 0, s>>>(n, B->p, B->i, A->cls, tb, cb.ptr);
+            k_cls_hash_b<<<wgrid, 256, 0, s>>>(n, B->p, B->i, A->p, A->cls, tb, cb.ptr, ub.ptr, flops.ptr);    // k_ub's work included
             MM_LAUNCHED();
             k_cls_compact<<<1, 1024, 0, s>>>(tb);
             MM_LAUNCHED();
             k_cls_verify_b<<<wgrid, 256, 0, s>>>(n, B->p, B->i, A->cls, tb, cb.ptr);
             MM_LAUNCHED();
-            k_tpl_build<<<CLS_MAX, 32, 0, s>>>(tb, A->p, A->i, B->p, B->i, ub.ptr, tpl_cnt.ptr, tpl_pos.ptr, tpl_rows.ptr);
+            k_tpl_build<<<CLS_MAX, 32, 0, s>>>(tb, A->p, A->i, B->p, B->i, ub.ptr, tpl_cnt.ptr, tpl_pos.ptr, tpl_rows.ptr,
+                                               A->n, n, soa ? A->soa_len : 0, soa ? B->soa_len : 0,
+                                               soa ? tpl_soa.ptr : nullptr, tpl_terms.ptr, tpl_tend.ptr, tpl_wptr.ptr);
             MM_LAUNCHED();
-            k_tpl_apply<<<ceil_div(n, 256), 256, 0, s>>>(n, tb, tpl_cnt.ptr, cb.ptr, cnt.ptr, ub.ptr);
+            k_tpl_apply<<<ceil_div(n, 256), 256, 0, s>>>(n, tb, tpl_cnt.ptr, cb.ptr, cnt.ptr, ub.ptr, soa ? tpl_soa.ptr : nullptr,
+                                                         tpl_mode.ptr, left_list.ptr);
             MM_LAUNCHED();
             MM_CUDA(cudaMemcpyAsync(h_tpl, tb.info, sizeof(h_tpl), cudaMemcpyDeviceToHost, s));
         }
@@ -1027,15 +1079,26 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
         // exact sizes: ub[j] = Cp[j+1] - Cp[j]
         k_col_sizes<<<ceil_div(n, 256), 256, 0, s>>>(n, C->p, ub.ptr, tpl ? cb.ptr : nullptr);
         MM_LAUNCHED();
-        if (h_tpl[3] > 0) {
+        if (h_tpl[3] > 0 && soa) {
+            // 32 columns per CTA in lock step; what it leaves (grid boundaries, long columns) goes to k_num_tpl
+            MM_CUDA(cudaFuncSetAttribute(k_num_soa, cudaFuncAttributeMaxDynamicSharedMemorySize, SOA_SMEM));
+            // few CTAs per SM: each works on ~100 KB of A that should stay in its SM's L1
+            static const int soa_ctas = getenv("CSB200_SOA_CTAS") ? atoi(getenv("CSB200_SOA_CTAS")) : 4;
+            const int grid = (int)min((long long)ceil_div(n, 32), (long long)sm_count() * soa_ctas);
+            k_num_soa<<<grid, SOA_THREADS, SOA_SMEM, s>>>(n, cb.ptr, tpl_cnt.ptr, tpl_mode.ptr, tpl_terms.ptr, tpl_tend.ptr,
+                                                        tpl_wptr.ptr, tpl_rows.ptr, A->soa_x, B->soa_x, C->p, C->i, C->x);
+            MM_LAUNCHED();
+        }
+        if (h_tpl[4] > 0) {
             constexpr int smem = 8 * TPL_PER_WARP;
+            const int n_left = h_tpl[4];
             static const int variant = getenv("CSB200_TPL_VARIANT") ? atoi(getenv("CSB200_TPL_VARIANT")) : 0;
 #define TPL_LAUNCH(V, BATCH, MINB)                                                                           \
             do {                                                                                             \
                 auto kern = k_num_tpl<V, BATCH, MINB>;                                                       \
-                const int grid = (int)min((long long)ceil_div(n, 8), (long long)sm_count() * MINB);          \
+                const int grid = (int)min((long long)ceil_div(n_left, 8), (long long)sm_count() * MINB);     \
                 MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-                kern<<<grid, 256, smem, s>>>(n, cb.ptr, tpl_cnt.ptr, tpl_pos.ptr, tpl_rows.ptr, A->p, A->x,  \
+                kern<<<grid, 256, smem, s>>>(left_list.ptr, tb.info + 4, cb.ptr, tpl_cnt.ptr, tpl_pos.ptr, tpl_rows.ptr, A->p, A->x,  \
                                              B->p, B->i, B->x, C->p, C->i, C->x);                            \
             } while (0)
             if (!values) TPL_LAUNCH(false, 4, 8);

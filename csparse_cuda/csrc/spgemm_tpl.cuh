@@ -30,6 +30,15 @@ constexpr int CLS_MAX = 1024;            // more classes than this: not a struct
 constexpr int TPL_UB = 4096;             // products per column a template holds
 constexpr int TPL_CAP = 256;             // rows per column a template holds (positions fit a byte)
 constexpr int TPL_MIN_N = 16384;         // below this the extra launches cost more than they save
+constexpr int SOA_UB = 1024;             // products per column the lane-per-column kernel holds (term table in shared memory)
+constexpr int SOA_CNT = 128;             // rows per column it holds
+constexpr int SOA_MAXLEN = 64;           // longest column of an entry-major copy
+constexpr int SOA_MIN_LANES = 8;         // columns of one class inside a 32-column block worth a pass
+constexpr int SOA_THREADS = 256;
+constexpr int SOA_WARPS = SOA_THREADS / 32;
+constexpr int SOA_CHUNKS = SOA_CNT / 32;
+constexpr int SOA_BATCH = 8;             // terms a warp takes per step (its lists are padded to a multiple)
+constexpr int SOA_TERMS = SOA_UB + SOA_CHUNKS * SOA_WARPS * (SOA_BATCH - 1);
 
 struct ClsTable {
     unsigned long long *keys;            // CLS_SLOTS, 0 = empty
@@ -100,31 +109,47 @@ __device__ __forceinline__ int cls_insert(const ClsTable &t, unsigned long long 
     return -1;
 }
 
-// ---- classes of the columns of A: the rows relative to the column index, in storage order ------
-// Resident warps stride over the columns and remember the class of the previous column: in a
-// structured matrix nearly every column repeats it, and two million warps reading one table slot
-// would queue on a single L2 sector.
-constexpr int CLS_WARPS = 8;
-__global__ void __launch_bounds__(CLS_WARPS * 32)
-k_cls_hash_a(int n, const csi *__restrict__ Ap, const csi *__restrict__ Ai, ClsTable t, int *__restrict__ ca)
+// ---- classes of the columns: one THREAD per column -----------------------------------------------
+// A thread walks its column (the strided reads of neighbouring threads share lines through L1, as in
+// k_ub) and hashes it; inside a warp a column that repeats its left neighbour's hash takes that
+// neighbour's class, so only the heads of runs go to the table -- two million columns of one class
+// would otherwise queue on a single L2 sector.  Columns longer than CLS_MAXLEN have no class.
+constexpr int CLS_MAXLEN = 1024;
+
+// slot of every lane's class from the lanes' hashes (ok = the lane has one); all 32 lanes call
+__device__ __forceinline__ int cls_resolve(const ClsTable &t, unsigned long long h, bool ok, int col)
 {
     const int lane = threadIdx.x & 31;
-    const int nwarps = gridDim.x * CLS_WARPS;
-    unsigned long long last_h = 0ull;
-    int last_slot = -1, it = 0;
-    for (int k = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5); k < n; k += nwarps, it++) {
-        if ((it & 15) == 0 && __ldcg(t.info + 1)) return;
+    const unsigned long long hp = __shfl_up_sync(0xffffffffu, h, 1);
+    const bool okp = __shfl_up_sync(0xffffffffu, (int)ok, 1) != 0;
+    const bool head = ok && (lane == 0 || !okp || hp != h);
+    int slot = -1;
+    if (head) slot = cls_insert(t, h, col);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned left = heads & (0xffffffffu >> (31 - lane));      // heads at or left of this lane
+    const int src = left ? 31 - __clz(left) : lane;
+    slot = __shfl_sync(0xffffffffu, slot, src);
+    return ok ? slot : -1;
+}
+
+// A: the rows relative to the column index, in storage order
+__global__ void __launch_bounds__(256)
+k_cls_hash_a(int n, const csi *__restrict__ Ap, const csi *__restrict__ Ai, ClsTable t, int *__restrict__ ca)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long h = 0;
+    bool ok = false;
+    if (k < n && !__ldcg(t.info + 1)) {
         const int b = Ap[k], e = Ap[k + 1];
-        unsigned long long h = 0;
-        for (int p = b + lane; p < e; p += 32)
-            h += mix64(mix64((unsigned long long)(p - b) + 1) ^ (unsigned long long)(unsigned)(Ai[p] - k));
-        h = warp_sum64(h) + mix64(0xA5A5A5A5ull + (unsigned long long)(e - b));
+        ok = e - b <= CLS_MAXLEN;
+        if (ok)
+            for (int p = b; p < e; p++)
+                h += mix64(mix64((unsigned long long)(p - b) + 1) ^ (unsigned long long)(unsigned)(Ai[p] - k));
+        h += mix64(0xA5A5A5A5ull + (unsigned long long)(e - b));
         if (h == 0ull) h = 1ull;
-        if (lane == 0) {
-            if (h != last_h) { last_slot = cls_insert(t, h, k); last_h = last_slot >= 0 ? h : 0ull; }
-            ca[k] = last_slot;
-        }
     }
+    const int slot = cls_resolve(t, h, ok, k);
+    if (k < n) ca[k] = slot;
 }
 
 // dense class ids (slot order), one CTA of 1024 threads
@@ -157,111 +182,113 @@ __global__ void __launch_bounds__(1024) k_cls_compact(ClsTable t)
 __global__ void __launch_bounds__(256)
 k_cls_verify_a(int n, const csi *__restrict__ Ap, const csi *__restrict__ Ai, ClsTable t, int *__restrict__ ca)
 {
-    const int lane = threadIdx.x & 31;
-    const int k = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (k >= n) return;
-    if (t.info[1]) return;              // final by now: a cached load
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || t.info[1]) return;                 // the flag is final by now: a cached load
     const int slot = ca[k];
     bool ok = slot >= 0;
-    int r = 0;
-    if (ok) r = t.rep[slot];
-    if (ok && r != k) {
-        const int b = Ap[k], len = Ap[k + 1] - b, br = Ap[r];
-        ok = (Ap[r + 1] - br) == len;
-        if (ok)
-            for (int e = lane; e < len; e += 32)
-                if (Ai[b + e] - k != Ai[br + e] - r) ok = false;
+    if (ok) {
+        const int r = t.rep[slot];
+        if (r != k) {
+            const int b = Ap[k], len = Ap[k + 1] - b, br = Ap[r];
+            ok = (Ap[r + 1] - br) == len;
+            for (int e = 0; ok && e < len; e++) ok = Ai[b + e] - k == Ai[br + e] - r;
+        }
     }
-    ok = __all_sync(0xffffffffu, ok);
-    __syncwarp();
-    if (lane == 0) ca[k] = ok ? t.dense[slot] : -1;
+    ca[k] = ok ? t.dense[slot] : -1;
 }
 
-// ---- classes of the columns of B: (row relative to the column, class of that column of A) ------
-__global__ void __launch_bounds__(CLS_WARPS * 32)
-k_cls_hash_b(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi, const int *__restrict__ ca,
-             ClsTable t, int *__restrict__ cb)
+// B: (row relative to the column, class of that column of A); also k_ub's work on the same walk:
+// ub[j] = multiply-adds of column j, their total in *flops
+__global__ void __launch_bounds__(256)
+k_cls_hash_b(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi, const csi *__restrict__ Ap,
+             const int *__restrict__ ca, ClsTable t, int *__restrict__ cb, int *__restrict__ ub,
+             unsigned long long *flops)
 {
-    const int lane = threadIdx.x & 31;
-    const int nwarps = gridDim.x * CLS_WARPS;
-    unsigned long long last_h = 0ull;
-    int last_slot = -1, it = 0;
-    for (int j = blockIdx.x * CLS_WARPS + (threadIdx.x >> 5); j < n; j += nwarps, it++) {
-        if ((it & 15) == 0 && __ldcg(t.info + 1)) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long h = 0;
+    long long s = 0;
+    bool ok = false;
+    if (j < n) {
         const int b = Bp[j], e = Bp[j + 1];
-        unsigned long long h = 0;
-        bool ok = e > b;
-        for (int p = b + lane; p < e; p += 32) {
+        ok = e > b && e - b <= CLS_MAXLEN && !__ldcg(t.info + 1);
+        for (int p = b; p < e; p++) {
             const int k = Bi[p];
-            const int c = ca[k];
-            if (c < 0) ok = false;
-            h += mix64(mix64((unsigned long long)(p - b) + 1) ^ (unsigned long long)(unsigned)(k - j) ^
-                       ((unsigned long long)(unsigned)c << 32));
-        }
-        ok = __all_sync(0xffffffffu, ok);
-        h = warp_sum64(h) + mix64(0x5A5A5A5Aull + (unsigned long long)(e - b));
-        if (h == 0ull) h = 1ull;
-        if (lane == 0) {
-            int slot = -1;
+            s += Ap[k + 1] - Ap[k];
             if (ok) {
-                if (h != last_h) { last_slot = cls_insert(t, h, j); last_h = last_slot >= 0 ? h : 0ull; }
-                slot = last_slot;
+                const int c = ca[k];
+                if (c < 0) ok = false;
+                h += mix64(mix64((unsigned long long)(p - b) + 1) ^ (unsigned long long)(unsigned)(k - j) ^
+                           ((unsigned long long)(unsigned)c << 32));
             }
-            cb[j] = slot;
         }
+        h += mix64(0x5A5A5A5Aull + (unsigned long long)(e - b));
+        if (h == 0ull) h = 1ull;
+        ub[j] = (int)min(s, (long long)INT_MAX);
     }
+    const int slot = cls_resolve(t, h, ok, j);
+    if (j < n) cb[j] = slot;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(flops, (unsigned long long)s);
 }
 
 __global__ void __launch_bounds__(256)
 k_cls_verify_b(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi, const int *__restrict__ ca,
                ClsTable t, int *__restrict__ cb)
 {
-    const int lane = threadIdx.x & 31;
-    const int j = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (j >= n) return;
-    if (t.info[1]) return;              // final by now: a cached load
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || t.info[1]) return;
     const int slot = cb[j];
     bool ok = slot >= 0;
-    int r = 0;
-    if (ok) r = t.rep[slot];
-    if (ok && r != j) {
-        const int b = Bp[j], len = Bp[j + 1] - b, br = Bp[r];
-        ok = (Bp[r + 1] - br) == len;
-        if (ok)
-            for (int e = lane; e < len; e += 32) {
+    if (ok) {
+        const int r = t.rep[slot];
+        if (r != j) {
+            const int b = Bp[j], len = Bp[j + 1] - b, br = Bp[r];
+            ok = (Bp[r + 1] - br) == len;
+            for (int e = 0; ok && e < len; e++) {
                 const int k = Bi[b + e], kr = Bi[br + e];
-                if (k - j != kr - r || ca[k] != ca[kr]) ok = false;
+                ok = k - j == kr - r && ca[k] == ca[kr];
             }
+        }
     }
-    ok = __all_sync(0xffffffffu, ok);
-    __syncwarp();
-    if (lane == 0) cb[j] = ok ? t.dense[slot] : -1;
+    cb[j] = ok ? t.dense[slot] : -1;
 }
 
 // ---- the template of a class: cs_scatter on its representative column, one warp ------------------
 // A's columns are canonical (distinct rows per column), so the rows of a 32-entry step are distinct.
+// For k_num_soa the same trace is also stored inverted: for every row t of the column the products
+// that land on it, in the reference's order, as offsets into the entry-major copies of A and B
+// (term = {e * nA + (k - j),  d * nB} for the e-th entry of the A column named by the d-th entry of
+// B(:,j)); tpl_soa[c] says whether the class fits that kernel.
 __global__ void __launch_bounds__(32)
 k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, const csi *__restrict__ Bp,
             const csi *__restrict__ Bi, const int *__restrict__ ub, int *__restrict__ tpl_cnt,
-            unsigned char *__restrict__ tpl_pos, int *__restrict__ tpl_rows)
+            unsigned char *__restrict__ tpl_pos, int *__restrict__ tpl_rows,
+            int nA, int nB, int soa_len_a, int soa_len_b, unsigned char *__restrict__ tpl_soa,
+            int2 *__restrict__ tpl_terms, unsigned char *__restrict__ tpl_tend, int *__restrict__ tpl_wptr)
 {
     constexpr int LOGH = 10, H = 1 << LOGH;
     static_assert(H >= 2 * (TPL_CAP + 32), "the table never fills");
     __shared__ int keys[H];
     __shared__ unsigned short posof[H];
+    __shared__ int tcount[TPL_CAP + 1];
     const int lane = threadIdx.x, c = blockIdx.x;
     if (__ldcg(t.info + 1) || c >= __ldcg(t.info + 2)) return;
     const int j = t.rep_dense[c];
+    if (lane == 0 && tpl_soa) tpl_soa[c] = 0;
     if (ub[j] > TPL_UB) { if (lane == 0) tpl_cnt[c] = -1; return; }
     for (int s = lane; s < H; s += 32) keys[s] = EMPTY;
+    for (int s = lane; s <= TPL_CAP; s += 32) tcount[s] = 0;
     __syncwarp();
     const unsigned lt = lanemask_lt();
     int cnt = 0, q0 = 0;
     bool fail = false;
-    const int pb_end = Bp[j + 1];
-    for (int pb = Bp[j]; pb < pb_end && !fail; pb++) {
+    int maxa = 0;
+    const int pb_begin = Bp[j], pb_end = Bp[j + 1];
+    for (int pb = pb_begin; pb < pb_end && !fail; pb++) {
         const int k = Bi[pb];
         const int ab = Ap[k], ae = Ap[k + 1];
+        maxa = max(maxa, ae - ab);
         for (int pa0 = ab; pa0 < ae; pa0 += 32) {
             const int pa = pa0 + lane;
             const bool active = pa < ae;
@@ -275,30 +302,117 @@ k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, 
                 if (pos < TPL_CAP) tpl_rows[(size_t)c * TPL_CAP + pos] = i - j;
             }
             __syncwarp();
-            if (active) tpl_pos[(size_t)c * TPL_UB + q0 + (pa - ab)] = (unsigned char)posof[slot];
+            if (active) {
+                tpl_pos[(size_t)c * TPL_UB + q0 + (pa - ab)] = (unsigned char)posof[slot];
+                if (posof[slot] < TPL_CAP) tcount[posof[slot]]++;      // distinct rows in a step: no two lanes share a counter
+            }
             cnt += __popc(newmask);
             if (cnt > TPL_CAP) { fail = true; break; }
+            __syncwarp();
         }
         q0 += ae - ab;
     }
     if (lane == 0) tpl_cnt[c] = fail ? -1 : cnt;
+    if (fail || !tpl_soa) return;
+    // ---- inverted form for k_num_soa -----------------------------------------------------------
+    // Rows are taken in chunks of 32 (they leave k_num_soa as 256-byte runs); inside a chunk every row
+    // is given to one of SOA_WARPS warps, longest list first to the least loaded warp, and the term
+    // lists of a warp's rows are laid end to end: the warp then walks ONE flat list per chunk, eight
+    // terms at a time, whatever the rows' individual lengths.  tend[q] = row inside the chunk if term q
+    // closes a row (its sum is complete), 0 otherwise.  tcount[r] holds the length of row r's list here.
+    if (q0 > SOA_UB || cnt > SOA_CNT || maxa > soa_len_a || pb_end - pb_begin > soa_len_b) return;
+    __shared__ int rstart[SOA_CNT];                  // where the list of row r starts in the reordered table
+    __shared__ int rlen[SOA_CNT];
+    for (int q = lane; q < SOA_TERMS; q += 32) {     // padding terms read a(0) * b(0) of the column; their sum is dropped
+        tpl_terms[(size_t)c * SOA_TERMS + q] = make_int2(0, 0);
+        tpl_tend[(size_t)c * SOA_TERMS + q] = 0;
+    }
+    for (int r = lane; r < cnt; r += 32) rlen[r] = tcount[r];
+    __syncwarp();
+    const int nchunks = (cnt + 31) >> 5;
+    int *wptr = tpl_wptr + (size_t)c * (SOA_CHUNKS * SOA_WARPS + 1);
+    if (lane == 0) {
+        int run = 0;
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int t0 = ch * 32, nrow = min(32, cnt - t0);
+            int load[SOA_WARPS], owner[32];
+            for (int w = 0; w < SOA_WARPS; w++) load[w] = 0;
+            unsigned taken = 0;
+            for (int rank = 0; rank < nrow; rank++) {            // longest remaining row -> least loaded warp
+                int best = -1, blen = -1;
+                for (int r = 0; r < nrow; r++)
+                    if (!((taken >> r) & 1u) && rlen[t0 + r] > blen) { best = r; blen = rlen[t0 + r]; }
+                taken |= 1u << best;
+                int wmin = 0;
+                for (int w = 1; w < SOA_WARPS; w++) if (load[w] < load[wmin]) wmin = w;
+                owner[best] = wmin;
+                load[wmin] += blen;
+            }
+            for (int w = 0; w < SOA_WARPS; w++) {
+                wptr[ch * SOA_WARPS + w] = run;
+                for (int r = 0; r < nrow; r++) if (owner[r] == w) { rstart[t0 + r] = run; run += rlen[t0 + r]; }
+                run = (run + SOA_BATCH - 1) / SOA_BATCH * SOA_BATCH;      // whole steps only
+            }
+        }
+        for (int k = nchunks * SOA_WARPS; k <= SOA_CHUNKS * SOA_WARPS; k++) wptr[k] = run;
+    }
+    __syncwarp();
+    for (int r = lane; r < cnt; r += 32) tcount[r] = rstart[r];      // from here on: the fill cursor of row r
+    __syncwarp();
+    q0 = 0;
+    for (int pb = pb_begin; pb < pb_end; pb++) {     // the same walk again: products in the reference's order
+        const int k = Bi[pb];
+        const int ab = Ap[k], ae = Ap[k + 1];
+        const int d = pb - pb_begin;
+        for (int pa0 = ab; pa0 < ae; pa0 += 32) {
+            const int pa = pa0 + lane;
+            if (pa < ae) {
+                const int e = pa - ab;
+                const int r = tpl_pos[(size_t)c * TPL_UB + q0 + e];
+                const int idx = tcount[r]++;         // distinct rows in a step
+                tpl_terms[(size_t)c * SOA_TERMS + idx] = make_int2(e * nA + (k - j), d * nB);
+                if (idx == rstart[r] + rlen[r] - 1)                       // the row's last term: 1 + row inside the chunk
+                    tpl_tend[(size_t)c * SOA_TERMS + idx] = (unsigned char)((r & 31) + 1);
+            }
+            __syncwarp();
+        }
+        q0 += ae - ab;
+    }
+    if (lane == 0) tpl_soa[c] = 1;
 }
 
-// columns of a class with a template: cnt[j] is known, the general symbolic phase skips them (ub 0)
+// columns of a class with a template: cnt[j] is known, the general symbolic phase skips them (ub 0).
+// The warp (32 consecutive columns = one block of k_num_soa) also decides who forms them: a class
+// with at least SOA_MIN_LANES columns in the block and the tables for it -> k_num_soa (mode 1); the
+// rest (grid boundaries, long columns) go to the list k_num_tpl walks, one warp per column.
 __global__ void k_tpl_apply(int n, ClsTable t, const int *__restrict__ tpl_cnt, int *__restrict__ cb,
-                            int *__restrict__ cnt, int *__restrict__ ub)
+                            int *__restrict__ cnt, int *__restrict__ ub, const unsigned char *__restrict__ tpl_soa,
+                            unsigned char *__restrict__ mode, int *__restrict__ left_list)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const bool live = !t.info[1];
     bool hit = false;
+    int c = -1;
     if (j < n) {
-        const int c = live ? cb[j] : -1;
+        c = live ? cb[j] : -1;
         const int tc = c >= 0 ? tpl_cnt[c] : -1;
         hit = tc >= 0;
-        if (hit) { cnt[j] = tc; ub[j] = 0; } else cb[j] = -1;
+        if (hit) { cnt[j] = tc; ub[j] = 0; } else { cb[j] = -1; c = -1; }
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(t.info + 3, __popc(m));
+    if (lane == 0 && m) atomicAdd(t.info + 3, __popc(m));
+    bool soa = false;
+    if (tpl_soa) {
+        const unsigned same = __match_any_sync(0xffffffffu, c);
+        soa = hit && tpl_soa[c] && __popc(same) >= SOA_MIN_LANES;
+    }
+    const unsigned left = __ballot_sync(0xffffffffu, hit && !soa);
+    int base = 0;
+    if (lane == 0 && left) base = atomicAdd(t.info + 4, __popc(left));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit && !soa) left_list[base + __popc(left & lanemask_lt())] = j;
+    if (j < n) mode[j] = soa ? 1 : 0;
 }
 
 // ---- numeric on templates, one warp per column ----------------------------------------------------
@@ -309,7 +423,8 @@ __global__ void k_tpl_apply(int n, ClsTable t, const int *__restrict__ tpl_cnt, 
 constexpr int TPL_PER_WARP = TPL_CAP * 8 + 32 * 16;
 template <bool VALUES, int TPL_BATCH, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-k_num_tpl(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt,
+k_num_tpl(const int *__restrict__ left_list, const int *__restrict__ left_count, const int *__restrict__ cb,
+          const int *__restrict__ tpl_cnt,
           const unsigned char *__restrict__ tpl_pos, const int *__restrict__ tpl_rows,
           const csi *__restrict__ Ap, const double *__restrict__ Ax,
           const csi *__restrict__ Bp, const csi *__restrict__ Bi, const double *__restrict__ Bx,
@@ -333,16 +448,20 @@ k_num_tpl(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt,
         return st;
     };
 
-    int j = blockIdx.x * 8 + wid;
+    // the columns of the list (every one has a template: cb[j] >= 0), strided over the warps
+    const int n = *left_count;
+    int ix = blockIdx.x * 8 + wid;
+    int j = ix < n ? left_list[ix] : 0;
     int c = -1, pb_begin = 0, pb_end = 0;
     int4 st = make_int4(0, 0, 0, 0);
-    if (j < n) {
+    if (ix < n) {
         c = cb[j];
         if (c >= 0) { pb_begin = Bp[j]; pb_end = Bp[j + 1]; if (VALUES) st = fetch(pb_begin + lane, pb_end); }
     }
-    while (j < n) {
+    while (ix < n) {
         // the next column of this warp: its class and first 32 B entries travel while this one is summed
-        const int jn = j + nwarps;
+        const int ixn = ix + nwarps;
+        const int jn = ixn < n ? left_list[ixn] : 0;
         int cn = -1, pbn_begin = 0, pbn_end = 0;
         int4 stn = make_int4(0, 0, 0, 0);
         if (c >= 0) {
@@ -358,7 +477,7 @@ k_num_tpl(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt,
                     __syncwarp();
                     stage[lane] = st;
                     __syncwarp();
-                    if (pb0 == pb_begin && jn < n) {
+                    if (pb0 == pb_begin && ixn < n) {
                         cn = cb[jn];
                         if (cn >= 0) { pbn_begin = Bp[jn]; pbn_end = Bp[jn + 1]; stn = fetch(pbn_begin + lane, pbn_end); }
                     }
@@ -410,7 +529,7 @@ k_num_tpl(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt,
                         }
                     }
                 }
-            } else if (jn < n) {
+            } else if (ixn < n) {
                 cn = cb[jn];
             }
             const int *rows = tpl_rows + (size_t)c * TPL_CAP;
@@ -419,11 +538,147 @@ k_num_tpl(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt,
                 if (VALUES) Cx[out + t] = vals[t];
             }
             __syncwarp();
-        } else if (jn < n) {
+        } else if (ixn < n) {
             cn = cb[jn];
             if (VALUES && cn >= 0) { pbn_begin = Bp[jn]; pbn_end = Bp[jn + 1]; stn = fetch(pbn_begin + lane, pbn_end); }
         }
-        j = jn; c = cn; pb_begin = pbn_begin; pb_end = pbn_end; st = stn;
+        ix = ixn; j = jn; c = cn; pb_begin = pbn_begin; pb_end = pbn_end; st = stn;
+    }
+}
+
+// ---- entry-major copies ------------------------------------------------------------------------------
+// xT[e * n + k] = the e-th stored value of column k (columns shorter than `len` leave their slots
+// unset; they are never read).  One thread per column: the strided reads of consecutive e share
+// sectors through L1, the writes are coalesced.  Built once per handle.
+__global__ void k_soa_build(int n, int len, const csi *__restrict__ Ap, const double *__restrict__ Ax,
+                            double *__restrict__ xT)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int b = Ap[k], l = min(len, Ap[k + 1] - b);
+    for (int e = 0; e < l; e++) xT[(size_t)e * n + k] = Ax[b + e];
+}
+
+__global__ void k_max_col_len(int n, const csi *__restrict__ Ap, int *out)
+{
+    int mx = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) mx = max(mx, Ap[k + 1] - Ap[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
+// ---- numeric on templates, one LANE per column ------------------------------------------------------
+// Columns of one class do the same thing to different data, so 32 of them run in lock step: lane L
+// owns column j = 32 g + L and walks the class's term lists -- for every row t of the column the
+// products b * a that land on it, in the reference's order -- with both operands read from the
+// entry-major copies, where the 32 lanes' operands are 32 consecutive doubles (one coalesced 256-byte
+// request each).  The sum of a row lives in a register; nothing is accumulated in shared memory, no
+// row index is read and the control flow is uniform.  The eight warps of a CTA share the 32 columns
+// and split the rows, so they read the same lines of A and B through L1: the CTA's working set is
+// the ~100 KB of A the 32 columns touch, which is why few CTAs are resident per SM (the grid is sized
+// for it) and shared memory is kept small -- rows are staged 32 at a time and leave as 256-byte runs.
+// Columns whose class has fewer than SOA_MIN_LANES members inside the 32-column block (grid
+// boundaries) are left to k_num_tpl (k_tpl_apply makes that choice and lists them).
+struct SoaTables {
+    int2 terms[SOA_TERMS];
+    unsigned char tend[SOA_TERMS];
+    int wptr[SOA_CHUNKS * SOA_WARPS + 1];
+    int rows[SOA_CNT];
+    int out[32], mcol[32], mlane[32];                       // the member columns of the pass: Cp, column, lane
+};
+constexpr int SOA_SMEM = (int)sizeof(SoaTables) + 2 * 32 * 33 * 8;
+
+__global__ void __launch_bounds__(SOA_THREADS, 4)
+k_num_soa(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt, const unsigned char *__restrict__ mode,
+          const int2 *__restrict__ tpl_terms, const unsigned char *__restrict__ tpl_tend, const int *__restrict__ tpl_wptr,
+          const int *__restrict__ tpl_rows, const double *__restrict__ AxT, const double *__restrict__ BxT,
+          const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
+{
+    constexpr int NW = SOA_WARPS, BATCH = SOA_BATCH;
+    static_assert(BATCH == 8 && SOA_TERMS % 8 == 0, "one 8-byte word of row marks per step");
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    SoaTables &tb = *reinterpret_cast<SoaTables *>(sm_raw);
+    double *sCbuf = reinterpret_cast<double *>(sm_raw + sizeof(SoaTables));    // 2 x [lane][33]: 32 rows of 32 columns
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int cur = -1;                                          // class whose tables are loaded (uniform over the CTA)
+    const int nblocks = (n + 31) >> 5;
+    for (int g = blockIdx.x; g < nblocks; g += gridDim.x) {
+        const int j = g * 32 + lane;
+        int c = (j < n && mode[j]) ? cb[j] : -1;           // k_tpl_apply decided which columns are formed here
+        unsigned todo = __ballot_sync(0xffffffffu, c >= 0);
+        while (todo) {                                     // one pass per class present in the block
+            const int cc = __shfl_sync(0xffffffffu, c, __ffs(todo) - 1);
+            const unsigned members = __ballot_sync(0xffffffffu, c == cc);
+            todo &= ~members;
+            const int nmem = __popc(members);
+            const int cnt = tpl_cnt[cc];
+            __syncthreads();                               // the previous pass has left the tables and sC
+            if (cc != cur) {
+                const int *wp = tpl_wptr + (size_t)cc * (SOA_CHUNKS * SOA_WARPS + 1);
+                const int nterms = wp[SOA_CHUNKS * SOA_WARPS];
+                for (int q = tid; q < nterms; q += SOA_THREADS) {
+                    tb.terms[q] = tpl_terms[(size_t)cc * SOA_TERMS + q];
+                    tb.tend[q] = tpl_tend[(size_t)cc * SOA_TERMS + q];
+                }
+                for (int r = tid; r <= SOA_CHUNKS * SOA_WARPS; r += SOA_THREADS) tb.wptr[r] = wp[r];
+                for (int r = tid; r < cnt; r += SOA_THREADS) tb.rows[r] = tpl_rows[(size_t)cc * TPL_CAP + r];
+                cur = cc;
+            }
+            const bool active = (members >> lane) & 1u;
+            if (w == 0 && active) {                        // the member columns, densely: column and where it starts in C
+                const int rank = __popc(members & lanemask_lt());
+                tb.mcol[rank] = j;
+                tb.out[rank] = Cp[j];
+                tb.mlane[rank] = lane;
+            }
+            __syncthreads();
+            const double *Aj = AxT + j, *Bj = BxT + j;     // this lane's column in the entry-major copies
+            int buf = 0;
+            for (int t0 = 0; t0 < cnt; t0 += 32, buf ^= 1) {
+                double *sC = sCbuf + buf * (32 * 33) + lane * 33;
+                // this warp's share of the chunk: one flat list of terms, eight per step -- sixteen
+                // independent loads in flight, then the sums in list order.  -0.0 is the exact additive
+                // identity: the first product of a row lands as the reference's first-touch assignment
+                // (csparse.py:1986), the rest are added in its order (:1988)
+                const int Q1 = tb.wptr[(t0 >> 5) * NW + w + 1];
+                if (active) {
+                    double acc = -0.0;
+                    for (int q = tb.wptr[(t0 >> 5) * NW + w]; q < Q1; q += BATCH) {
+                        int2 tm[BATCH];
+                        double a[BATCH], b[BATCH];
+#pragma unroll
+                        for (int u = 0; u < BATCH; u += 2) {
+                            const int4 two = *reinterpret_cast<const int4 *>(&tb.terms[q + u]);
+                            tm[u] = make_int2(two.x, two.y);
+                            tm[u + 1] = make_int2(two.z, two.w);
+                        }
+                        const unsigned long long marks = *reinterpret_cast<const unsigned long long *>(&tb.tend[q]);
+#pragma unroll
+                        for (int u = 0; u < BATCH; u++) { b[u] = Bj[tm[u].y]; a[u] = Aj[tm[u].x]; }
+#pragma unroll
+                        for (int u = 0; u < BATCH; u++) {
+                            acc = __dadd_rn(acc, __dmul_rn(b[u], a[u]));
+                            const int e = (int)((marks >> (8 * u)) & 0xffull);
+                            if (e) { sC[e - 1] = acc; acc = -0.0; }          // warp-uniform: the row is complete
+                        }
+                    }
+                }
+                __syncthreads();
+                // every warp writes 32 consecutive rows of one member column: a 256-byte run of Cx.  The
+                // next chunk is summed into the other buffer, so one barrier per chunk is enough.
+                const int t = t0 + lane;
+                if (t < cnt) {
+                    const int rt = tb.rows[t];
+                    const double *src = sCbuf + buf * (32 * 33) + lane;
+                    for (int mi = w; mi < nmem; mi += NW) {
+                        const int o = tb.out[mi] + t;
+                        Cx[o] = src[tb.mlane[mi] * 33];
+                        Ci[o] = tb.mcol[mi] + rt;
+                    }
+                }
+            }
+        }
     }
 }
 

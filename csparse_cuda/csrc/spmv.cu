@@ -20,7 +20,7 @@
 #include <string.h>
 
 struct SpmvPlan {
-    int kind = 0;            // 1 stream (TMA-staged), 2 merge, 3 stream (plain loads)
+    int kind = 0;            // 1 stream (TMA-staged), 2 merge, 3 stream (plain loads), 4 split (long rows / short rows)
     int rows_per_cta = 0;    // stream
     bool long_rows = false;  // stream: which stage-ring shape (TsLong / TsShort)
     int merge_ctas = 0;      // merge
@@ -31,6 +31,15 @@ struct SpmvPlan {
     // host pipeline of csb200_gaxpy: largest column index used by each row chunk (cached)
     int chunk_rows = 0, chunk_count = 0;
     int chunk_maxcol[8] = {0};
+    // split: rows binned by length -- long rows cut into items of <= SPLIT_CHUNK entries (one warp
+    // each), mid rows (eight lanes each), short rows (one thread each); all read the CSR arrays in place
+    int n_items = 0, n_long = 0, n_mid = 0, n_short = 0;
+    int4 *items = nullptr;          // {first entry, end, row, unused}
+    int *long_list = nullptr;       // n_long: the long rows
+    int *long_ptr = nullptr;        // n_long + 1: items of every long row
+    double *partial = nullptr;      // n_items
+    int *mid_list = nullptr;        // n_mid
+    int *short_list = nullptr;      // n_short
 };
 
 namespace csb {
@@ -518,12 +527,182 @@ __global__ void k_max_len(const csi *__restrict__ rowptr, int m, int *out)
     if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
 }
 
+// ---- split plan: power-law rows ----------------------------------------------------------------
+// A row with hundreds of entries needs no shared memory at all: a warp streams it 32 entries at a
+// time (coalesced col / val, x gathered through L1), every lane keeps its own running sums and the
+// warp reduces once at the end.  Rows are therefore binned by length, once per handle, and every bin
+// reads the CSR arrays in place:
+//   long   (>= SPLIT_LONG entries: 80+ % of the nonzeros of the R-MAT matrix) cut into items of at
+//          most SPLIT_CHUNK entries, one warp per item; the items' sums are parked and added to y
+//          per row in item order by a small second kernel (deterministic, like the merge path's
+//          carry fix-up);
+//   mid    (SPLIT_MID .. SPLIT_LONG-1 entries) eight lanes per row, four rows per warp;
+//   short  (1 .. SPLIT_MID-1 entries) one thread per row.
+// Empty rows are in no list: y is untouched there, as in the reference.
+constexpr int SPLIT_LONG = 64;
+constexpr int SPLIT_MID = 8;
+constexpr int SPLIT_CHUNK = 2048;
+
+__global__ void k_split_count(int m, const csi *__restrict__ rowptr, int *__restrict__ nitems, int *__restrict__ islong,
+                              int *__restrict__ ismid, int *__restrict__ isshort)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const int len = rowptr[r + 1] - rowptr[r];
+    const bool lg = len >= SPLIT_LONG;
+    nitems[r] = lg ? (len + SPLIT_CHUNK - 1) / SPLIT_CHUNK : 0;
+    islong[r] = lg ? 1 : 0;
+    ismid[r] = (!lg && len >= SPLIT_MID) ? 1 : 0;
+    isshort[r] = (len > 0 && len < SPLIT_MID) ? 1 : 0;
+}
+
+// iptr / lptr / mptr / sptr: exclusive scans of the four arrays above
+__global__ void k_split_fill(int m, const csi *__restrict__ rowptr, const int *__restrict__ iptr,
+                             const int *__restrict__ lptr, const int *__restrict__ mptr, const int *__restrict__ sptr,
+                             int4 *__restrict__ items, int *__restrict__ long_list, int *__restrict__ long_ptr,
+                             int *__restrict__ mid_list, int *__restrict__ short_list)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const int b = rowptr[r], e = rowptr[r + 1];
+    const int len = e - b;
+    if (len >= SPLIT_LONG) {
+        const int li = lptr[r];
+        long_list[li] = r;
+        long_ptr[li] = iptr[r];
+        int k = iptr[r];
+        // equal items: a row of 2049 entries becomes 1025 + 1024, not 2048 + 1
+        const int n = (len + SPLIT_CHUNK - 1) / SPLIT_CHUNK;
+        for (int c = 0; c < n; c++, k++) {
+            const int ib = b + (int)((long long)len * c / n), ie = b + (int)((long long)len * (c + 1) / n);
+            items[k] = make_int4(ib, ie, r, 0);
+        }
+    } else if (len >= SPLIT_MID) {
+        mid_list[mptr[r]] = r;
+    } else if (len > 0) {
+        short_list[sptr[r]] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_spmv_long(int n_items, const int4 *__restrict__ items, const csi *__restrict__ col, const double *__restrict__ val,
+            const double *__restrict__ x, double *__restrict__ partial)
+{
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * 8;
+    for (int it = blockIdx.x * 8 + (threadIdx.x >> 5); it < n_items; it += nwarps) {
+        const int4 im = items[it];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int p = im.x + lane;
+        for (; p + 96 < im.y; p += 128) {                   // four independent gathers in flight per lane
+            const int c0 = ldg_stream(col + p), c1 = ldg_stream(col + p + 32), c2 = ldg_stream(col + p + 64), c3 = ldg_stream(col + p + 96);
+            const double v0 = ldg_stream(val + p), v1 = ldg_stream(val + p + 32), v2 = ldg_stream(val + p + 64), v3 = ldg_stream(val + p + 96);
+            a0 = __dadd_rn(a0, __dmul_rn(v0, __ldg(x + c0)));
+            a1 = __dadd_rn(a1, __dmul_rn(v1, __ldg(x + c1)));
+            a2 = __dadd_rn(a2, __dmul_rn(v2, __ldg(x + c2)));
+            a3 = __dadd_rn(a3, __dmul_rn(v3, __ldg(x + c3)));
+        }
+        for (; p < im.y; p += 32) a0 = __dadd_rn(a0, __dmul_rn(ldg_stream(val + p), __ldg(x + ldg_stream(col + p))));
+        double s = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (lane == 0) partial[it] = s;
+    }
+}
+
+__global__ void k_long_fix(int n_long, const int *__restrict__ long_rows, const int *__restrict__ long_ptr,
+                           const double *__restrict__ partial, double *__restrict__ y)
+{
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_long) return;
+    double s = 0.0;
+    for (int k = long_ptr[li]; k < long_ptr[li + 1]; k++) s = __dadd_rn(s, partial[k]);
+    const int r = long_rows[li];
+    y[r] = __dadd_rn(y[r], s);
+}
+
+// eight lanes per row
+__global__ void __launch_bounds__(256)
+k_spmv_mid(int n_mid, const int *__restrict__ mid_list, const csi *__restrict__ rowptr, const csi *__restrict__ col,
+           const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int gi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+    const int sub = threadIdx.x & 7;
+    double s = 0.0;
+    int r = -1;
+    if (gi < n_mid) {
+        r = mid_list[gi];
+        const int e = rowptr[r + 1];
+        for (int p = rowptr[r] + sub; p < e; p += 8) s = __dadd_rn(s, __dmul_rn(val[p], __ldg(x + col[p])));
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (r >= 0 && sub == 0) y[r] = __dadd_rn(y[r], s);
+}
+
+// one thread per row, entries in storage order
+__global__ void __launch_bounds__(256)
+k_spmv_short(int n_short, const int *__restrict__ short_list, const csi *__restrict__ rowptr, const csi *__restrict__ col,
+             const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_short) return;
+    const int r = short_list[gi];
+    const int e = rowptr[r + 1];
+    double s = y[r];
+    for (int p = rowptr[r]; p < e; p++) s = __dadd_rn(s, __dmul_rn(val[p], __ldg(x + col[p])));   // the reference's order (csparse.py:1210-1212)
+    y[r] = s;
+}
+
+static int build_split(csb200_mat *AT, SpmvPlan *pl)
+{
+    const int m = AT->n;
+    cudaStream_t s = stream();
+    DevBuf<int> nitems, islong, ismid, isshort, iptr, lptr, mptr, sptr;
+    DevBuf<long long> tot;
+    const size_t cap = (size_t)m + 1;
+    CSB_TRY(nitems.alloc(cap)); CSB_TRY(islong.alloc(cap)); CSB_TRY(ismid.alloc(cap)); CSB_TRY(isshort.alloc(cap));
+    CSB_TRY(iptr.alloc(cap)); CSB_TRY(lptr.alloc(cap)); CSB_TRY(mptr.alloc(cap)); CSB_TRY(sptr.alloc(cap));
+    CSB_TRY(tot.alloc(4));
+    k_split_count<<<ceil_div(m, 256), 256, 0, s>>>(m, AT->p, nitems.ptr, islong.ptr, ismid.ptr, isshort.ptr);
+    CSB_LAUNCHED();
+    CSB_TRY(launch_excl_scan(iptr.ptr, nitems.ptr, m, tot.ptr, nullptr));
+    CSB_TRY(launch_excl_scan(lptr.ptr, islong.ptr, m, tot.ptr + 1, nullptr));
+    CSB_TRY(launch_excl_scan(mptr.ptr, ismid.ptr, m, tot.ptr + 2, nullptr));
+    CSB_TRY(launch_excl_scan(sptr.ptr, isshort.ptr, m, tot.ptr + 3, nullptr));
+    long long h[4] = {0, 0, 0, 0};
+    CSB_CUDA(cudaMemcpyAsync(h, tot.ptr, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CSB_CUDA(cudaStreamSynchronize(s));
+    pl->n_items = (int)h[0];
+    pl->n_long = (int)h[1];
+    pl->n_mid = (int)h[2];
+    pl->n_short = (int)h[3];
+    CSB_TRY(dev_alloc(&pl->items, (size_t)pl->n_items + 1));
+    CSB_TRY(dev_alloc(&pl->long_list, (size_t)pl->n_long + 1));
+    CSB_TRY(dev_alloc(&pl->long_ptr, (size_t)pl->n_long + 1));
+    CSB_TRY(dev_alloc(&pl->partial, (size_t)pl->n_items + 1));
+    CSB_TRY(dev_alloc(&pl->mid_list, (size_t)pl->n_mid + 1));
+    CSB_TRY(dev_alloc(&pl->short_list, (size_t)pl->n_short + 1));
+    k_split_fill<<<ceil_div(m, 256), 256, 0, s>>>(m, AT->p, iptr.ptr, lptr.ptr, mptr.ptr, sptr.ptr, pl->items,
+                                                  pl->long_list, pl->long_ptr, pl->mid_list, pl->short_list);
+    CSB_LAUNCHED();
+    CSB_CUDA(cudaMemcpyAsync(pl->long_ptr + pl->n_long, &pl->n_items, sizeof(int), cudaMemcpyHostToDevice, s));
+    CSB_CUDA(cudaStreamSynchronize(s));      // n_items is a host variable of the plan: copied before it can change
+    return CSB200_OK;
+}
+
 void spmv_plan_free(SpmvPlan *pl)
 {
     if (!pl) return;
     dev_free(pl->merge_part);
     dev_free(pl->carry_row);
     dev_free(pl->carry_val);
+    dev_free(pl->items);
+    dev_free(pl->long_list);
+    dev_free(pl->long_ptr);
+    dev_free(pl->partial);
+    dev_free(pl->mid_list);
+    dev_free(pl->short_list);
     delete pl;
 }
 
@@ -549,7 +728,7 @@ int spmv_build_plan(csb200_mat *AT)
     pl->max_len = h_max;
     const double avg = m > 0 ? (double)nnz / m : 0.0;
     int kind = (h_max <= 64 || h_max <= 4.0 * avg + 16.0) ? 1 : 2;
-    if ((long long)m + nnz >= 0x7fffffffLL - MP_TILE) kind = 1;     // merge coordinates are int32
+    if (kind == 2 && (long long)m + nnz >= 0x7fffffffLL - MP_TILE) kind = 1;     // merge coordinates are int32
     if (AT->forced_plan) kind = AT->forced_plan;
     pl->kind = kind;
     if (kind == 1) {
@@ -563,6 +742,9 @@ int spmv_build_plan(csb200_mat *AT)
     } else if (kind == 3) {
         int R = (int)(0.8 * SP_TILE / (avg > 1.0 ? avg : 1.0));
         pl->rows_per_cta = R < 1 ? 1 : (R > SP_THREADS ? SP_THREADS : R);
+    } else if (kind == 4) {
+        int st = build_split(AT, pl);
+        if (st != CSB200_OK) { spmv_plan_free(pl); return st; }
     } else {
         const long long total = (long long)m + nnz;
         pl->merge_ctas = (int)((total + MP_TILE - 1) / MP_TILE);
@@ -596,6 +778,22 @@ int spmv_run(csb200_mat *AT, const double *d_x, double *d_y)
         const int R = pl->rows_per_cta;
         k_spmv_stream<<<ceil_div(m, R), SP_THREADS, 0, stream()>>>(m, AT->p, AT->i, AT->x, d_x, d_y, R);
         CSB_LAUNCHED();
+    } else if (pl->kind == 4) {
+        if (pl->n_items > 0) {
+            const int grid = min(ceil_div(pl->n_items, 8), sm_count() * 8);
+            k_spmv_long<<<grid, 256, 0, stream()>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
+            CSB_LAUNCHED();
+            k_long_fix<<<ceil_div(pl->n_long, 256), 256, 0, stream()>>>(pl->n_long, pl->long_list, pl->long_ptr, pl->partial, d_y);
+            CSB_LAUNCHED();
+        }
+        if (pl->n_mid > 0) {
+            k_spmv_mid<<<ceil_div((long long)pl->n_mid * 8, 256), 256, 0, stream()>>>(pl->n_mid, pl->mid_list, AT->p, AT->i, AT->x, d_x, d_y);
+            CSB_LAUNCHED();
+        }
+        if (pl->n_short > 0) {
+            k_spmv_short<<<ceil_div(pl->n_short, 256), 256, 0, stream()>>>(pl->n_short, pl->short_list, AT->p, AT->i, AT->x, d_x, d_y);
+            CSB_LAUNCHED();
+        }
     } else {
         k_spmv_merge<<<pl->merge_ctas, MP_THREADS, 0, stream()>>>(m, (int)AT->nnz, AT->p, AT->i, AT->x, d_x, d_y,
                                                                    pl->merge_part, pl->carry_row, pl->carry_val);
@@ -701,6 +899,28 @@ static HaloArgs halo_args(csb200_halo *h, int top_blocks, int bot_blocks)
     a.bot_blocks = bot_blocks;
     return a;
 }
+
+namespace csb {
+// the stand-alone halo protocol for the host-buffer pipeline of csb200_gaxpy_halo (api.cu): pull the
+// neighbours' lines into the window now / wait until the neighbours have pulled mine
+int halo_pull_launch(csb200_halo *h, cudaStream_t s)
+{
+    h->epoch++;
+    const HaloArgs a = halo_args(h, 0, 0);
+    k_halo_pull<<<1, 512, 0, s>>>(a);
+    CSB_LAUNCHED();
+    return CSB200_OK;
+}
+int halo_acks_launch(csb200_halo *h, cudaStream_t s)
+{
+    const HaloArgs a = halo_args(h, 0, 0);
+    k_halo_acks<<<1, 1, 0, s>>>(a);
+    CSB_LAUNCHED();
+    return CSB200_OK;
+}
+double *halo_window_ptr(csb200_halo *h) { return h->window; }
+long long halo_window_count(csb200_halo *h) { return h->count; }
+}  // namespace csb
 
 extern "C" {
 

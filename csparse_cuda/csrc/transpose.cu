@@ -1061,19 +1061,20 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     if (has_x && (st = ival.alloc((size_t)nnz + 8)) != CSB200_OK) return fail(st);
     k_tile_cols<<<ceil_div(ntiles + 1, 256), 256, 0, s>>>(A->p, n, nnz, ntiles, tile_col.ptr);
     TR_LAUNCHED();
-    // Slabs: a banded matrix completes its buckets in order -- once the entries up to some tile are
-    // partitioned, no later tile feeds the buckets below the smallest bucket those later tiles
-    // touch.  The partition is therefore cut into slabs of a few million entries, and after each
-    // slab the buckets it completed are sorted at once, while their share of the intermediate is
-    // still in the 126 MB L2: the second hop then reads L2 instead of HBM.  A matrix whose buckets
-    // stay open for long (more than SLAB_LAG_BYTES of intermediate) takes one slab, as before.
+    // Slabs (opt-in, csb200_transpose_force_path(3)): a banded matrix completes its buckets in order
+    // -- once the entries up to some tile are partitioned, no later tile feeds the buckets below the
+    // smallest bucket those later tiles touch.  The partition can therefore be cut into slabs of a
+    // few million entries, the buckets a slab completes being sorted at once while their share of
+    // the intermediate is still in the 126 MB L2.  MEASURED (B200, profiles/r2_notes.md): the ~40
+    // short launches cost more in ramp-up and tail than the second hop saves -- lap2d 4096^2 1.77 ms
+    // against 1.34 ms for two whole passes, st27 128^3 1.88 against 1.50 -- so the default is one slab.
     struct Slab { int tile_end, bucket_end; };
     std::vector<Slab> slabs;
     {
         constexpr long long SLAB_LAG_BYTES = 40LL << 20;
         const long long slab_entries = std::min<long long>(4LL << 20, std::max<long long>(1LL << 20, nnz / 16));
         const int step = (int)(slab_entries / TR_TILE);
-        bool ok = tls().force_transpose != 3 && h_ct[0] == 0 && nht >= 4 * step;
+        bool ok = tls().force_transpose == 3 && h_ct[0] == 0 && nht >= 4 * step;
         if (ok) {
             std::vector<int> sufmin((size_t)nht + 1);
             sufmin[nht] = nbuckets;

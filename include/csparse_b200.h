@@ -91,8 +91,8 @@ CSB200_API int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
  * with sorted duplicate-free columns and a symmetric pattern -- verified by the kernel itself --,
  * else the two-level bucket sort, or the stable radix sort when power-law rows overflow the
  * buckets), 1 = always the radix sort, 2 = automatic without the mirror path, 3 = like 2 with the
- * bucket sort's partition and sort phases as two whole passes instead of L2-sized slabs; for tests
- * and benchmarks */
+ * bucket sort's partition and sort phases interleaved in L2-sized slabs (measured slower than two
+ * whole passes); for tests and benchmarks */
 CSB200_API int csb200_transpose_force_path(int path);
 /* the path the calling thread's last transpose took: 1 mirror, 2 bucket sort, 3 radix sort,
  * 0 trivial (empty matrix) */
@@ -141,6 +141,12 @@ CSB200_API int csb200_halo_connect_local(csb200_halo *h, int side, csb200_halo *
 /* y[0..AT.n) += AT' * window; top_rows / bot_rows = rows at the two ends of the block that read
  * halo entries (0, 0 with no neighbours).  Every rank must call it the same number of times. */
 CSB200_API int csb200_gaxpy_halo_dev(csb200_mat *AT, csb200_halo *h, double *d_y, csi top_rows, csi bot_rows);
+/* the same step on HOST vectors: x_own (own_len doubles) is this rank's slice of x, stored at offset
+ * own_off of the window; y (AT.n doubles) is read and written; edge_lo / edge_hi = how many doubles at
+ * the two ends of the slice the neighbours read (they travel first).  Chunked duplex copies as in
+ * csb200_gaxpy.  Returns when y is back in host memory and the neighbours have pulled their lines. */
+CSB200_API int csb200_gaxpy_halo(csb200_mat *AT, csb200_halo *h, const double *x_own, int64_t own_off, int64_t own_len,
+                                 int64_t edge_lo, int64_t edge_hi, double *y);
 CSB200_API int csb200_halo_status(csb200_halo *h, int *timed_out);         /* 1: a neighbour never showed up (2 s) */
 CSB200_API int csb200_halo_free(csb200_halo *h);
 
@@ -159,7 +165,8 @@ CSB200_API int csb200_multiply_ordered(const csb200_mat *A, const csb200_mat *B,
  * (then p, i, x are bit-identical to cs_multiply on canonical inputs).  The set of rows and every
  * value are the same either way.  2 / 3 = automatic with the first / second version of the
  * blocked numeric kernel, for A/B measurements and tests.  4 = automatic without the pattern-class
- * templates, 5 = templates tried at any size (automatic: from 16384 columns).  Columns formed from a
+ * templates, 5 = templates tried at any size (automatic: from 16384 columns), 6 = like 5 with one warp
+ * per column only (without the kernel that runs 32 columns of a class in lock step).  Columns formed from a
  * class template (matrices of translation-invariant operators: one symbolic pass per class of
  * columns instead of one per column) are always in the reference's discovery order. */
 CSB200_API int csb200_multiply_force_path(int path);

@@ -42,7 +42,7 @@ def test_c3_lap2d_4096_transpose_and_gaxpy():
     xv, y0 = synth.vectors(m, n)
     yref = y0.copy()
     orc.cs_gaxpy(A, xv, yref)
-    for plan in ("stream", "merge"):
+    for plan in ("stream", "merge", "split"):
         dA.force_gaxpy_plan(plan)
         y = y0.copy()
         assert cc.cs_gaxpy(dA, xv, y)
@@ -143,10 +143,14 @@ def test_c5_rmat20_transpose_and_gaxpy():
     orc.cs_gaxpy(A, xv, yref)
     y = y0.copy()
     assert cc.cs_gaxpy(dA, xv, y)
-    assert dA.gaxpy_plan() == "merge"
+    assert dA.gaxpy_plan() == "split"
     assert normwise(y, yref) <= 1e-12
     untouched = np.diff(R.p) == 0                 # empty rows keep y bit for bit
     assert np.array_equal(bits(y[untouched]), bits(y0[untouched]))
+    dA.force_gaxpy_plan("merge")
+    y = y0.copy()
+    assert cc.cs_gaxpy(dA, xv, y) and dA.gaxpy_plan() == "merge"
+    assert normwise(y, yref) <= 1e-12
 
 
 def test_c5_rmat24_transpose_and_gaxpy():
@@ -177,7 +181,7 @@ def test_c5_rmat24_transpose_and_gaxpy():
     orc.cs_gaxpy(A, xv, yref)
     y = y0.copy()
     assert cc.cs_gaxpy(dA, xv, y)
-    assert dA.gaxpy_plan() == "merge"
+    assert dA.gaxpy_plan() == "split"
     assert normwise(y, yref) <= 1e-12
     untouched = np.diff(R.p) == 0                 # empty rows keep y bit for bit
     assert np.array_equal(bits(y[untouched]), bits(y0[untouched]))

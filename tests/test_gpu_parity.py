@@ -112,6 +112,24 @@ def test_transpose_synthetic(gen):
     assert np.array_equal(p2, p) and np.array_equal(i2, i) and np.array_equal(bits(x2), bits(x))
 
 
+def test_transpose_slab_schedule():
+    """The opt-in slab schedule of the bucket sort (partition and sort interleaved per L2-sized slab,
+    csb200_transpose_force_path(3)) needs >= 4 M entries to cut anything: same bits as the oracle."""
+    m, n, p, i, x = synth.lap2d(1024)
+    x = np.random.default_rng(8).standard_normal(len(i))
+    R = orc.cs_transpose(orc.csc(m, n, p, i, x), True)
+    dA = cc.from_arrays(m, n, p, i, x)
+    for path in ("bucket_slab", "bucket"):
+        cc.force_transpose_path(path)
+        try:
+            cp, ci, cx = cc.cs_transpose(dA, True).arrays()
+            assert cc.last_transpose_path() == "bucket"
+        finally:
+            cc.force_transpose_path(None)
+        assert np.array_equal(cp, R.p) and np.array_equal(ci, R.i[:len(i)]), path
+        assert np.array_equal(bits(cx), bits(R.x[:len(i)])), path
+
+
 def test_transpose_unsorted_duplicates_long_rows():
     """Unsorted columns, duplicate (i,j) entries and rows far longer than a warp/CTA tile."""
     rng = np.random.default_rng(7)
@@ -229,7 +247,7 @@ def test_gaxpy_fixtures(name):
         ref = g.z[key]
         assert normwise(y, ref) <= RTOL
         # both plans, on a device-resident handle
-        for plan in ("stream", "merge", "stream_ld"):
+        for plan in ("stream", "merge", "stream_ld", "split"):
             dA = cc.from_arrays(M.m, M.n, M.p, M.i, M.x)
             dA.force_gaxpy_plan(plan)
             yy = y0.copy()
@@ -239,12 +257,12 @@ def test_gaxpy_fixtures(name):
             # sequential in-row order, no FMA: bit-exact -- except where a block of rows
             # overflows the shared-memory stage and falls back to warp-per-row (mbeacxc's
             # 250..484-entry rows, the power-law rows of rmat_9)
-            if plan != "merge" and name not in ("mbeacxc", "rmat_9"):
+            if plan not in ("merge", "split") and name not in ("mbeacxc", "rmat_9"):
                 assert np.array_equal(bits(yy), bits(ref)), (name, "stream plan not bit-exact")
 
 
 @pytest.mark.parametrize("gen,plan", [(lambda: synth.lap2d(300), "stream"), (lambda: synth.st27(20), "stream"),
-                                      (lambda: synth.rmat(16, 16), "merge"), (lambda: synth.rmat(13, 4), None)])
+                                      (lambda: synth.rmat(16, 16), None), (lambda: synth.rmat(13, 4), None)])
 def test_gaxpy_synthetic(gen, plan):
     m, n, p, i, x = gen()
     A = orc.csc(m, n, p, i, x)
@@ -254,7 +272,7 @@ def test_gaxpy_synthetic(gen, plan):
     dA = cc.from_arrays(m, n, p, i, x)
     if plan is not None:
         assert dA.gaxpy_plan() == plan       # the automatic choice
-    for force in ("stream", "merge", "stream_ld"):
+    for force in ("stream", "merge", "stream_ld", "split"):
         dA.force_gaxpy_plan(force)
         y = y0.copy()
         assert cc.cs_gaxpy(dA, xv, y)

@@ -17,10 +17,12 @@ from tests.test_gpu_parity import as_omat, assert_multiply_parity, assert_same_m
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def templates():
-    cc.force_multiply_path("templates")
-    yield
+@pytest.fixture(params=["templates", "templates_percol"])
+def templates(request):
+    """both numeric kernels of the template path: 32 columns of a class in lock step on the
+    entry-major copies (k_num_soa, the rest by k_num_tpl), and one warp per column only"""
+    cc.force_multiply_path(request.param)
+    yield request.param
     cc.force_multiply_path(None)
 
 

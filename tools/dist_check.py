@@ -67,6 +67,17 @@ for fused in (False, True):
         if not same:
             say(f"halo fused={fused} step {step}: max err {np.abs(got - y_ref[r0:r1]).max():.3e}")
     if fused:
+        # the same step on pinned HOST slices (csb200_gaxpy_halo: chunked duplex copies around the halo pull)
+        for step in range(2):
+            xg = rng.standard_normal(n)
+            hx = torch.from_numpy(xg[r0:r1].copy()).pin_memory()
+            hy = torch.from_numpy(y_ref[r0:r1].copy()).pin_memory()
+            sh.step_host(hx, hy)
+            orc.cs_gaxpy(A, xg, y_ref)
+            same = np.array_equal(hy.numpy().view(np.int64), y_ref[r0:r1].view(np.int64))
+            ok &= same
+            if not same:
+                say(f"halo host step {step}: max err {np.abs(hy.numpy() - y_ref[r0:r1]).max():.3e}")
         ok &= not sh.halo.timed_out()
     dist.barrier()
     if fused:

@@ -1,0 +1,7 @@
+#!/bin/bash
+timeout 300 python -m pytest tests/test_gpu_templates.py tests/test_gpu_parity.py -x -q --timeout 120 -p no:cacheprovider -k "templates or multiply or slab" 2>&1 | tail -12
+M='python tools/quick_perf.py --only multiply --lap 0 --rmat 0 --st 128 --mul-paths auto,templates_percol'
+timeout 200 $M 2>&1 | grep cs_multiply > gpurun_out/r2g_mm.log; cat gpurun_out/r2g_mm.log
+M1='python tools/quick_perf.py --only multiply --lap 0 --rmat 0 --st 128 --once --mul-paths auto'
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2g_mm_launches.csv $M1 > gpurun_out/r2g_ncu_mm.log 2>&1; echo rc_ncu=$?
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_num_soa -s 1 -c 1 -o gpurun_out/r2g_num_soa -f $M1 > gpurun_out/r2g_ncu_full.log 2>&1; echo rc_full=$?

@@ -17,6 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=24)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--no-gaxpy", action="store_true")
+ap.add_argument("--no-transpose", action="store_true")
+ap.add_argument("--plans", default="auto", help="comma list of auto,merge,split,stream")
 a = ap.parse_args()
 torch.cuda.init()
 cc.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -46,15 +48,18 @@ def tr():
     c.free()
 
 
-med, best = timed(tr, 2, a.iters)
-b = synth.transpose_bytes(m, n, nnz)
-print(json.dumps({"what": f"rmat {a.scale} cs_transpose", "nnz": nnz, "ms_median": med, "ms_best": best,
-                  "GBs": b / med / 1e6}), flush=True)
+if not a.no_transpose:
+    med, best = timed(tr, 2, a.iters)
+    b = synth.transpose_bytes(m, n, nnz)
+    print(json.dumps({"what": f"rmat {a.scale} cs_transpose", "nnz": nnz, "ms_median": med, "ms_best": best,
+                      "GBs": b / med / 1e6}), flush=True)
 if not a.no_gaxpy:
-    dA.prepare_gaxpy()
     xv = torch.randn(n, dtype=torch.float64, device="cuda")
     yv = torch.randn(m, dtype=torch.float64, device="cuda")
-    med, best = timed(lambda: dA.gaxpy_dev(xv.data_ptr(), yv.data_ptr()), 3, 4 * a.iters)
-    b = synth.gaxpy_bytes(m, n, nnz)
-    print(json.dumps({"what": f"rmat {a.scale} cs_gaxpy[{dA.gaxpy_plan()}]", "ms_median": med, "ms_best": best,
-                      "GBs": b / med / 1e6}), flush=True)
+    for plan in a.plans.split(","):
+        dA.force_gaxpy_plan(None if plan == "auto" else plan)
+        dA.prepare_gaxpy()
+        med, best = timed(lambda: dA.gaxpy_dev(xv.data_ptr(), yv.data_ptr()), 3, 4 * a.iters)
+        b = synth.gaxpy_bytes(m, n, nnz)
+        print(json.dumps({"what": f"rmat {a.scale} cs_gaxpy[{dA.gaxpy_plan()}]", "ms_median": med, "ms_best": best,
+                          "GBs": b / med / 1e6, "frac_of_measured_peak": b / med / 1e6 / 6456.5}), flush=True)
