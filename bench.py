@@ -549,7 +549,7 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
         # N > 1, host slices of x and y per rank (pinned, allocated after binding the process to the
         # CPUs next to its GPU).  Fused halo: csb200_gaxpy_halo -- the ends of x first, the neighbours'
         # lines pulled over NVLink, y in row chunks with duplex copies, as csb200_gaxpy does at N = 1.
-        node = bind_numa(local)
+        node = bind_numa(torch.cuda.current_device())
         hx_own, hy_own = x_own.cpu().pin_memory(), y_own.cpu().pin_memory()
         if sh.fused:
             e2e_step = lambda: sh.step_host(hx_own, hy_own)
@@ -695,7 +695,7 @@ def bench_gaxpy_rmat_dist(a, torch, dist, cc, synth, csd, world, rank, k, peak, 
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cs_gaxpy, R-MAT scale {k} ef 16 (n={n}, nnz={nnz}), row blocks balanced by nonzeros "
                                    f"({r1 - r0} rows / {nnz_local} nnz on rank 0), x all-gathered every step",
-                       "kernel": "k_spmv_merge / k_spmv_tma by row statistics of the block",
+                       "kernel": "k_spmv_long + k_spmv_mid + k_spmv_short (rows binned by length) / k_spmv_tma, by row statistics of the block",
                        "exchange": "all-gather", "exchange_bytes_per_rank_step": 8 * (n - xs),
                        "l2": "inputs exceed L2"},
             "clocks": clocks, "gpu_launches": int(launches),
@@ -875,7 +875,7 @@ def extras(a, torch, cc, synth, peak):
         yv = torch.randn(m, dtype=torch.float64, device="cuda")
         ms = timed(lambda: dA.gaxpy_dev(xv.data_ptr(), yv.data_ptr()), 3, 20)
         b = synth.gaxpy_bytes(m, n, nnz)
-        ex["cs_gaxpy rmat 2^24 (merge path)"] = {"ms": ms, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak,
+        ex[f"cs_gaxpy rmat 2^24 ({dA.gaxpy_plan()} plan)"] = {"ms": ms, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak,
                                                  "nnz": nnz, "GFLOP/s": 2 * nnz / ms / 1e6}
         dA.free()
         # the rows either side of the hot path, lap2d 4096^2, device-resident

@@ -1014,14 +1014,12 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             MM_LAUNCHED();
             k_cls_compact<<<1, 1024, 0, s>>>(tb);
             MM_LAUNCHED();
-            k_cls_verify_b<<<wgrid, 256, 0, s>>>(n, B->p, B->i, A->cls, tb, cb.ptr);
-            MM_LAUNCHED();
             k_tpl_build<<<CLS_MAX, 32, 0, s>>>(tb, A->p, A->i, B->p, B->i, ub.ptr, tpl_cnt.ptr, tpl_pos.ptr, tpl_rows.ptr,
                                                A->n, n, soa ? A->soa_len : 0, soa ? B->soa_len : 0,
                                                soa ? tpl_soa.ptr : nullptr, tpl_terms.ptr, tpl_tend.ptr, tpl_wptr.ptr);
             MM_LAUNCHED();
-            k_tpl_apply<<<ceil_div(n, 256), 256, 0, s>>>(n, tb, tpl_cnt.ptr, cb.ptr, cnt.ptr, ub.ptr, soa ? tpl_soa.ptr : nullptr,
-                                                         tpl_mode.ptr, left_list.ptr);
+            k_cls_verify_apply<<<wgrid, 256, 0, s>>>(n, B->p, B->i, A->cls, tb, tpl_cnt.ptr, cb.ptr, cnt.ptr, ub.ptr,
+                                                     soa ? tpl_soa.ptr : nullptr, tpl_mode.ptr, left_list.ptr);
             MM_LAUNCHED();
             MM_CUDA(cudaMemcpyAsync(h_tpl, tb.info, sizeof(h_tpl), cudaMemcpyDeviceToHost, s));
         }

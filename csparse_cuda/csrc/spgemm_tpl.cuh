@@ -232,28 +232,6 @@ k_cls_hash_b(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi, cons
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(flops, (unsigned long long)s);
 }
 
-__global__ void __launch_bounds__(256)
-k_cls_verify_b(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi, const int *__restrict__ ca,
-               ClsTable t, int *__restrict__ cb)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n || t.info[1]) return;
-    const int slot = cb[j];
-    bool ok = slot >= 0;
-    if (ok) {
-        const int r = t.rep[slot];
-        if (r != j) {
-            const int b = Bp[j], len = Bp[j + 1] - b, br = Bp[r];
-            ok = (Bp[r + 1] - br) == len;
-            for (int e = 0; ok && e < len; e++) {
-                const int k = Bi[b + e], kr = Bi[br + e];
-                ok = k - j == kr - r && ca[k] == ca[kr];
-            }
-        }
-    }
-    cb[j] = ok ? t.dense[slot] : -1;
-}
-
 // ---- the template of a class: cs_scatter on its representative column, one warp ------------------
 // A's columns are canonical (distinct rows per column), so the rows of a 32-entry step are distinct.
 // For k_num_soa the same trace is also stored inverted: for every row t of the column the products
@@ -331,30 +309,40 @@ k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, 
     __syncwarp();
     const int nchunks = (cnt + 31) >> 5;
     int *wptr = tpl_wptr + (size_t)c * (SOA_CHUNKS * SOA_WARPS + 1);
-    if (lane == 0) {
-        int run = 0;
-        for (int ch = 0; ch < nchunks; ch++) {
-            const int t0 = ch * 32, nrow = min(32, cnt - t0);
-            int load[SOA_WARPS], owner[32];
-            for (int w = 0; w < SOA_WARPS; w++) load[w] = 0;
-            unsigned taken = 0;
-            for (int rank = 0; rank < nrow; rank++) {            // longest remaining row -> least loaded warp
-                int best = -1, blen = -1;
-                for (int r = 0; r < nrow; r++)
-                    if (!((taken >> r) & 1u) && rlen[t0 + r] > blen) { best = r; blen = rlen[t0 + r]; }
-                taken |= 1u << best;
-                int wmin = 0;
-                for (int w = 1; w < SOA_WARPS; w++) if (load[w] < load[wmin]) wmin = w;
-                owner[best] = wmin;
-                load[wmin] += blen;
-            }
-            for (int w = 0; w < SOA_WARPS; w++) {
-                wptr[ch * SOA_WARPS + w] = run;
-                for (int r = 0; r < nrow; r++) if (owner[r] == w) { rstart[t0 + r] = run; run += rlen[t0 + r]; }
-                run = (run + SOA_BATCH - 1) / SOA_BATCH * SOA_BATCH;      // whole steps only
-            }
+    __shared__ unsigned char owner[SOA_CNT];
+    __shared__ int wstart[SOA_CHUNKS * SOA_WARPS + 1];
+    if (lane < nchunks) {                            // one lane per chunk: longest remaining row -> least loaded warp
+        const int t0 = lane * 32, nrow = min(32, cnt - t0);
+        int load[SOA_WARPS];
+        for (int w = 0; w < SOA_WARPS; w++) load[w] = 0;
+        unsigned taken = 0;
+        for (int rank = 0; rank < nrow; rank++) {
+            int best = -1, blen = -1;
+            for (int r = 0; r < nrow; r++)
+                if (!((taken >> r) & 1u) && rlen[t0 + r] > blen) { best = r; blen = rlen[t0 + r]; }
+            taken |= 1u << best;
+            int wmin = 0;
+            for (int w = 1; w < SOA_WARPS; w++) if (load[w] < load[wmin]) wmin = w;
+            owner[t0 + best] = (unsigned char)wmin;
+            load[wmin] += blen;
         }
-        for (int k = nchunks * SOA_WARPS; k <= SOA_CHUNKS * SOA_WARPS; k++) wptr[k] = run;
+        for (int w = 0; w < SOA_WARPS; w++)
+            wstart[lane * SOA_WARPS + w] = (load[w] + SOA_BATCH - 1) / SOA_BATCH * SOA_BATCH;   // whole steps only
+    }
+    __syncwarp();
+    if (lane == 0) {                                 // where every (chunk, warp) list starts
+        int run = 0;
+        for (int k = 0; k < nchunks * SOA_WARPS; k++) { const int v = wstart[k]; wstart[k] = run; run += v; }
+        for (int k = nchunks * SOA_WARPS; k <= SOA_CHUNKS * SOA_WARPS; k++) wstart[k] = run;
+    }
+    __syncwarp();
+    for (int k = lane; k <= SOA_CHUNKS * SOA_WARPS; k += 32) wptr[k] = wstart[k];
+    if (lane < nchunks) {
+        const int t0 = lane * 32, nrow = min(32, cnt - t0);
+        for (int w = 0; w < SOA_WARPS; w++) {
+            int run = wstart[lane * SOA_WARPS + w];
+            for (int r = 0; r < nrow; r++) if (owner[t0 + r] == w) { rstart[t0 + r] = run; run += rlen[t0 + r]; }
+        }
     }
     __syncwarp();
     for (int r = lane; r < cnt; r += 32) tcount[r] = rstart[r];      // from here on: the fill cursor of row r
@@ -381,24 +369,44 @@ k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, 
     if (lane == 0) tpl_soa[c] = 1;
 }
 
-// columns of a class with a template: cnt[j] is known, the general symbolic phase skips them (ub 0).
-// The warp (32 consecutive columns = one block of k_num_soa) also decides who forms them: a class
-// with at least SOA_MIN_LANES columns in the block and the tables for it -> k_num_soa (mode 1); the
-// rest (grid boundaries, long columns) go to the list k_num_tpl walks, one warp per column.
-__global__ void k_tpl_apply(int n, ClsTable t, const int *__restrict__ tpl_cnt, int *__restrict__ cb,
-                            int *__restrict__ cnt, int *__restrict__ ub, const unsigned char *__restrict__ tpl_soa,
-                            unsigned char *__restrict__ mode, int *__restrict__ left_list)
+// ---- verification and hand-out, one thread per column ----------------------------------------------
+// Entry-by-entry comparison of the column with its class representative (a hash collision only sends
+// the column to the general kernels).  Columns of a class with a template: cnt[j] is known and the
+// general symbolic phase skips them (ub 0).  The warp (32 consecutive columns = one block of
+// k_num_soa) also decides who forms them: a class with at least SOA_MIN_LANES columns in the block and
+// the tables for it -> k_num_soa (mode 1); the rest (grid boundaries, long columns) go to the list
+// k_num_tpl walks, one warp per column.  cb[j] <- dense class id, or -1.
+__global__ void __launch_bounds__(256)
+k_cls_verify_apply(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi, const int *__restrict__ ca,
+                   ClsTable t, const int *__restrict__ tpl_cnt, int *__restrict__ cb, int *__restrict__ cnt,
+                   int *__restrict__ ub, const unsigned char *__restrict__ tpl_soa, unsigned char *__restrict__ mode,
+                   int *__restrict__ left_list)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool live = !t.info[1];
-    bool hit = false;
     int c = -1;
+    if (j < n && !t.info[1]) {                       // the flag is final by now: a cached load
+        const int slot = cb[j];
+        bool ok = slot >= 0;
+        if (ok) {
+            const int r = t.rep[slot];
+            if (r != j) {
+                const int b = Bp[j], len = Bp[j + 1] - b, br = Bp[r];
+                ok = (Bp[r + 1] - br) == len;
+                for (int e = 0; ok && e < len; e++) {
+                    const int k = Bi[b + e], kr = Bi[br + e];
+                    ok = k - j == kr - r && ca[k] == ca[kr];
+                }
+            }
+            if (ok) c = t.dense[slot];
+        }
+    }
+    const int tc = c >= 0 ? tpl_cnt[c] : -1;
+    const bool hit = tc >= 0;
+    if (!hit) c = -1;
     if (j < n) {
-        c = live ? cb[j] : -1;
-        const int tc = c >= 0 ? tpl_cnt[c] : -1;
-        hit = tc >= 0;
-        if (hit) { cnt[j] = tc; ub[j] = 0; } else { cb[j] = -1; c = -1; }
+        cb[j] = c;
+        if (hit) { cnt[j] = tc; ub[j] = 0; }
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (lane == 0 && m) atomicAdd(t.info + 3, __popc(m));

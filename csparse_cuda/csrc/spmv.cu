@@ -18,6 +18,7 @@
 //                  the unfinished row fixed up by k_merge_fixup (deterministic).
 #include "common.cuh"
 #include <string.h>
+#include <type_traits>
 
 struct SpmvPlan {
     int kind = 0;            // 1 stream (TMA-staged), 2 merge, 3 stream (plain loads), 4 split (long rows / short rows)
@@ -234,7 +235,19 @@ __device__ __forceinline__ void halo_pull(const HaloArgs &h, int tid)
 #pragma unroll
     for (int side = 0; side < 2; side++)
         if (h.peer_x[side])
-            for (int k = tid; k < h.cnt[side]; k += NTHREADS) h.dst[side][k] = ld_relaxed_sys(h.peer_x[side] + k);
+        {
+            // four remote loads in flight per thread (one NVLink round trip is ~1 us)
+            const double *src = h.peer_x[side];
+            double *dst = h.dst[side];
+            const int cnt = h.cnt[side];
+            int k = tid;
+            for (; k + 3 * NTHREADS < cnt; k += 4 * NTHREADS) {
+                const double v0 = ld_relaxed_sys(src + k), v1 = ld_relaxed_sys(src + k + NTHREADS),
+                             v2 = ld_relaxed_sys(src + k + 2 * NTHREADS), v3 = ld_relaxed_sys(src + k + 3 * NTHREADS);
+                dst[k] = v0; dst[k + NTHREADS] = v1; dst[k + 2 * NTHREADS] = v2; dst[k + 3 * NTHREADS] = v3;
+            }
+            for (; k < cnt; k += NTHREADS) dst[k] = ld_relaxed_sys(src + k);
+        }
     __threadfence();
     asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
     if (tid == 0) {
@@ -262,7 +275,20 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TS_STAGES * TS_STAGE_BYTES);
     const int tid = threadIdx.x;
-    const int niter = (nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // HALO: CTA 0 (dispatched first; the grid leaves it a resident slot) owns no row blocks.  It runs
+    // the halo protocol -- tell the neighbours, wait for them, pull their lines, raise the local
+    // flag, wait until they have pulled mine -- so that no worker falls behind its share of the
+    // sweep while a neighbour is late.
+    const int workers = HALO ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const int wix = HALO ? (int)blockIdx.x - 1 : (int)blockIdx.x;      // this CTA among the workers
+    if (HALO && blockIdx.x == 0) {
+        if (tid < TS_CONSUMERS) {
+            halo_pull<TS_CONSUMERS>(halo, tid);
+            if (tid == 0) halo_wait_acks(halo);
+        }
+        return;
+    }
+    const int niter = (nblocks - wix + workers - 1) / workers;
     // HALO: interior row blocks first, the blocks that read halo entries last
     const int n_int = HALO ? nblocks - halo.top_blocks - halo.bot_blocks : nblocks;
     auto block_of = [&](int q) -> int {
@@ -286,7 +312,7 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
             for (int it = 0; it < niter; it++) {
                 const int stage = it % TS_STAGES;
                 if (it >= TS_STAGES) mbar_wait(smem_u32(&bars[TS_STAGES + stage]), ((it / TS_STAGES) - 1) & 1);
-                const int blk = block_of(blockIdx.x + it * gridDim.x);
+                const int blk = block_of(wix + it * workers);
                 const int r0 = blk * R;
                 const int nrows = min(R, m - r0);
                 const int start = rowptr[r0], end = rowptr[r0 + nrows];
@@ -309,18 +335,12 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
 
     // ---------------- consumers ----------------
     const int lane = tid & 31;
-    if (HALO && blockIdx.x == 0) halo_pull<TS_CONSUMERS>(halo, tid);
-    bool halo_seen = false;
-    for (int it = 0; it < niter; it++) {
+    // one row block; EDGE (compile time) = the block reads halo entries, which landed during this
+    // launch and are therefore read from L2 -- the interior blocks keep the read-only path untouched
+    auto run_block = [&](int it, auto edge_tag) {
+        constexpr bool edge = decltype(edge_tag)::value;
         const int stage = it % TS_STAGES;
-        const int q = blockIdx.x + it * gridDim.x;
-        const int blk = block_of(q);
-        const bool edge = HALO && q >= n_int;          // this block reads halo entries: they must have landed
-        if (edge && !halo_seen) {
-            if (tid == 0) halo_wait(halo.comm + 4, halo.epoch, halo.comm + 5);
-            asm volatile("bar.sync 1, %0;" ::"n"(TS_CONSUMERS) : "memory");
-            halo_seen = true;
-        }
+        const int blk = block_of(wix + it * workers);
         const int r0 = blk * R;
         const int nrows = min(R, m - r0);
         double yv = 0.0;
@@ -381,22 +401,27 @@ k_spmv_tma(int m, int nblocks, int R, const csi *__restrict__ rowptr, const csi 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[TS_STAGES + stage]));
+    };
+    int it = 0;
+    for (; it < niter && (!HALO || wix + it * workers < n_int); it++) run_block(it, std::false_type{});
+    if (HALO && it < niter) {                            // the blocks that read halo entries: they must have landed
+        if (tid == 0) halo_wait(halo.comm + 4, halo.epoch, halo.comm + 5);
+        asm volatile("bar.sync 1, %0;" ::"n"(TS_CONSUMERS) : "memory");
+        for (; it < niter; it++) run_block(it, std::true_type{});
     }
-    // the neighbours have read my x of this epoch: the caller may overwrite it after this launch
-    if (HALO && blockIdx.x == 0 && tid == 0) halo_wait_acks(halo);
 }
 
 static int launch_spmv_tma(bool long_rows, int m, int nblocks, int R, const csi *rowptr, const csi *col,
                            const double *val, const double *x, double *y, cudaStream_t s, const HaloArgs *halo = nullptr)
 {
     const int sms = sm_count();
-    const int grid = min(nblocks, 2 * sms);          // two resident CTAs per SM
+    const int grid = min(nblocks, 2 * sms - (halo ? 1 : 0));   // two resident CTAs per SM (one slot is the halo protocol CTA's)
     HaloArgs h{};
     if (halo) h = *halo;
 #define TMA_LAUNCH(SH, HALO)                                                                                  \
     do {                                                                                                      \
         CSB_CUDA(cudaFuncSetAttribute(k_spmv_tma<SH, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH::smem)); \
-        k_spmv_tma<SH, HALO><<<grid, TS_THREADS, SH::smem, s>>>(m, nblocks, R, rowptr, col, val, x, y, h);       \
+        k_spmv_tma<SH, HALO><<<grid + (HALO ? 1 : 0), TS_THREADS, SH::smem, s>>>(m, nblocks, R, rowptr, col, val, x, y, h); \
     } while (0)
     if (long_rows) { if (halo) TMA_LAUNCH(TsLong, true); else TMA_LAUNCH(TsLong, false); }
     else           { if (halo) TMA_LAUNCH(TsShort, true); else TMA_LAUNCH(TsShort, false); }
@@ -633,7 +658,16 @@ k_spmv_mid(int n_mid, const int *__restrict__ mid_list, const csi *__restrict__ 
     if (gi < n_mid) {
         r = mid_list[gi];
         const int e = rowptr[r + 1];
-        for (int p = rowptr[r] + sub; p < e; p += 8) s = __dadd_rn(s, __dmul_rn(val[p], __ldg(x + col[p])));
+        int p = rowptr[r] + sub;
+        double s2 = 0.0;
+        for (; p + 8 < e; p += 16) {                        // two gathers in flight per lane
+            const int c0 = col[p], c1 = col[p + 8];
+            const double v0 = val[p], v1 = val[p + 8];
+            s = __dadd_rn(s, __dmul_rn(v0, __ldg(x + c0)));
+            s2 = __dadd_rn(s2, __dmul_rn(v1, __ldg(x + c1)));
+        }
+        if (p < e) s = __dadd_rn(s, __dmul_rn(val[p], __ldg(x + col[p])));
+        s = __dadd_rn(s, s2);
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
@@ -652,6 +686,29 @@ k_spmv_short(int n_short, const int *__restrict__ short_list, const csi *__restr
     double s = y[r];
     for (int p = rowptr[r]; p < e; p++) s = __dadd_rn(s, __dmul_rn(val[p], __ldg(x + col[p])));   // the reference's order (csparse.py:1210-1212)
     y[r] = s;
+}
+
+// side stream of the split plan (per thread and device, like the host pipeline's copy streams)
+struct SplitStreams {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int device = -1;
+    int init()
+    {
+        int dev = 0;
+        CSB_CUDA(cudaGetDevice(&dev));
+        if (device == dev) return CSB200_OK;
+        CSB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        CSB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CSB_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        device = dev;
+        return CSB200_OK;
+    }
+};
+static SplitStreams &split_streams()
+{
+    static thread_local SplitStreams ss;
+    return ss;
 }
 
 static int build_split(csb200_mat *AT, SpmvPlan *pl)
@@ -728,6 +785,7 @@ int spmv_build_plan(csb200_mat *AT)
     pl->max_len = h_max;
     const double avg = m > 0 ? (double)nnz / m : 0.0;
     int kind = (h_max <= 64 || h_max <= 4.0 * avg + 16.0) ? 1 : 2;
+    if (kind == 2 && nnz >= (1 << 20)) kind = 4;                    // power-law rows: binned by length (1.23 ms against the merge path's 1.87 on R-MAT 2^24)
     if (kind == 2 && (long long)m + nnz >= 0x7fffffffLL - MP_TILE) kind = 1;     // merge coordinates are int32
     if (AT->forced_plan) kind = AT->forced_plan;
     pl->kind = kind;
@@ -779,21 +837,30 @@ int spmv_run(csb200_mat *AT, const double *d_x, double *d_y)
         k_spmv_stream<<<ceil_div(m, R), SP_THREADS, 0, stream()>>>(m, AT->p, AT->i, AT->x, d_x, d_y, R);
         CSB_LAUNCHED();
     } else if (pl->kind == 4) {
+        // the three bins write disjoint rows of y: the mid and short kernels run beside the long one
+        // on a second stream (forked and joined with events), so their tails overlap
+        cudaStream_t s = stream();
+        SplitStreams &ss = split_streams();
+        CSB_TRY(ss.init());
+        CSB_CUDA(cudaEventRecord(ss.fork, s));
+        CSB_CUDA(cudaStreamWaitEvent(ss.side, ss.fork, 0));
         if (pl->n_items > 0) {
             const int grid = min(ceil_div(pl->n_items, 8), sm_count() * 8);
-            k_spmv_long<<<grid, 256, 0, stream()>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
+            k_spmv_long<<<grid, 256, 0, s>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
             CSB_LAUNCHED();
-            k_long_fix<<<ceil_div(pl->n_long, 256), 256, 0, stream()>>>(pl->n_long, pl->long_list, pl->long_ptr, pl->partial, d_y);
+            k_long_fix<<<ceil_div(pl->n_long, 256), 256, 0, s>>>(pl->n_long, pl->long_list, pl->long_ptr, pl->partial, d_y);
             CSB_LAUNCHED();
         }
         if (pl->n_mid > 0) {
-            k_spmv_mid<<<ceil_div((long long)pl->n_mid * 8, 256), 256, 0, stream()>>>(pl->n_mid, pl->mid_list, AT->p, AT->i, AT->x, d_x, d_y);
+            k_spmv_mid<<<ceil_div((long long)pl->n_mid * 8, 256), 256, 0, ss.side>>>(pl->n_mid, pl->mid_list, AT->p, AT->i, AT->x, d_x, d_y);
             CSB_LAUNCHED();
         }
         if (pl->n_short > 0) {
-            k_spmv_short<<<ceil_div(pl->n_short, 256), 256, 0, stream()>>>(pl->n_short, pl->short_list, AT->p, AT->i, AT->x, d_x, d_y);
+            k_spmv_short<<<ceil_div(pl->n_short, 256), 256, 0, ss.side>>>(pl->n_short, pl->short_list, AT->p, AT->i, AT->x, d_x, d_y);
             CSB_LAUNCHED();
         }
+        CSB_CUDA(cudaEventRecord(ss.join, ss.side));
+        CSB_CUDA(cudaStreamWaitEvent(s, ss.join, 0));
     } else {
         k_spmv_merge<<<pl->merge_ctas, MP_THREADS, 0, stream()>>>(m, (int)AT->nnz, AT->p, AT->i, AT->x, d_x, d_y,
                                                                    pl->merge_part, pl->carry_row, pl->carry_val);
@@ -1032,7 +1099,10 @@ int csb200_gaxpy_halo_dev(csb200_mat *AT, csb200_halo *h, double *d_y, csi top_r
     if (m > 0 && AT->nnz > 0 && pl->kind == 1) {
         const int R = pl->rows_per_cta;
         const int nblocks = ceil_div(m, R);
-        int tb = ceil_div(top_rows, R), bb = ceil_div(bot_rows, R);
+        // blocks that hold a row reading halo entries: the first ceil(top_rows / R), and every block
+        // from the one holding row m - bot_rows on (the last block may be short)
+        int tb = ceil_div(top_rows, R);
+        int bb = bot_rows > 0 ? nblocks - max(0, m - (int)bot_rows) / R : 0;
         if (tb + bb > nblocks) { tb = nblocks; bb = 0; }
         const HaloArgs a = halo_args(h, tb, bb);
         return launch_spmv_tma(pl->long_rows, m, nblocks, R, AT->p, AT->i, AT->x, h->window, d_y, s, &a);

@@ -93,7 +93,7 @@ row_bounds = csd.balanced_bounds(T.p.astype(np.int64), world)
 r0, r1 = int(row_bounds[rank]), int(row_bounds[rank + 1])
 blk = csd.csr_row_block(T.p, T.i[:nnzT], T.x[:nnzT], r0, r1)
 sh = csd.ShardedGaxpy(blk, m, n, row_bounds, x_bounds=csd.even_bounds(n, world), make_local=csd.cuda_make_local,
-                      local_spmv=csd.cuda_local_spmv, device="cuda")
+                      local_spmv=csd.cuda_local_spmv, device="cuda", force_gather=True)   # two ranks are always neighbours
 assert sh.plan.mode == "gather"
 c0, c1 = sh.c0, sh.c1
 rng = np.random.default_rng(9)
