@@ -1079,12 +1079,17 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
         MM_LAUNCHED();
         if (h_tpl[3] > 0 && soa) {
             // 32 columns per CTA in lock step; what it leaves (grid boundaries, long columns) goes to k_num_tpl
-            MM_CUDA(cudaFuncSetAttribute(k_num_soa, cudaFuncAttributeMaxDynamicSharedMemorySize, SOA_SMEM));
             // few CTAs per SM: each works on ~100 KB of A that should stay in its SM's L1
             static const int soa_ctas = getenv("CSB200_SOA_CTAS") ? atoi(getenv("CSB200_SOA_CTAS")) : 4;
             const int grid = (int)min((long long)ceil_div(n, 32), (long long)sm_count() * soa_ctas);
-            k_num_soa<<<grid, SOA_THREADS, SOA_SMEM, s>>>(n, cb.ptr, tpl_cnt.ptr, tpl_mode.ptr, tpl_terms.ptr, tpl_tend.ptr,
-                                                        tpl_wptr.ptr, tpl_rows.ptr, A->soa_x, B->soa_x, C->p, C->i, C->x);
+#define SOA_LAUNCH(MINB)                                                                                       \
+            do {                                                                                               \
+                MM_CUDA(cudaFuncSetAttribute(k_num_soa<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOA_SMEM)); \
+                k_num_soa<MINB><<<grid, SOA_THREADS, SOA_SMEM, s>>>(n, cb.ptr, tpl_cnt.ptr, tpl_mode.ptr, tpl_terms.ptr, tpl_tend.ptr, \
+                                                                  tpl_wptr.ptr, tpl_rows.ptr, A->soa_x, B->soa_x, C->p, C->i, C->x);    \
+            } while (0)
+            if (soa_ctas >= 6) SOA_LAUNCH(6); else if (soa_ctas == 5) SOA_LAUNCH(5); else SOA_LAUNCH(4);
+#undef SOA_LAUNCH
             MM_LAUNCHED();
         }
         if (h_tpl[4] > 0) {

@@ -597,7 +597,8 @@ struct SoaTables {
 };
 constexpr int SOA_SMEM = (int)sizeof(SoaTables) + 2 * 32 * 33 * 8;
 
-__global__ void __launch_bounds__(SOA_THREADS, 4)
+template <int MINB>
+__global__ void __launch_bounds__(SOA_THREADS, MINB)
 k_num_soa(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt, const unsigned char *__restrict__ mode,
           const int2 *__restrict__ tpl_terms, const unsigned char *__restrict__ tpl_tend, const int *__restrict__ tpl_wptr,
           const int *__restrict__ tpl_rows, const double *__restrict__ AxT, const double *__restrict__ BxT,

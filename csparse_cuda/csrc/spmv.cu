@@ -18,6 +18,7 @@
 //                  the unfinished row fixed up by k_merge_fixup (deterministic).
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <type_traits>
 
 struct SpmvPlan {
@@ -557,32 +558,38 @@ __global__ void k_max_len(const csi *__restrict__ rowptr, int m, int *out)
 // time (coalesced col / val, x gathered through L1), every lane keeps its own running sums and the
 // warp reduces once at the end.  Rows are therefore binned by length, once per handle, and every bin
 // reads the CSR arrays in place:
-//   long   (>= SPLIT_LONG entries: 80+ % of the nonzeros of the R-MAT matrix) cut into items of at
-//          most SPLIT_CHUNK entries, one warp per item; the items' sums are parked and added to y
+//   long   (>= 64 entries: 80+ % of the nonzeros of the R-MAT matrix) cut into items of at
+//          most 1024 entries, one warp per item; the items' sums are parked and added to y
 //          per row in item order by a small second kernel (deterministic, like the merge path's
 //          carry fix-up);
-//   mid    (SPLIT_MID .. SPLIT_LONG-1 entries) eight lanes per row, four rows per warp;
-//   short  (1 .. SPLIT_MID-1 entries) one thread per row.
+//   mid    (16 .. 63 entries) eight lanes per row, four rows per warp;
+//   short  (1 .. 15 entries) one thread per row.
+// (cuts swept on R-MAT 2^24: 64 / 8 / 2048 -> 1.227 ms, 64 / 16 / 1024 -> 1.176 ms, 32 / 8 / 2048 -> 1.289 ms)
 // Empty rows are in no list: y is untouched there, as in the reference.
-constexpr int SPLIT_LONG = 64;
-constexpr int SPLIT_MID = 8;
-constexpr int SPLIT_CHUNK = 2048;
+struct SplitCuts { int lng, mid, chunk; };      // rows >= lng: long; mid .. lng-1: mid; 1 .. mid-1: short; items of <= chunk entries
+static SplitCuts split_cuts()
+{
+    static const SplitCuts c = {getenv("CSB200_SPLIT_LONG") ? atoi(getenv("CSB200_SPLIT_LONG")) : 64,
+                                getenv("CSB200_SPLIT_MID") ? atoi(getenv("CSB200_SPLIT_MID")) : 16,
+                                getenv("CSB200_SPLIT_CHUNK") ? atoi(getenv("CSB200_SPLIT_CHUNK")) : 1024};
+    return c;
+}
 
-__global__ void k_split_count(int m, const csi *__restrict__ rowptr, int *__restrict__ nitems, int *__restrict__ islong,
-                              int *__restrict__ ismid, int *__restrict__ isshort)
+__global__ void k_split_count(int m, const csi *__restrict__ rowptr, SplitCuts cut, int *__restrict__ nitems,
+                              int *__restrict__ islong, int *__restrict__ ismid, int *__restrict__ isshort)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     const int len = rowptr[r + 1] - rowptr[r];
-    const bool lg = len >= SPLIT_LONG;
-    nitems[r] = lg ? (len + SPLIT_CHUNK - 1) / SPLIT_CHUNK : 0;
+    const bool lg = len >= cut.lng;
+    nitems[r] = lg ? (len + cut.chunk - 1) / cut.chunk : 0;
     islong[r] = lg ? 1 : 0;
-    ismid[r] = (!lg && len >= SPLIT_MID) ? 1 : 0;
-    isshort[r] = (len > 0 && len < SPLIT_MID) ? 1 : 0;
+    ismid[r] = (!lg && len >= cut.mid) ? 1 : 0;
+    isshort[r] = (len > 0 && len < cut.mid) ? 1 : 0;
 }
 
 // iptr / lptr / mptr / sptr: exclusive scans of the four arrays above
-__global__ void k_split_fill(int m, const csi *__restrict__ rowptr, const int *__restrict__ iptr,
+__global__ void k_split_fill(int m, const csi *__restrict__ rowptr, SplitCuts cut, const int *__restrict__ iptr,
                              const int *__restrict__ lptr, const int *__restrict__ mptr, const int *__restrict__ sptr,
                              int4 *__restrict__ items, int *__restrict__ long_list, int *__restrict__ long_ptr,
                              int *__restrict__ mid_list, int *__restrict__ short_list)
@@ -591,24 +598,25 @@ __global__ void k_split_fill(int m, const csi *__restrict__ rowptr, const int *_
     if (r >= m) return;
     const int b = rowptr[r], e = rowptr[r + 1];
     const int len = e - b;
-    if (len >= SPLIT_LONG) {
+    if (len >= cut.lng) {
         const int li = lptr[r];
         long_list[li] = r;
         long_ptr[li] = iptr[r];
         int k = iptr[r];
         // equal items: a row of 2049 entries becomes 1025 + 1024, not 2048 + 1
-        const int n = (len + SPLIT_CHUNK - 1) / SPLIT_CHUNK;
+        const int n = (len + cut.chunk - 1) / cut.chunk;
         for (int c = 0; c < n; c++, k++) {
             const int ib = b + (int)((long long)len * c / n), ie = b + (int)((long long)len * (c + 1) / n);
             items[k] = make_int4(ib, ie, r, 0);
         }
-    } else if (len >= SPLIT_MID) {
+    } else if (len >= cut.mid) {
         mid_list[mptr[r]] = r;
     } else if (len > 0) {
         short_list[sptr[r]] = r;
     }
 }
 
+template <int UNR>
 __global__ void __launch_bounds__(256)
 k_spmv_long(int n_items, const int4 *__restrict__ items, const csi *__restrict__ col, const double *__restrict__ val,
             const double *__restrict__ x, double *__restrict__ partial)
@@ -617,18 +625,22 @@ k_spmv_long(int n_items, const int4 *__restrict__ items, const csi *__restrict__
     const int nwarps = gridDim.x * 8;
     for (int it = blockIdx.x * 8 + (threadIdx.x >> 5); it < n_items; it += nwarps) {
         const int4 im = items[it];
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double acc[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) acc[u] = 0.0;
         int p = im.x + lane;
-        for (; p + 96 < im.y; p += 128) {                   // four independent gathers in flight per lane
-            const int c0 = ldg_stream(col + p), c1 = ldg_stream(col + p + 32), c2 = ldg_stream(col + p + 64), c3 = ldg_stream(col + p + 96);
-            const double v0 = ldg_stream(val + p), v1 = ldg_stream(val + p + 32), v2 = ldg_stream(val + p + 64), v3 = ldg_stream(val + p + 96);
-            a0 = __dadd_rn(a0, __dmul_rn(v0, __ldg(x + c0)));
-            a1 = __dadd_rn(a1, __dmul_rn(v1, __ldg(x + c1)));
-            a2 = __dadd_rn(a2, __dmul_rn(v2, __ldg(x + c2)));
-            a3 = __dadd_rn(a3, __dmul_rn(v3, __ldg(x + c3)));
+        for (; p + 32 * (UNR - 1) < im.y; p += 32 * UNR) {  // UNR independent gathers in flight per lane
+            int c[UNR];
+            double v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) { c[u] = ldg_stream(col + p + 32 * u); v[u] = ldg_stream(val + p + 32 * u); }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) acc[u] = __dadd_rn(acc[u], __dmul_rn(v[u], __ldg(x + c[u])));
         }
-        for (; p < im.y; p += 32) a0 = __dadd_rn(a0, __dmul_rn(ldg_stream(val + p), __ldg(x + ldg_stream(col + p))));
-        double s = __dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3));
+        for (; p < im.y; p += 32) acc[0] = __dadd_rn(acc[0], __dmul_rn(ldg_stream(val + p), __ldg(x + ldg_stream(col + p))));
+        double s = acc[0];
+#pragma unroll
+        for (int u = 1; u < UNR; u++) s = __dadd_rn(s, acc[u]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
         if (lane == 0) partial[it] = s;
@@ -721,7 +733,8 @@ static int build_split(csb200_mat *AT, SpmvPlan *pl)
     CSB_TRY(nitems.alloc(cap)); CSB_TRY(islong.alloc(cap)); CSB_TRY(ismid.alloc(cap)); CSB_TRY(isshort.alloc(cap));
     CSB_TRY(iptr.alloc(cap)); CSB_TRY(lptr.alloc(cap)); CSB_TRY(mptr.alloc(cap)); CSB_TRY(sptr.alloc(cap));
     CSB_TRY(tot.alloc(4));
-    k_split_count<<<ceil_div(m, 256), 256, 0, s>>>(m, AT->p, nitems.ptr, islong.ptr, ismid.ptr, isshort.ptr);
+    const SplitCuts cut = split_cuts();
+    k_split_count<<<ceil_div(m, 256), 256, 0, s>>>(m, AT->p, cut, nitems.ptr, islong.ptr, ismid.ptr, isshort.ptr);
     CSB_LAUNCHED();
     CSB_TRY(launch_excl_scan(iptr.ptr, nitems.ptr, m, tot.ptr, nullptr));
     CSB_TRY(launch_excl_scan(lptr.ptr, islong.ptr, m, tot.ptr + 1, nullptr));
@@ -740,7 +753,7 @@ static int build_split(csb200_mat *AT, SpmvPlan *pl)
     CSB_TRY(dev_alloc(&pl->partial, (size_t)pl->n_items + 1));
     CSB_TRY(dev_alloc(&pl->mid_list, (size_t)pl->n_mid + 1));
     CSB_TRY(dev_alloc(&pl->short_list, (size_t)pl->n_short + 1));
-    k_split_fill<<<ceil_div(m, 256), 256, 0, s>>>(m, AT->p, iptr.ptr, lptr.ptr, mptr.ptr, sptr.ptr, pl->items,
+    k_split_fill<<<ceil_div(m, 256), 256, 0, s>>>(m, AT->p, cut, iptr.ptr, lptr.ptr, mptr.ptr, sptr.ptr, pl->items,
                                                   pl->long_list, pl->long_ptr, pl->mid_list, pl->short_list);
     CSB_LAUNCHED();
     CSB_CUDA(cudaMemcpyAsync(pl->long_ptr + pl->n_long, &pl->n_items, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -845,8 +858,11 @@ int spmv_run(csb200_mat *AT, const double *d_x, double *d_y)
         CSB_CUDA(cudaEventRecord(ss.fork, s));
         CSB_CUDA(cudaStreamWaitEvent(ss.side, ss.fork, 0));
         if (pl->n_items > 0) {
-            const int grid = min(ceil_div(pl->n_items, 8), sm_count() * 8);
-            k_spmv_long<<<grid, 256, 0, s>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
+            static const int long_unr = getenv("CSB200_LONG_UNR") ? atoi(getenv("CSB200_LONG_UNR")) : 4;
+            static const int long_ctas = getenv("CSB200_LONG_CTAS") ? atoi(getenv("CSB200_LONG_CTAS")) : 8;
+            const int grid = min(ceil_div(pl->n_items, 8), sm_count() * long_ctas);
+            if (long_unr == 8) k_spmv_long<8><<<grid, 256, 0, s>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
+            else               k_spmv_long<4><<<grid, 256, 0, s>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
             CSB_LAUNCHED();
             k_long_fix<<<ceil_div(pl->n_long, 256), 256, 0, s>>>(pl->n_long, pl->long_list, pl->long_ptr, pl->partial, d_y);
             CSB_LAUNCHED();

@@ -43,10 +43,7 @@ constexpr int PT_EPT = 8;                     // entries per thread in the parti
 constexpr int PT_TILE = TR_THREADS * PT_EPT;  // 2048 entries per partition CTA
 constexpr int PT_SMEM_COLS = 3072;            // column pointers staged per partition tile
 constexpr int HIST_WIN = 4096;                // bucket window counted in shared memory
-#ifndef WB_EPT_DEF
-#define WB_EPT_DEF 12
-#endif
-constexpr int WB_EPT = WB_EPT_DEF;            // entries per lane in the warp-per-bucket kernel
+constexpr int WB_EPT = 12;                    // entries per lane in the warp-per-bucket kernel
 constexpr int WB_CAP = 32 * WB_EPT;           // 384 entries staged per warp
 constexpr int WB_RB_MAX = 128;                // rows per bucket (power of two)
 constexpr int WB_WARPS = 8;                   // warps (independent bucket pipelines) per CTA
@@ -966,8 +963,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     // rows per bucket: the largest power of two whose average bucket fills <= 85 % of the staging area
     const double avg = (double)nnz / m;
     // short rows: one warp per small bucket; longer rows: one CTA per larger bucket
-    static const double warp_avg = getenv("CSB200_TR_WARP_AVG") ? atof(getenv("CSB200_TR_WARP_AVG")) : 8.0;
-    const bool warp_path = avg <= warp_avg;
+    const bool warp_path = avg <= 8.0;       // (one warp per bucket with 16 entries per lane on the 27-point stencil: 1.63 ms against 1.50)
     const int bcap = warp_path ? WB_CAP : BK_CAP;
     int log_rb = 2;
     while (log_rb < (warp_path ? 7 : 10) && (double)(2 << log_rb) * avg <= 0.85 * bcap) log_rb++;
