@@ -552,10 +552,13 @@ def bench_gaxpy_lap2d(a, torch, dist, cc, synth, csd, world, rank, k, peak, peak
         node = bind_numa(torch.cuda.current_device())
         hx_own, hy_own = x_own.cpu().pin_memory(), y_own.cpu().pin_memory()
         if sh.fused:
-            e2e_step = lambda: sh.step_host(hx_own, hy_own)
-            call = ("per rank: csb200_gaxpy_halo(block, halo, x_slice, y_slice) on pinned host slices -- x and y H2D, "
-                    "halo lines pulled from the neighbours' windows, y D2H in row chunks (duplex), matrix block resident")
-            h2d = 16 * (r1 - r0)
+            # y accumulates in HBM between steps (as in a solver loop); the host gets the step's result.
+            # All ranks of this box share two PCIe uplinks (~106 GB/s H2D in aggregate, measured at N = 8
+            # with y travelling up as well: 20.2 ms per step), so the bytes per step are what counts.
+            e2e_step = lambda: sh.step_host(hx_own, hy_own, y_own)
+            call = ("per rank: csb200_gaxpy_halo(block, halo, x_slice, y_copy, d_y) on pinned host slices -- x H2D (ends first), "
+                    "halo lines pulled from the neighbours' windows, y D2H in row chunks (duplex), y and the matrix block resident")
+            h2d = 8 * (r1 - r0)
         else:
             def e2e_step():
                 x_own.copy_(hx_own, non_blocking=True)

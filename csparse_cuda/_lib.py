@@ -58,7 +58,8 @@ PROTOTYPES = {
     "csb200_halo_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "csb200_halo_connect_local": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "csb200_gaxpy_halo_dev": (C.c_int, [mat_t, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
-    "csb200_gaxpy_halo": (C.c_int, [mat_t, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "csb200_gaxpy_halo": (C.c_int, [mat_t, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                    C.c_void_p]),
     "csb200_halo_status": (C.c_int, [C.c_void_p, intp]),
     "csb200_halo_free": (C.c_int, [C.c_void_p]),
     "csb200_multiply": (C.c_int, [mat_t, mat_t, matp]),

@@ -612,10 +612,10 @@ int csb200_gaxpy(csb200_mat *A, const double *x, double *y)
 // two copy streams exactly as in csb200_gaxpy -- the D2H of a finished chunk overlaps the H2D of the
 // next ones, the SpMV of a chunk starts when the part of x it reads has landed.
 int csb200_gaxpy_halo(csb200_mat *AT, csb200_halo *h, const double *x_own, int64_t own_off, int64_t own_len,
-                      int64_t edge_lo, int64_t edge_hi, double *y)
+                      int64_t edge_lo, int64_t edge_hi, double *y, double *d_y_resident)
 {
     ArenaScope arena_scope;
-    if (!AT || !h || !x_own || !y || own_off < 0 || own_len < 0 || edge_lo < 0 || edge_hi < 0)
+    if (!AT || !h || !x_own || (!y && !d_y_resident) || own_off < 0 || own_len < 0 || edge_lo < 0 || edge_hi < 0)
         return set_error(CSB200_ERR_ARG, "cs_gaxpy: bad arguments");
     if (!AT->x) return set_error(CSB200_ERR_ARG, "cs_gaxpy: matrix has no values");
     if (own_off + own_len > halo_window_count(h) || AT->m > halo_window_count(h))
@@ -625,8 +625,12 @@ int csb200_gaxpy_halo(csb200_mat *AT, csb200_halo *h, const double *x_own, int64
     const int m = AT->n;
     double *win = halo_window_ptr(h);
     double *d_own = win + own_off;
-    DevBuf<double> d_y;
-    CSB_TRY(d_y.alloc((size_t)(m > 0 ? m : 1)));
+    // y: a host vector that travels up and down (d_y_resident == NULL), or a vector that stays in HBM
+    // and accumulates there, of which the host gets a copy (y != NULL) after every step
+    DevBuf<double> d_y_tmp;
+    const bool y_up = d_y_resident == nullptr;
+    if (y_up) CSB_TRY(d_y_tmp.alloc((size_t)(m > 0 ? m : 1)));
+    struct { double *ptr; } d_y = {y_up ? d_y_tmp.ptr : d_y_resident};
     cudaStream_t s = stream();
     HostPipe &hp = host_pipe();
     CSB_TRY(hp.init());
@@ -664,23 +668,23 @@ int csb200_gaxpy_halo(csb200_mat *AT, csb200_halo *h, const double *x_own, int64
                                          cudaMemcpyHostToDevice, hp.h2d));
                 x_sent = upto;
             }
-            CSB_CUDA(cudaMemcpyAsync(d_y.ptr + ra, y + ra, bytes, cudaMemcpyHostToDevice, hp.h2d));
+            if (y_up) CSB_CUDA(cudaMemcpyAsync(d_y.ptr + ra, y + ra, bytes, cudaMemcpyHostToDevice, hp.h2d));
             CSB_CUDA(cudaEventRecord(hp.up[c], hp.h2d));
             CSB_CUDA(cudaStreamWaitEvent(s, hp.up[c], 0));
             CSB_TRY(spmv_run_rows(AT, win, d_y.ptr, ra, rb, s));
             CSB_CUDA(cudaEventRecord(hp.done[c], s));
             CSB_CUDA(cudaStreamWaitEvent(hp.d2h, hp.done[c], 0));
-            CSB_CUDA(cudaMemcpyAsync(y + ra, d_y.ptr + ra, bytes, cudaMemcpyDeviceToHost, hp.d2h));
+            if (y) CSB_CUDA(cudaMemcpyAsync(y + ra, d_y.ptr + ra, bytes, cudaMemcpyDeviceToHost, hp.d2h));
         }
     } else {
         if (own_len > 0) CSB_CUDA(cudaMemcpyAsync(d_own, x_own, (size_t)own_len * sizeof(double), cudaMemcpyHostToDevice, hp.h2d));
-        if (m > 0) CSB_CUDA(cudaMemcpyAsync(d_y.ptr, y, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, hp.h2d));
+        if (m > 0 && y_up) CSB_CUDA(cudaMemcpyAsync(d_y.ptr, y, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, hp.h2d));
         CSB_CUDA(cudaEventRecord(hp.up[0], hp.h2d));
         CSB_CUDA(cudaStreamWaitEvent(s, hp.up[0], 0));
         CSB_TRY(spmv_run(AT, win, d_y.ptr));
         CSB_CUDA(cudaEventRecord(hp.done[0], s));
         CSB_CUDA(cudaStreamWaitEvent(hp.d2h, hp.done[0], 0));
-        if (m > 0) CSB_CUDA(cudaMemcpyAsync(y, d_y.ptr, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, hp.d2h));
+        if (m > 0 && y) CSB_CUDA(cudaMemcpyAsync(y, d_y.ptr, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, hp.d2h));
     }
     // the neighbours have pulled my lines: the next call may overwrite x
     CSB_TRY(halo_acks_launch(h, s));

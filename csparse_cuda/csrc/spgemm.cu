@@ -982,6 +982,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
     MM_CUDA(cudaMemsetAsync(cnt.ptr, 0, ncap * sizeof(int), s));
 
     int h_counts[8] = {0};
+    bool generic_cols = true;
     int h_tpl[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // ClsTable::info: [3] templated columns, [4] of them for k_num_tpl
     unsigned long long h_flops = 0;
     constexpr int DENSE_CTAS = 64;
@@ -1033,6 +1034,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
         tls().last_flops = (int64_t)h_flops;
         tls().last_templated = h_tpl[3];
         int *ovf_list = lists.ptr + 2 * ncap, *ovf_count = counts.ptr + 2;
+        generic_cols = h_counts[0] + h_counts[1] + h_counts[2] + h_counts[3] > 0;     // columns without a template
         if (h_counts[0] + h_counts[1] > 0) MM_TRY(ensure_compressed(A));
         if (blocked) {
             MM_TRY(nblk.alloc(ncap));
@@ -1112,7 +1114,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             MM_LAUNCHED();
         }
         int n_blocked = 0;
-        if (blocked) {
+        if (blocked && generic_cols) {
             // columns whose block list was kept go to the blocked kernel (list 3 region is free here)
             k_pick_blocked<<<ceil_div(n, 256), 256, 0, s>>>(n, nblk.ptr, ub.ptr, pick.ptr);
             MM_LAUNCHED();
@@ -1155,12 +1157,16 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
                 MM_LAUNCHED();
             }
         }
-        MM_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * sizeof(int), s));
-        // numeric classes by exact column size: <=128 | <=512 | <=2048 | dense
-        k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, INT_MAX, 128, 512, 2048, lists.ptr, counts.ptr);
-        MM_LAUNCHED();
-        MM_CUDA(cudaMemcpyAsync(h_counts, counts.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-        MM_CUDA(cudaStreamSynchronize(s));
+        // numeric classes by exact column size: <=128 | <=512 | <=2048 | dense (nothing to do, and no
+        // host round trip, when every column came from a template)
+        h_counts[0] = h_counts[1] = h_counts[2] = h_counts[3] = 0;
+        if (generic_cols) {
+            MM_CUDA(cudaMemsetAsync(counts.ptr, 0, 8 * sizeof(int), s));
+            k_bin<<<ceil_div(n, 256), 256, 0, s>>>(n, ub.ptr, INT_MAX, 128, 512, 2048, lists.ptr, counts.ptr);
+            MM_LAUNCHED();
+            MM_CUDA(cudaMemcpyAsync(h_counts, counts.ptr, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            MM_CUDA(cudaStreamSynchronize(s));
+        }
         MM_TRY((run_num_warp<8, 128, 8>(lists.ptr, h_counts[0], A, B, C, values, canon != 0)));
         MM_TRY((run_num_warp<10, 512, 8>(lists.ptr + ncap, h_counts[1], A, B, C, values, canon != 0)));
         MM_TRY((run_num_warp<12, 2048, 4>(lists.ptr + 2 * ncap, h_counts[2], A, B, C, values, canon != 0)));

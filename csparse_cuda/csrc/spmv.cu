@@ -858,11 +858,9 @@ int spmv_run(csb200_mat *AT, const double *d_x, double *d_y)
         CSB_CUDA(cudaEventRecord(ss.fork, s));
         CSB_CUDA(cudaStreamWaitEvent(ss.side, ss.fork, 0));
         if (pl->n_items > 0) {
-            static const int long_unr = getenv("CSB200_LONG_UNR") ? atoi(getenv("CSB200_LONG_UNR")) : 4;
-            static const int long_ctas = getenv("CSB200_LONG_CTAS") ? atoi(getenv("CSB200_LONG_CTAS")) : 8;
-            const int grid = min(ceil_div(pl->n_items, 8), sm_count() * long_ctas);
-            if (long_unr == 8) k_spmv_long<8><<<grid, 256, 0, s>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
-            else               k_spmv_long<4><<<grid, 256, 0, s>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
+            // four gathers in flight per lane, eight CTAs per SM (eight in flight / 4-12 CTAs: 1.18-1.28 ms, no better)
+            const int grid = min(ceil_div(pl->n_items, 8), sm_count() * 8);
+            k_spmv_long<4><<<grid, 256, 0, s>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
             CSB_LAUNCHED();
             k_long_fix<<<ceil_div(pl->n_long, 256), 256, 0, s>>>(pl->n_long, pl->long_list, pl->long_ptr, pl->partial, d_y);
             CSB_LAUNCHED();

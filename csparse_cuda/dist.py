@@ -265,16 +265,18 @@ class ShardedGaxpy:
         self.exchanged_bytes = nbytes
         return dist.batch_isend_irecv(ops) if ops else []
 
-    def step_host(self, x_own_host, y_own_host):
+    def step_host(self, x_own_host, y_own_host, y_own_dev=None):
         """One distributed cs_gaxpy on pinned HOST tensors (fused mode): x slice up, halo pull, row
-        chunks of y up / SpMV / down with duplex copies (csb200_gaxpy_halo); y_own_host += A_block * x."""
+        chunks of y up / SpMV / down with duplex copies (csb200_gaxpy_halo); y_own_host += A_block * x.
+        With ``y_own_dev`` y accumulates in that device tensor and y_own_host receives a copy."""
         if not self.fused:
             raise RuntimeError("step_host needs the fused halo exchange")
         pl, r = self.plan, self.rank
         edge_lo = pl.hi_need[r - 1] if r > 0 else 0              # the rank below reads the head of my slice
         edge_hi = pl.lo_need[r + 1] if r + 1 < self.world else 0
         self.halo.step_host(self.handle, x_own_host.data_ptr(), self.own.start, self.own.stop - self.own.start,
-                            edge_lo, edge_hi, y_own_host.data_ptr())
+                            edge_lo, edge_hi, y_own_host.data_ptr() if y_own_host is not None else 0,
+                            y_own_dev.data_ptr() if y_own_dev is not None else 0)
         return y_own_host
 
     def step(self, x_own, y_own):
@@ -356,11 +358,14 @@ class FusedHalo:
         _lib.check(_lib.lib().csb200_gaxpy_halo_dev(handle._h, self._h, C.c_void_p(y_own.data_ptr()),
                                                     int(top_rows), int(bot_rows)), "gaxpy_halo_dev")
 
-    def step_host(self, handle, x_own_ptr: int, own_off: int, own_len: int, edge_lo: int, edge_hi: int, y_ptr: int):
-        """The step on HOST slices of x and y (raw addresses of pinned buffers): csb200_gaxpy_halo."""
+    def step_host(self, handle, x_own_ptr: int, own_off: int, own_len: int, edge_lo: int, edge_hi: int, y_ptr: int,
+                  d_y_ptr: int = 0):
+        """The step on HOST slices (raw addresses of pinned buffers): csb200_gaxpy_halo.  d_y_ptr: y
+        accumulates in that device vector; the host slice at y_ptr (0 = none) gets a copy."""
         C, _lib = self._C, self._lib
         _lib.check(_lib.lib().csb200_gaxpy_halo(handle._h, self._h, C.c_void_p(x_own_ptr), int(own_off), int(own_len),
-                                                int(edge_lo), int(edge_hi), C.c_void_p(y_ptr)), "gaxpy_halo")
+                                                int(edge_lo), int(edge_hi), C.c_void_p(y_ptr or None),
+                                                C.c_void_p(d_y_ptr or None)), "gaxpy_halo")
 
     def timed_out(self) -> bool:
         v = self._C.c_int()

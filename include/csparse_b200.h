@@ -19,6 +19,14 @@
  *     (the reference's `cs` object with nz == -1, csparse.py:37-54).
  *   - no CPU fallback: without a CUDA device every compute call fails with
  *     CSB200_ERR_CUDA.
+ *   - threads and streams: the library keeps its state per thread (stream, last error, path
+ *     switches, a workspace block that call temporaries are carved from).  Different threads may
+ *     work on different handles concurrently.  A handle -- with the caches it builds on first use
+ *     (CSR view, gaxpy plan and its scratch, pattern classes, entry-major copy) -- is bound to ONE
+ *     thread and ONE stream at a time: use it, and free it, from the thread / stream that last
+ *     used it, or synchronise in between (csb200_synchronize).  Calls that take host buffers
+ *     return after the stream has drained; "_dev" calls and calls on handles only are
+ *     asynchronous.
  */
 #ifndef CSPARSE_B200_H
 #define CSPARSE_B200_H
@@ -142,11 +150,13 @@ CSB200_API int csb200_halo_connect_local(csb200_halo *h, int side, csb200_halo *
  * halo entries (0, 0 with no neighbours).  Every rank must call it the same number of times. */
 CSB200_API int csb200_gaxpy_halo_dev(csb200_mat *AT, csb200_halo *h, double *d_y, csi top_rows, csi bot_rows);
 /* the same step on HOST vectors: x_own (own_len doubles) is this rank's slice of x, stored at offset
- * own_off of the window; y (AT.n doubles) is read and written; edge_lo / edge_hi = how many doubles at
- * the two ends of the slice the neighbours read (they travel first).  Chunked duplex copies as in
- * csb200_gaxpy.  Returns when y is back in host memory and the neighbours have pulled their lines. */
+ * own_off of the window; edge_lo / edge_hi = how many doubles at the two ends of the slice the
+ * neighbours read (they travel first).  d_y_resident == NULL: y (AT.n host doubles) is read and
+ * written.  d_y_resident != NULL: y accumulates in that device vector and the host vector y, if not
+ * NULL, receives a copy of the result.  Chunked duplex copies as in csb200_gaxpy.  Returns when y is
+ * back in host memory and the neighbours have pulled their lines. */
 CSB200_API int csb200_gaxpy_halo(csb200_mat *AT, csb200_halo *h, const double *x_own, int64_t own_off, int64_t own_len,
-                                 int64_t edge_lo, int64_t edge_hi, double *y);
+                                 int64_t edge_lo, int64_t edge_hi, double *y, double *d_y_resident);
 CSB200_API int csb200_halo_status(csb200_halo *h, int *timed_out);         /* 1: a neighbour never showed up (2 s) */
 CSB200_API int csb200_halo_free(csb200_halo *h);
 

@@ -78,6 +78,19 @@ for fused in (False, True):
             ok &= same
             if not same:
                 say(f"halo host step {step}: max err {np.abs(hy.numpy() - y_ref[r0:r1]).max():.3e}")
+        # y resident on the device, the host gets a copy of the result
+        y_dev = torch.from_numpy(y_ref[r0:r1].copy()).cuda()
+        hy = torch.zeros(r1 - r0, dtype=torch.float64).pin_memory()
+        for step in range(2):
+            xg = rng.standard_normal(n)
+            hx = torch.from_numpy(xg[r0:r1].copy()).pin_memory()
+            sh.step_host(hx, hy, y_dev)
+            orc.cs_gaxpy(A, xg, y_ref)
+            same = np.array_equal(hy.numpy().view(np.int64), y_ref[r0:r1].view(np.int64)) and \
+                np.array_equal(y_dev.cpu().numpy().view(np.int64), y_ref[r0:r1].view(np.int64))
+            ok &= same
+            if not same:
+                say(f"halo host step {step} (y resident): max err {np.abs(hy.numpy() - y_ref[r0:r1]).max():.3e}")
         ok &= not sh.halo.timed_out()
     dist.barrier()
     if fused:
