@@ -219,9 +219,11 @@ class DeviceMatrix(object):
 def force_transpose_path(path: Optional[str]):
     """Tests / benchmarks: None or "auto" = automatic choice, "radix" = always the stable radix sort,
     "bucket" = automatic choice without the one-pass mirror path, "bucket_slab" = the same with the
-    partition and the sort interleaved in L2-sized slabs (measured slower; A/B measurements)."""
+    partition and the sort interleaved in L2-sized slabs (measured slower; A/B measurements),
+    "bucket_fused" = partition and sort in one persistent launch, a bucket sorted by the CTA that
+    completes it (measured slower as well)."""
     _lib.check(_lib.lib().csb200_transpose_force_path({None: 0, "auto": 0, "radix": 1, "bucket": 2,
-                                                       "bucket_slab": 3}[path]))
+                                                       "bucket_slab": 3, "bucket_fused": 4}[path]))
 
 
 def last_transpose_path() -> str:

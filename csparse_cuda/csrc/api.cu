@@ -474,7 +474,7 @@ int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
 
 int csb200_transpose_force_path(int path)
 {
-    if (path < 0 || path > 3) return set_error(CSB200_ERR_ARG, "bad transpose path");
+    if (path < 0 || path > 4) return set_error(CSB200_ERR_ARG, "bad transpose path");
     tls().force_transpose = path;
     return CSB200_OK;
 }

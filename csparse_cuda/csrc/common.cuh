@@ -17,7 +17,7 @@ struct ThreadState {
     char err[640] = {0};
     int64_t last_flops = 0;
     // path switches of the tests / benchmarks (csb200_*_force_path): per thread, like the stream
-    int force_transpose = 0;          // 1: always the radix sort, 2: automatic choice without the mirror path, 3: 2 in L2-sized slabs
+    int force_transpose = 0;          // 1: always the radix sort, 2: automatic choice without the mirror path, 3: 2 in L2-sized slabs, 4: 2 fused into one persistent launch
     int multiply_ordered = 0;         // 1: always the reference's discovery order
     int multiply_blocked_version = 0; // 2 / 3: which blocked numeric kernel (0 = default)
     int multiply_templates = 0;       // pattern-class path: 0 automatic, 1 off, 2 on at any size, 3 like 2 without the lane-per-column kernel

@@ -628,16 +628,21 @@ k_spmv_long(int n_items, const int4 *__restrict__ items, const csi *__restrict__
         double acc[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) acc[u] = 0.0;
-        int p = im.x + lane;
-        for (; p + 32 * (UNR - 1) < im.y; p += 32 * UNR) {  // UNR independent gathers in flight per lane
+        // UNR independent gathers in flight per lane all the way: the last round is predicated instead
+        // of falling back to one entry at a time (the kernel is latency bound: long scoreboard 90 per issue)
+        for (int p = im.x + lane; p < im.y; p += 32 * UNR) {
             int c[UNR];
             double v[UNR];
 #pragma unroll
-            for (int u = 0; u < UNR; u++) { c[u] = ldg_stream(col + p + 32 * u); v[u] = ldg_stream(val + p + 32 * u); }
+            for (int u = 0; u < UNR; u++) {
+                const bool ok = p + 32 * u < im.y;
+                c[u] = ok ? ldg_stream(col + p + 32 * u) : -1;
+                v[u] = ok ? ldg_stream(val + p + 32 * u) : 0.0;
+            }
 #pragma unroll
-            for (int u = 0; u < UNR; u++) acc[u] = __dadd_rn(acc[u], __dmul_rn(v[u], __ldg(x + c[u])));
+            for (int u = 0; u < UNR; u++)
+                if (c[u] >= 0) acc[u] = __dadd_rn(acc[u], __dmul_rn(v[u], __ldg(x + c[u])));
         }
-        for (; p < im.y; p += 32) acc[0] = __dadd_rn(acc[0], __dmul_rn(ldg_stream(val + p), __ldg(x + ldg_stream(col + p))));
         double s = acc[0];
 #pragma unroll
         for (int u = 1; u < UNR; u++) s = __dadd_rn(s, acc[u]);
@@ -670,15 +675,21 @@ k_spmv_mid(int n_mid, const int *__restrict__ mid_list, const csi *__restrict__ 
     if (gi < n_mid) {
         r = mid_list[gi];
         const int e = rowptr[r + 1];
-        int p = rowptr[r] + sub;
         double s2 = 0.0;
-        for (; p + 8 < e; p += 16) {                        // two gathers in flight per lane
-            const int c0 = col[p], c1 = col[p + 8];
-            const double v0 = val[p], v1 = val[p + 8];
-            s = __dadd_rn(s, __dmul_rn(v0, __ldg(x + c0)));
-            s2 = __dadd_rn(s2, __dmul_rn(v1, __ldg(x + c1)));
+        for (int p = rowptr[r] + sub; p < e; p += 32) {     // four predicated gathers in flight per lane
+            int c[4];
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const bool ok = p + 8 * u < e;
+                c[u] = ok ? col[p + 8 * u] : -1;
+                v[u] = ok ? val[p + 8 * u] : 0.0;
+            }
+            if (c[0] >= 0) s = __dadd_rn(s, __dmul_rn(v[0], __ldg(x + c[0])));
+            if (c[1] >= 0) s2 = __dadd_rn(s2, __dmul_rn(v[1], __ldg(x + c[1])));
+            if (c[2] >= 0) s = __dadd_rn(s, __dmul_rn(v[2], __ldg(x + c[2])));
+            if (c[3] >= 0) s2 = __dadd_rn(s2, __dmul_rn(v[3], __ldg(x + c[3])));
         }
-        if (p < e) s = __dadd_rn(s, __dmul_rn(val[p], __ldg(x + col[p])));
         s = __dadd_rn(s, s2);
     }
 #pragma unroll
@@ -858,8 +869,9 @@ int spmv_run(csb200_mat *AT, const double *d_x, double *d_y)
         CSB_CUDA(cudaEventRecord(ss.fork, s));
         CSB_CUDA(cudaStreamWaitEvent(ss.side, ss.fork, 0));
         if (pl->n_items > 0) {
-            // four gathers in flight per lane, eight CTAs per SM (eight in flight / 4-12 CTAs: 1.18-1.28 ms, no better)
-            const int grid = min(ceil_div(pl->n_items, 8), sm_count() * 8);
+            // four predicated gathers in flight per lane, twelve CTAs per SM (4 or 8 in flight x 4..16 CTAs:
+            // 1.136 .. 1.146 ms on R-MAT 2^24 -- flat; an L2 evict-first policy on the streamed entries: no change)
+            const int grid = min(ceil_div(pl->n_items, 8), sm_count() * 12);
             k_spmv_long<4><<<grid, 256, 0, s>>>(pl->n_items, pl->items, AT->i, AT->x, d_x, pl->partial);
             CSB_LAUNCHED();
             k_long_fix<<<ceil_div(pl->n_long, 256), 256, 0, s>>>(pl->n_long, pl->long_list, pl->long_ptr, pl->partial, d_y);

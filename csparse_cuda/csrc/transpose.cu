@@ -139,16 +139,20 @@ k_bucket_hist(const csi *__restrict__ Ai, long long nnz, int log_rb, int *__rest
 // inside the tile come from shared-memory counters over the tile's bucket window;
 // one global atomic per (tile, bucket) reserves the slots, so the global atomics
 // are few and all in flight together.
+// `arrived` (fused kernel only): per bucket, how many of its entries have been WRITTEN; the tile that
+// brings a bucket to its full size lists it in ready[] (shared memory) -- that bucket can be sorted now,
+// and its share of the intermediate is still in L2.
 template <bool VALUES>
-__global__ void __launch_bounds__(TR_THREADS, 4)
-k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
-            long long nnz, const int *__restrict__ tile_col, int log_rb, int colbits, int *__restrict__ bfill,
-            int *__restrict__ ikey, double *__restrict__ ival, int tile0)
+__device__ __forceinline__ void
+partition_tile(const int t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+               long long nnz, const int *__restrict__ tile_col, int log_rb, int colbits, int *__restrict__ bfill,
+               int *__restrict__ ikey, double *__restrict__ ival,
+               int *__restrict__ arrived, const int *__restrict__ bstart, int *ready, int *nready)
 {
     __shared__ int sAp[PT_SMEM_COLS];
     __shared__ int cnt[HIST_WIN];
+    __shared__ unsigned short cnt_own[HIST_WIN];   // fused kernel: this tile's entries per bucket (<= PT_TILE; cnt becomes the base)
     __shared__ int s_red[16];
-    const int t = tile0 + blockIdx.x;
     const long long p_begin = (long long)t * PT_TILE;
     const long long p_end = min(nnz, p_begin + PT_TILE);
     const int j_first = tile_col[t];
@@ -216,6 +220,7 @@ k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double
         __syncthreads();
         for (int k = threadIdx.x; k < win; k += TR_THREADS) {
             const int c = cnt[k];
+            if (arrived) cnt_own[k] = (unsigned short)c;
             if (c) cnt[k] = atomicAdd(&bfill[bmin + k], c);      // cnt becomes the reserved base
         }
         __syncthreads();
@@ -230,6 +235,29 @@ k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double
             if (VALUES) ival[pos] = vals[k];
         }
     }
+    if (arrived) {                                   // windowed is guaranteed by the caller (no wide tiles)
+        __threadfence();                             // this tile's entries are visible before they are counted
+        __syncthreads();
+        for (int k = threadIdx.x; k < win; k += TR_THREADS) {
+            const int c = cnt_own[k];
+            if (c) {
+                const int b = bmin + k;
+                const int before = atomicAdd(&arrived[b], c);
+                if (before + c == bstart[b + 1] - bstart[b]) ready[atomicAdd(nready, 1)] = b;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool VALUES>
+__global__ void __launch_bounds__(TR_THREADS, 4)
+k_partition(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+            long long nnz, const int *__restrict__ tile_col, int log_rb, int colbits, int *__restrict__ bfill,
+            int *__restrict__ ikey, double *__restrict__ ival, int tile0)
+{
+    partition_tile<VALUES>(tile0 + (int)blockIdx.x, Ap, Ai, Ax, nnz, tile_col, log_rb, colbits, bfill, ikey, ival,
+                           nullptr, nullptr, nullptr, nullptr);
 }
 
 // ---- order repair helpers ------------------------------------------------------------
@@ -475,40 +503,44 @@ k_bucket_sort(int m, int log_rb, int colbits, int nbuckets, const int *__restric
 // independent pipelines.  Each warp walks its own sequence of buckets and has the row fields
 // of the NEXT bucket in flight while it works on the current one.  Only (column, source slot)
 // pairs are staged; values are gathered from the bucket (L1/L2-resident) on output.
-template <bool VALUES>
-__global__ void __launch_bounds__(WB_WARPS * 32, 4)
-k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__restrict__ bstart,
-                   const int *__restrict__ ikey, const double *__restrict__ ival,
-                   const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
-                   csi *__restrict__ Cp, csi *Ci, double *Cx, int b0, int b1)
+// One warp, a sequence of buckets bucket_at(first), bucket_at(first + stride), ... < count.  CG: the
+// intermediate was written by other CTAs of this same launch (fused kernel): read it from L2.
+template <bool VALUES, bool CG, class BucketAt>
+__device__ __forceinline__ void
+warp_sort_buckets(const int first, const int stride, const int count, BucketAt bucket_at, unsigned char *mine,
+                  int m, int log_rb, int colbits, int nbuckets, const int *__restrict__ bstart,
+                  const int *ikey, const double *ival,
+                  const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+                  csi *__restrict__ Cp, csi *Ci, double *Cx)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned char *mine = smem + wid * WB_WARP_BYTES;
+    auto LDK = [](const int *q) { return CG ? __ldcg(q) : *q; };
+    auto LDV = [](const double *q) { return CG ? __ldcg(q) : *q; };
+    const int lane = threadIdx.x & 31;
     int *scol = reinterpret_cast<int *>(mine);
     int *cnt = scol + WB_CAP;                      // WB_RB_MAX
     int *start = cnt + WB_RB_MAX;                  // WB_RB_MAX + 1
     unsigned short *sidx = reinterpret_cast<unsigned short *>(start + WB_RB_MAX + 8);
-    const int nwarps = gridDim.x * WB_WARPS;
     const int rb = 1 << log_rb;
     const int colmask = (1 << colbits) - 1;
 
-    int b = b0 + blockIdx.x * WB_WARPS + wid;          // this launch sorts the buckets [b0, b1)
-    if (b >= b1) return;
+    int idx = first;                                   // position in the sequence of buckets bucket_at(0 .. count)
+    if (idx >= count) return;
+    int b = bucket_at(idx);
     // prologue: bounds and row fields of the first bucket
     int base = bstart[b], nb = bstart[b + 1] - base;
     int rows[WB_EPT];
 #pragma unroll
     for (int k = 0; k < WB_EPT; k++) {
         const int e = lane + k * 32;
-        rows[k] = (e < nb && nb <= WB_CAP) ? ikey[base + e] : 0;      // packed (local row, column) words
+        rows[k] = (e < nb && nb <= WB_CAP) ? LDK(ikey + base + e) : 0;      // packed (local row, column) words
     }
-    while (b < b1) {
+    while (idx < count) {
         const int R0 = b << log_rb;
         const int nrows = min(rb, m - R0);
-        const int bn = b + nwarps;                 // next bucket of this warp
+        const int idxn = idx + stride;             // next bucket of this warp
+        const int bn = idxn < count ? bucket_at(idxn) : 0;
         int nbase = 0, nnb = 0;
-        if (bn < b1) { nbase = bstart[bn]; nnb = bstart[bn + 1] - nbase; }
+        if (idxn < count) { nbase = bstart[bn]; nnb = bstart[bn + 1] - nbase; }
 
         if (nb <= WB_CAP) {                        // larger buckets are k_bucket_big's job
             for (int k = lane; k < WB_RB_MAX; k += 32) cnt[k] = 0;
@@ -523,7 +555,7 @@ k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__re
 #pragma unroll
             for (int k = 0; k < WB_EPT; k++) {
                 const int e = lane + k * 32;
-                rows[k] = (e < nnb && nnb <= WB_CAP) ? ikey[nbase + e] : 0;
+                rows[k] = (e < nnb && nnb <= WB_CAP) ? LDK(ikey + nbase + e) : 0;
             }
             __syncwarp();
             {   // exclusive scan of cnt[0..WB_RB_MAX) -> start[0..WB_RB_MAX]; 4 consecutive rows per lane
@@ -545,7 +577,7 @@ k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__re
                 const int e = lane + k * 32;
                 if (e < nb) {
                     const int pos = start[slot[k] >> 16] + (slot[k] & 0xffff);
-                    scol[pos] = ikey[base + e] & colmask;            // coalesced re-read (L1 hit)
+                    scol[pos] = LDK(ikey + base + e) & colmask;            // coalesced re-read (L1 hit)
                     sidx[pos] = (unsigned short)e;
                 }
             }
@@ -583,7 +615,7 @@ k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__re
             if (b == nbuckets - 1 && lane == 0) Cp[m] = base + nb;
             for (int t = lane; t < nb; t += 32) {
                 Ci[base + t] = scol[t];
-                if (VALUES) Cx[base + t] = ival[base + sidx[t]];
+                if (VALUES) Cx[base + t] = LDV(ival + base + sidx[t]);
             }
             if (VALUES && __any_sync(0xffffffffu, any_tie)) {
                 // duplicates of one (i,j) pair: their values go out in A's storage order
@@ -603,10 +635,59 @@ k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__re
 #pragma unroll
             for (int k = 0; k < WB_EPT; k++) {
                 const int e = lane + k * 32;
-                rows[k] = (e < nnb && nnb <= WB_CAP) ? ikey[nbase + e] : 0;
+                rows[k] = (e < nnb && nnb <= WB_CAP) ? LDK(ikey + nbase + e) : 0;
             }
         }
-        b = bn; base = nbase; nb = nnb;
+        idx = idxn; b = bn; base = nbase; nb = nnb;
+    }
+}
+
+
+template <bool VALUES>
+__global__ void __launch_bounds__(WB_WARPS * 32, 4)
+k_bucket_sort_warp(int m, int log_rb, int colbits, int nbuckets, const int *__restrict__ bstart,
+                   const int *__restrict__ ikey, const double *__restrict__ ival,
+                   const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+                   csi *__restrict__ Cp, csi *Ci, double *Cx, int b0, int b1)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wid = threadIdx.x >> 5;
+    // this launch sorts the buckets [b0, b1), strided over all warps of the grid
+    warp_sort_buckets<VALUES, false>(blockIdx.x * WB_WARPS + wid, gridDim.x * WB_WARPS, b1 - b0,
+                                     [b0](int i) { return b0 + i; }, smem + wid * WB_WARP_BYTES,
+                                     m, log_rb, colbits, nbuckets, bstart, ikey, ival, Ap, Ai, Ax, Cp, Ci, Cx);
+}
+
+// ---- partition and sort in ONE persistent launch (warp-per-bucket matrices) -----------------------
+// Tiles are claimed in order through a ticket.  After a CTA has written a tile's entries it adds them
+// to the buckets' arrival counters; the tile that completes a bucket lists it, and the CTA's eight warps
+// sort the listed buckets at once -- their share of the intermediate was written moments ago and is read
+// back from L2, not HBM.  Nothing waits for anything: a bucket is sorted by whoever completes it.
+template <bool VALUES>
+__global__ void __launch_bounds__(TR_THREADS, 3)
+k_partition_sort(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *__restrict__ Ax,
+                 long long nnz, int ntiles, const int *__restrict__ tile_col, int m, int log_rb, int colbits, int nbuckets,
+                 int *__restrict__ bfill, const int *__restrict__ bstart, int *__restrict__ arrived, unsigned *ticket,
+                 int *ikey, double *ival, csi *__restrict__ Cp, csi *Ci, double *Cx)
+{
+    extern __shared__ __align__(16) unsigned char smem[];        // WB_WARPS x WB_WARP_BYTES
+    __shared__ int ready[PT_TILE];                               // a tile completes at most one bucket per entry
+    __shared__ int nready;
+    __shared__ unsigned s_tile;
+    const int wid = threadIdx.x >> 5;
+    while (true) {
+        if (threadIdx.x == 0) { s_tile = atomicAdd(ticket, 1u); nready = 0; }
+        __syncthreads();
+        const unsigned t = s_tile;
+        if (t >= (unsigned)ntiles) break;
+        partition_tile<VALUES>((int)t, Ap, Ai, Ax, nnz, tile_col, log_rb, colbits, bfill, ikey, ival,
+                               arrived, bstart, ready, &nready);
+        __threadfence();                                        // acquire side of the arrival counters
+        const int nr = nready;
+        if (nr > 0)
+            warp_sort_buckets<VALUES, true>(wid, WB_WARPS, nr, [&](int i) { return ready[i]; }, smem + wid * WB_WARP_BYTES,
+                                            m, log_rb, colbits, nbuckets, bstart, ikey, ival, Ap, Ai, Ax, Cp, Ci, Cx);
+        __syncthreads();                                        // ready[] is reused by the next tile
     }
 }
 
@@ -929,6 +1010,18 @@ k_mirror(const csi *__restrict__ Ap, const csi *__restrict__ Ai, const double *_
     }
 }
 
+// fused launch: a bucket without entries is completed by nobody; its rows' column pointers are set here
+__global__ void k_empty_buckets(int m, int log_rb, int nbuckets, const int *__restrict__ bstart, csi *__restrict__ Cp)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    const int base = bstart[b];
+    if (bstart[b + 1] != base) return;
+    const int R0 = b << log_rb, nrows = min(1 << log_rb, m - R0);
+    for (int r = 0; r < nrows; r++) Cp[R0 + r] = base;
+    if (b == nbuckets - 1) Cp[m] = base;
+}
+
 // ---- host side -------------------------------------------------------------------
 thread_local int t_last_path = 0;   // 1 mirror, 2 bucket sort, 3 radix sort, 0 trivial
 int transpose_last_path() { return t_last_path; }
@@ -1095,6 +1188,35 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
     }
     TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
     TR_CUDA(cudaFuncSetAttribute(k_bucket_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+    // opt-in (force_path 4), warp-per-bucket matrices: partition and sort in ONE persistent launch
+    // (k_partition_sort); the second hop reads L2.  MEASURED: 1.94 ms against 1.35 ms for the two whole
+    // passes on lap2d 4096^2 -- three CTAs per SM at 80 registers + 72 KB, and a CTA sorts its ~13
+    // completed buckets with eight warps only after its tile is partitioned, where the two kernels
+    // each run at their own best occupancy.  Not the default.
+    const bool fused = warp_path && h_ct[0] == 0 && slabs.size() == 1 && tls().force_transpose == 4;
+    if (fused) {
+        DevBuf<int> arrived;
+        DevBuf<unsigned> ticket;
+        if ((st = arrived.alloc((size_t)nbuckets + 1)) || (st = ticket.alloc(1))) return fail(st);
+        TR_CUDA(cudaMemsetAsync(arrived.ptr, 0, ((size_t)nbuckets + 1) * sizeof(int), s));
+        TR_CUDA(cudaMemsetAsync(ticket.ptr, 0, sizeof(unsigned), s));
+        constexpr int smem = WB_WARPS * WB_WARP_BYTES;
+        TR_CUDA(cudaFuncSetAttribute(k_partition_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        TR_CUDA(cudaFuncSetAttribute(k_partition_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (has_x) {
+            const int grid = min(ntiles, resident_grid(k_partition_sort<true>, TR_THREADS, smem));
+            k_partition_sort<true><<<grid, TR_THREADS, smem, s>>>(A->p, A->i, A->x, nnz, ntiles, tile_col.ptr, m, log_rb, colbits, nbuckets,
+                                                                  bfill.ptr, bstart.ptr, arrived.ptr, ticket.ptr, ikey.ptr, ival.ptr, C->p, C->i, C->x);
+        } else {
+            const int grid = min(ntiles, resident_grid(k_partition_sort<false>, TR_THREADS, smem));
+            k_partition_sort<false><<<grid, TR_THREADS, smem, s>>>(A->p, A->i, nullptr, nnz, ntiles, tile_col.ptr, m, log_rb, colbits, nbuckets,
+                                                                   bfill.ptr, bstart.ptr, arrived.ptr, ticket.ptr, ikey.ptr, nullptr, C->p, C->i, nullptr);
+        }
+        TR_LAUNCHED();
+        k_empty_buckets<<<ceil_div(nbuckets, 256), 256, 0, s>>>(m, log_rb, nbuckets, bstart.ptr, C->p);
+        TR_LAUNCHED();
+        slabs.clear();
+    }
     int tile0 = 0, b0 = 0;
     for (const Slab &sl : slabs) {
         const int nt = sl.tile_end - tile0;

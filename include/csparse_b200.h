@@ -100,7 +100,8 @@ CSB200_API int csb200_transpose(const csb200_mat *A, int values, csb200_mat **C)
  * else the two-level bucket sort, or the stable radix sort when power-law rows overflow the
  * buckets), 1 = always the radix sort, 2 = automatic without the mirror path, 3 = like 2 with the
  * bucket sort's partition and sort phases interleaved in L2-sized slabs (measured slower than two
- * whole passes); for tests and benchmarks */
+ * whole passes), 4 = like 2 with partition and sort in one persistent launch in which a bucket is
+ * sorted by the CTA that completes it (short rows only; measured slower too); for tests and benchmarks */
 CSB200_API int csb200_transpose_force_path(int path);
 /* the path the calling thread's last transpose took: 1 mirror, 2 bucket sort, 3 radix sort,
  * 0 trivial (empty matrix) */

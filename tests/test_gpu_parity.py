@@ -113,13 +113,14 @@ def test_transpose_synthetic(gen):
 
 
 def test_transpose_slab_schedule():
-    """The opt-in slab schedule of the bucket sort (partition and sort interleaved per L2-sized slab,
-    csb200_transpose_force_path(3)) needs >= 4 M entries to cut anything: same bits as the oracle."""
+    """The opt-in schedules of the bucket sort -- partition and sort interleaved per L2-sized slab
+    (csb200_transpose_force_path(3), needs >= 4 M entries to cut anything) and fused into one persistent
+    launch (force_path 4): same bits as the oracle."""
     m, n, p, i, x = synth.lap2d(1024)
     x = np.random.default_rng(8).standard_normal(len(i))
     R = orc.cs_transpose(orc.csc(m, n, p, i, x), True)
     dA = cc.from_arrays(m, n, p, i, x)
-    for path in ("bucket_slab", "bucket"):
+    for path in ("bucket_slab", "bucket_fused", "bucket"):
         cc.force_transpose_path(path)
         try:
             cp, ci, cx = cc.cs_transpose(dA, True).arrays()

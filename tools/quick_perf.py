@@ -61,14 +61,14 @@ def run_matrix(tag, m, n, p, i, x, do_mul, plans=(None,)):
     def tr():
         holder["c"] = cc.cs_transpose(dA, True)
     if ONLY != "multiply":
-        for path in (None, "bucket", "bucket_slab"):
+        for path in (None, "bucket", "bucket_fused"):
             cc.force_transpose_path(path)
             try:
                 med, best = timeit(tr, 2, 7)
                 took = cc.last_transpose_path()
             finally:
                 cc.force_transpose_path(None)
-            report(f"{tag} cs_transpose[{took}{' slabs' if path == 'bucket_slab' else ''}]", synth.transpose_bytes(m, n, nnz), med, best)
+            report(f"{tag} cs_transpose[{took}{' fused' if path == 'bucket_fused' else ''}]", synth.transpose_bytes(m, n, nnz), med, best)
             if took == "radix":
                 break
     holder.clear()
