@@ -21,6 +21,7 @@
 // (sorted keys written and searched); ceil(log2(nkeys) / 8) passes.
 #include "common.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace csb {
 
@@ -263,6 +264,195 @@ k_rs_pass(long long nnz, int shift,
     }
 }
 
+// ---- the same pass with the payload routed through shared memory -------------------------------------
+// k_rs_pass above routes only the tile's PERMUTATION through shared memory and gathers every record
+// from global memory in destination order: one 32-byte sector per entry through L1 (two for the first
+// pass, whose key and value live in separate arrays) -- the kernel ran at 80 % of the L1 data stage and
+// 45 % of the HBM rate.  Here a thread keeps the records it loaded (coalesced, once) in registers,
+// parks them in shared memory at their position in the tile's sorted order, and the tile leaves as
+// consecutive 16-byte records of every digit run.  Tile = 4096 entries (64 KB of records), two CTAs per SM.
+constexpr int RS2_EPT = 8;
+constexpr int RS2_TILE = RS_THREADS * RS2_EPT;
+constexpr int RS2_SEG = 32 * RS2_EPT;
+template <bool VALUES>
+constexpr int rs2_smem() { return RS_WARPS * RS_BINS * 4 + RS_BINS * 8 + RS_BINS * 4 + 64 + RS2_TILE * (VALUES ? 16 : 8); }
+
+template <int SRC, int DST, bool VALUES>
+__global__ void __launch_bounds__(RS_THREADS, 2)
+k_rs_pass_s(long long nnz, int shift,
+            const int *__restrict__ key_in, const int *__restrict__ a_in, const double *__restrict__ v_in,
+            const void *__restrict__ rec_in, const csi *__restrict__ Ap, int ncols,
+            int *__restrict__ key_out, int *__restrict__ a_out, double *__restrict__ v_out, void *__restrict__ rec_out,
+            const unsigned long long *__restrict__ digit_start, volatile unsigned long long *status, unsigned *ticket)
+{
+    using Rec = typename std::conditional<VALUES, RsRec, RsRecP>::type;
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    int (*cnt)[RS_BINS] = reinterpret_cast<int (*)[RS_BINS]>(rs_smem);
+    long long *gbase = reinterpret_cast<long long *>(rs_smem + RS_WARPS * RS_BINS * 4);
+    int *toff = reinterpret_cast<int *>(rs_smem + RS_WARPS * RS_BINS * 4 + RS_BINS * 8);
+    int *misc = toff + RS_BINS;                         // [0..7] wtot, [8] tile, [9..10] first / last column, 16 ints in all
+    Rec *srec = reinterpret_cast<Rec *>(rs_smem + RS_WARPS * RS_BINS * 4 + RS_BINS * 8 + RS_BINS * 4 + 64);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt = lanemask_lt();
+    if (tid == 0) misc[8] = (int)atomicAdd(ticket, 1u);
+    for (int k = tid; k < RS_WARPS * RS_BINS; k += RS_THREADS) (&cnt[0][0])[k] = 0;
+    __syncthreads();
+    const unsigned tile = (unsigned)misc[8];
+    const long long base = (long long)tile * RS2_TILE;
+    const long long seg = base + wid * RS2_SEG;
+    const int tile_n = (int)min((long long)RS2_TILE, nnz - base);
+    const Rec *rin = reinterpret_cast<const Rec *>(rec_in);
+    if (SRC == 2 && tid < 2) {
+        const long long pe = tid == 0 ? base : base + tile_n - 1;     // columns holding the tile's first / last position
+        misc[9 + tid] = upper_row(Ap, 0, ncols, (int)pe);
+    }
+
+    // ---- the thread's records, loaded once, coalesced ---------------------------------------------------
+    int key[RS2_EPT], pay[RS2_EPT];
+    double val[RS2_EPT];
+#pragma unroll
+    for (int u = 0; u < RS2_EPT; u++) {
+        const long long e = seg + u * 32 + lane;
+        key[u] = -1; pay[u] = 0; val[u] = 0.0;
+        if (e < nnz) {
+            if (SRC == 1) {
+                const Rec r = rin[e];
+                key[u] = r.key; pay[u] = r.a;
+                if constexpr (VALUES) val[u] = r.v;
+            } else {
+                key[u] = key_in[e];
+                if (SRC == 0) pay[u] = a_in[e];
+                if (VALUES) val[u] = v_in[e];
+            }
+        }
+    }
+    // ---- ranks in source order (as in k_rs_pass) ----------------------------------------------------------
+    int rank[RS2_EPT];
+#pragma unroll
+    for (int u = 0; u < RS2_EPT; u++) {
+        const bool valid = key[u] >= 0;
+        const int d = valid ? ((key[u] >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        int r = 0;
+        if (valid && lane == leader) { r = cnt[wid][d]; cnt[wid][d] = r + __popc(peers); }
+        rank[u] = __shfl_sync(0xffffffffu, r, leader) + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- tile counts -> look-back -> global base of every digit ------------------------------------------------
+    int my_total = 0;
+    if (tid < RS_BINS) {
+        const int d = tid;
+        int sum = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) { const int c = cnt[w][d]; cnt[w][d] = sum; sum += c; }
+        my_total = sum;
+        volatile unsigned long long *mine = status + (size_t)tile * RS_BINS + d;
+        long long prefix = 0;
+        if (tile == 0) {
+            *mine = RS_PREFIX | (unsigned long long)sum;
+        } else {
+            *mine = RS_AGG | (unsigned long long)sum;
+            for (long long t = (long long)tile - 1; t >= 0; t--) {
+                volatile unsigned long long *pst = status + (size_t)t * RS_BINS + d;
+                unsigned long long w = *pst;
+                while ((w >> 62) == 0) w = *pst;
+                prefix += (long long)(w & 0xffffffffull);
+                if (w & RS_PREFIX) break;
+            }
+            *mine = RS_PREFIX | (unsigned long long)(prefix + sum);
+        }
+        gbase[d] = (long long)digit_start[d] + prefix;
+    }
+    {
+        int inc = my_total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (tid < RS_BINS && lane == 31) misc[wid] = inc;
+        __syncthreads();
+        if (tid < RS_BINS) {
+            int before = inc - my_total;
+            for (int w = 0; w < wid; w++) before += misc[w];
+            toff[tid] = before;
+        }
+    }
+    __syncthreads();
+    // ---- position of every record inside the tile's sorted order (the counters are free afterwards) ------------
+    int tpos[RS2_EPT];
+#pragma unroll
+    for (int u = 0; u < RS2_EPT; u++) {
+        const int d = (key[u] >> shift) & (RS_BINS - 1);
+        tpos[u] = key[u] >= 0 ? toff[d] + cnt[wid][d] + rank[u] : 0;
+    }
+    __syncthreads();
+    if (SRC == 2) {
+        // the column of every entry: marks of the non-empty columns that start inside the tile, carried
+        // forward by a running maximum (16-bit offsets from the tile's first column, in the counters' space)
+        const int j_lo = misc[9], j_hi = misc[10];
+        unsigned short *colof = reinterpret_cast<unsigned short *>(&cnt[0][0]);
+        static_assert(RS_WARPS * RS_BINS * sizeof(int) >= RS2_TILE * sizeof(unsigned short), "the column table fits the counters' space");
+        if (j_hi - j_lo < 65535) {
+#pragma unroll
+            for (int k = 0; k < RS2_EPT; k++) colof[k * RS_THREADS + tid] = 0;
+            __syncthreads();
+            for (int j = j_lo + 1 + tid; j <= j_hi; j += RS_THREADS) {
+                const int a0 = Ap[j];
+                const long long q = (long long)a0 - base;
+                if (q >= 0 && q < tile_n && Ap[j + 1] > a0) colof[(int)q] = (unsigned short)(j - j_lo);
+            }
+            __syncthreads();
+            int v[RS2_EPT];
+            int run = 0;
+#pragma unroll
+            for (int k = 0; k < RS2_EPT; k++) { run = max(run, (int)colof[tid * RS2_EPT + k]); v[k] = run; }
+            int inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = max(inc, t); }
+            if (lane == 31) misc[wid] = inc;             // 16 warps: misc[0..15]... only [0..7] are free: see below
+            __syncthreads();
+            int before = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) before = 0;
+            for (int w = 0; w < wid; w++) before = max(before, misc[w]);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < RS2_EPT; k++) colof[tid * RS2_EPT + k] = (unsigned short)max(v[k], before);
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < RS2_EPT; u++) pay[u] = j_lo + (int)colof[wid * RS2_SEG + u * 32 + lane];
+        } else {
+#pragma unroll
+            for (int u = 0; u < RS2_EPT; u++)
+                if (key[u] >= 0) pay[u] = upper_row(Ap, j_lo, j_hi, (int)(seg + u * 32 + lane));
+        }
+    }
+    // ---- park the records at their sorted positions, then leave in order ---------------------------------------
+#pragma unroll
+    for (int u = 0; u < RS2_EPT; u++) {
+        if (key[u] < 0) continue;
+        Rec r;
+        r.key = key[u]; r.a = pay[u];
+        if constexpr (VALUES) r.v = val[u];
+        srec[tpos[u]] = r;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS2_EPT; k++) {
+        const int tp = k * RS_THREADS + tid;
+        if (tp >= tile_n) continue;
+        const Rec r = srec[tp];
+        const int d = (r.key >> shift) & (RS_BINS - 1);
+        const long long pos = gbase[d] + (tp - toff[d]);
+        if (DST == 1) {
+            reinterpret_cast<Rec *>(rec_out)[pos] = r;
+        } else {
+            key_out[pos] = r.key;
+            a_out[pos] = r.a;
+            if constexpr (VALUES) v_out[pos] = r.v;
+        }
+    }
+}
+
 // Cp[r] = number of entries with key < r, r = 0..nkeys (keys sorted ascending)
 __global__ void k_rs_bounds(const int *__restrict__ keys, long long nnz, int nkeys, csi *__restrict__ Cp)
 {
@@ -286,7 +476,8 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
     int bits = 1;
     while (bits < 31 && (1LL << bits) < (long long)nkeys) bits++;
     const int npasses = (bits + 7) / 8;
-    const int ntiles = ceil_div(nnz, RS_TILE);
+    static const bool staged = getenv("CSB200_RS_STAGED") && atoi(getenv("CSB200_RS_STAGED"));   // A/B switch: measured slower (12.8 vs 11.3 ms on R-MAT 2^24), off by default
+    const int ntiles = ceil_div(nnz, staged ? RS2_TILE : RS_TILE);
     const size_t recsz = VALUES ? sizeof(RsRec) : sizeof(RsRecP);
 
     arena_hint((size_t)nnz * 4 + (npasses >= 3 ? 2 : npasses >= 2 ? 1 : 0) * (size_t)nnz * recsz +
@@ -315,8 +506,16 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
         void *rout = last ? nullptr : ((q & 1) ? bufB.ptr : bufA.ptr);
         const unsigned long long *ds = hist.ptr + q * RS_BINS;
 #define RS_LAUNCH(SRC, DST)                                                                       \
-        k_rs_pass<SRC, DST, VALUES><<<ntiles, RS_THREADS, 0, s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
-            keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q)
+        do {                                                                                      \
+            if (staged) {                                                                         \
+                RS_CUDA(cudaFuncSetAttribute(k_rs_pass_s<SRC, DST, VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs2_smem<VALUES>())); \
+                k_rs_pass_s<SRC, DST, VALUES><<<ntiles, RS_THREADS, rs2_smem<VALUES>(), s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
+                    keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q);         \
+            } else {                                                                              \
+                k_rs_pass<SRC, DST, VALUES><<<ntiles, RS_THREADS, 0, s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
+                    keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q);         \
+            }                                                                                     \
+        } while (0)
         if (first && last)      { if (src0 == 0) RS_LAUNCH(0, 0); else RS_LAUNCH(2, 0); }
         else if (first)         { if (src0 == 0) RS_LAUNCH(0, 1); else RS_LAUNCH(2, 1); }
         else if (last)          RS_LAUNCH(1, 0);
