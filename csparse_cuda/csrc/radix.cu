@@ -85,6 +85,46 @@ k_rs_starts(int npasses, unsigned long long *hist)
     }
 }
 
+// Decoupled look-back of one digit: the sum of the counts of the tiles before `tile`.  A walk that
+// reads one predecessor per step is a chain of dependent L2 round trips (the whole CTA waits at the
+// next barrier meanwhile); `lb` statuses are read at once and consumed in order, so a walk of k tiles
+// costs ceil(k / lb) round trips.  A status that is not published yet ends the batch: the walk resumes there.
+constexpr int RS_LB_MAX = 8;
+__device__ __forceinline__ long long rs_look_back(volatile unsigned long long *status, unsigned tile, int d, int lb)
+{
+    long long prefix = 0;
+    long long t = (long long)tile - 1;
+    if (lb <= 1) {                                        // one predecessor per step
+        for (; t >= 0; t--) {
+            volatile unsigned long long *pst = status + (size_t)t * RS_BINS + d;
+            unsigned long long w = *pst;
+            while ((w >> 62) == 0) w = *pst;
+            prefix += (long long)(w & 0xffffffffull);
+            if (w & (2ull << 62)) break;
+        }
+        return prefix;
+    }
+    while (t >= 0) {
+        unsigned long long w[RS_LB_MAX];
+#pragma unroll
+        for (int u = 0; u < RS_LB_MAX; u++)
+            w[u] = (u < lb && t - u >= 0) ? status[(size_t)(t - u) * RS_BINS + d] : (2ull << 62);    // past the first tile: an empty prefix
+        int used = 0;
+        bool done = false;
+#pragma unroll
+        for (int u = 0; u < RS_LB_MAX; u++) {
+            if (done || u != used || u >= lb) continue;
+            if ((w[u] >> 62) == 0) continue;              // not published yet: stop consuming here
+            prefix += (long long)(w[u] & 0xffffffffull);
+            used = u + 1;
+            if (w[u] & RS_PREFIX) done = true;
+        }
+        if (done) break;
+        t -= used;
+    }
+    return prefix;
+}
+
 // SRC: 0 = separate key / a / v arrays, 1 = records, 2 = separate key / v arrays with the
 //      int payload derived as "the column of Ap that holds this position" (cs_transpose)
 // DST: 0 = separate arrays (last pass; the sorted keys are written too), 1 = records
@@ -94,7 +134,7 @@ k_rs_pass(long long nnz, int shift,
           const int *__restrict__ key_in, const int *__restrict__ a_in, const double *__restrict__ v_in,
           const void *__restrict__ rec_in, const csi *__restrict__ Ap, int ncols,
           int *__restrict__ key_out, int *__restrict__ a_out, double *__restrict__ v_out, void *__restrict__ rec_out,
-          const unsigned long long *__restrict__ digit_start, volatile unsigned long long *status, unsigned *ticket)
+          const unsigned long long *__restrict__ digit_start, volatile unsigned long long *status, unsigned *ticket, int lb)
 {
     using Rec = typename std::conditional<VALUES, RsRec, RsRecP>::type;
     __shared__ int cnt[RS_WARPS][RS_BINS];
@@ -158,13 +198,7 @@ k_rs_pass(long long nnz, int shift,
             *mine = RS_PREFIX | (unsigned long long)sum;
         } else {
             *mine = RS_AGG | (unsigned long long)sum;
-            for (long long t = (long long)tile - 1; t >= 0; t--) {
-                volatile unsigned long long *pst = status + (size_t)t * RS_BINS + d;
-                unsigned long long w = *pst;
-                while ((w >> 62) == 0) w = *pst;
-                prefix += (long long)(w & 0xffffffffull);
-                if (w & RS_PREFIX) break;
-            }
+            prefix = rs_look_back(status, tile, d, lb);
             *mine = RS_PREFIX | (unsigned long long)(prefix + sum);
         }
         gbase[d] = (long long)digit_start[d] + prefix;
@@ -271,31 +305,36 @@ k_rs_pass(long long nnz, int shift,
 // 45 % of the HBM rate.  Here a thread keeps the records it loaded (coalesced, once) in registers,
 // parks them in shared memory at their position in the tile's sorted order, and the tile leaves as
 // consecutive 16-byte records of every digit run.  Tile = 4096 entries (64 KB of records), two CTAs per SM.
+#ifndef RS2_THREADS_DEF
+#define RS2_THREADS_DEF 256
+#endif
+constexpr int RS2_THREADS = RS2_THREADS_DEF;        // 256: four CTAs per SM, every thread owns a digit during the look-back
+constexpr int RS2_WARPS = RS2_THREADS / 32;
 constexpr int RS2_EPT = 8;
-constexpr int RS2_TILE = RS_THREADS * RS2_EPT;
+constexpr int RS2_TILE = RS2_THREADS * RS2_EPT;
 constexpr int RS2_SEG = 32 * RS2_EPT;
 template <bool VALUES>
-constexpr int rs2_smem() { return RS_WARPS * RS_BINS * 4 + RS_BINS * 8 + RS_BINS * 4 + 64 + RS2_TILE * (VALUES ? 16 : 8); }
+constexpr int rs2_smem() { return RS2_WARPS * RS_BINS * 4 + RS_BINS * 8 + RS_BINS * 4 + 64 + RS2_TILE * (VALUES ? 16 : 8); }
 
 template <int SRC, int DST, bool VALUES>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS2_THREADS, 1024 / RS2_THREADS)
 k_rs_pass_s(long long nnz, int shift,
             const int *__restrict__ key_in, const int *__restrict__ a_in, const double *__restrict__ v_in,
             const void *__restrict__ rec_in, const csi *__restrict__ Ap, int ncols,
             int *__restrict__ key_out, int *__restrict__ a_out, double *__restrict__ v_out, void *__restrict__ rec_out,
-            const unsigned long long *__restrict__ digit_start, volatile unsigned long long *status, unsigned *ticket)
+            const unsigned long long *__restrict__ digit_start, volatile unsigned long long *status, unsigned *ticket, int lb)
 {
     using Rec = typename std::conditional<VALUES, RsRec, RsRecP>::type;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     int (*cnt)[RS_BINS] = reinterpret_cast<int (*)[RS_BINS]>(rs_smem);
-    long long *gbase = reinterpret_cast<long long *>(rs_smem + RS_WARPS * RS_BINS * 4);
-    int *toff = reinterpret_cast<int *>(rs_smem + RS_WARPS * RS_BINS * 4 + RS_BINS * 8);
+    long long *gbase = reinterpret_cast<long long *>(rs_smem + RS2_WARPS * RS_BINS * 4);
+    int *toff = reinterpret_cast<int *>(rs_smem + RS2_WARPS * RS_BINS * 4 + RS_BINS * 8);
     int *misc = toff + RS_BINS;                         // [0..7] wtot, [8] tile, [9..10] first / last column, 16 ints in all
-    Rec *srec = reinterpret_cast<Rec *>(rs_smem + RS_WARPS * RS_BINS * 4 + RS_BINS * 8 + RS_BINS * 4 + 64);
+    Rec *srec = reinterpret_cast<Rec *>(rs_smem + RS2_WARPS * RS_BINS * 4 + RS_BINS * 8 + RS_BINS * 4 + 64);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned lt = lanemask_lt();
     if (tid == 0) misc[8] = (int)atomicAdd(ticket, 1u);
-    for (int k = tid; k < RS_WARPS * RS_BINS; k += RS_THREADS) (&cnt[0][0])[k] = 0;
+    for (int k = tid; k < RS2_WARPS * RS_BINS; k += RS2_THREADS) (&cnt[0][0])[k] = 0;
     __syncthreads();
     const unsigned tile = (unsigned)misc[8];
     const long long base = (long long)tile * RS2_TILE;
@@ -346,7 +385,7 @@ k_rs_pass_s(long long nnz, int shift,
         const int d = tid;
         int sum = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) { const int c = cnt[w][d]; cnt[w][d] = sum; sum += c; }
+        for (int w = 0; w < RS2_WARPS; w++) { const int c = cnt[w][d]; cnt[w][d] = sum; sum += c; }
         my_total = sum;
         volatile unsigned long long *mine = status + (size_t)tile * RS_BINS + d;
         long long prefix = 0;
@@ -354,13 +393,7 @@ k_rs_pass_s(long long nnz, int shift,
             *mine = RS_PREFIX | (unsigned long long)sum;
         } else {
             *mine = RS_AGG | (unsigned long long)sum;
-            for (long long t = (long long)tile - 1; t >= 0; t--) {
-                volatile unsigned long long *pst = status + (size_t)t * RS_BINS + d;
-                unsigned long long w = *pst;
-                while ((w >> 62) == 0) w = *pst;
-                prefix += (long long)(w & 0xffffffffull);
-                if (w & RS_PREFIX) break;
-            }
+            prefix = rs_look_back(status, tile, d, lb);
             *mine = RS_PREFIX | (unsigned long long)(prefix + sum);
         }
         gbase[d] = (long long)digit_start[d] + prefix;
@@ -391,12 +424,12 @@ k_rs_pass_s(long long nnz, int shift,
         // forward by a running maximum (16-bit offsets from the tile's first column, in the counters' space)
         const int j_lo = misc[9], j_hi = misc[10];
         unsigned short *colof = reinterpret_cast<unsigned short *>(&cnt[0][0]);
-        static_assert(RS_WARPS * RS_BINS * sizeof(int) >= RS2_TILE * sizeof(unsigned short), "the column table fits the counters' space");
+        static_assert(RS2_WARPS * RS_BINS * sizeof(int) >= RS2_TILE * sizeof(unsigned short), "the column table fits the counters' space");
         if (j_hi - j_lo < 65535) {
 #pragma unroll
-            for (int k = 0; k < RS2_EPT; k++) colof[k * RS_THREADS + tid] = 0;
+            for (int k = 0; k < RS2_EPT; k++) colof[k * RS2_THREADS + tid] = 0;
             __syncthreads();
-            for (int j = j_lo + 1 + tid; j <= j_hi; j += RS_THREADS) {
+            for (int j = j_lo + 1 + tid; j <= j_hi; j += RS2_THREADS) {
                 const int a0 = Ap[j];
                 const long long q = (long long)a0 - base;
                 if (q >= 0 && q < tile_n && Ap[j + 1] > a0) colof[(int)q] = (unsigned short)(j - j_lo);
@@ -438,7 +471,7 @@ k_rs_pass_s(long long nnz, int shift,
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < RS2_EPT; k++) {
-        const int tp = k * RS_THREADS + tid;
+        const int tp = k * RS2_THREADS + tid;
         if (tp >= tile_n) continue;
         const Rec r = srec[tp];
         const int d = (r.key >> shift) & (RS_BINS - 1);
@@ -477,6 +510,8 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
     while (bits < 31 && (1LL << bits) < (long long)nkeys) bits++;
     const int npasses = (bits + 7) / 8;
     static const bool staged = getenv("CSB200_RS_STAGED") && atoi(getenv("CSB200_RS_STAGED"));   // A/B switch: measured slower (12.8 vs 11.3 ms on R-MAT 2^24), off by default
+    static const int lb_env = getenv("CSB200_RS_LB") ? atoi(getenv("CSB200_RS_LB")) : 1;    // batched look-back: A/B switch (helps the staged pass only)
+    const int lb = lb_env < 1 ? 1 : (lb_env > RS_LB_MAX ? RS_LB_MAX : lb_env);
     const int ntiles = ceil_div(nnz, staged ? RS2_TILE : RS_TILE);
     const size_t recsz = VALUES ? sizeof(RsRec) : sizeof(RsRecP);
 
@@ -509,11 +544,11 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
         do {                                                                                      \
             if (staged) {                                                                         \
                 RS_CUDA(cudaFuncSetAttribute(k_rs_pass_s<SRC, DST, VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs2_smem<VALUES>())); \
-                k_rs_pass_s<SRC, DST, VALUES><<<ntiles, RS_THREADS, rs2_smem<VALUES>(), s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
-                    keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q);         \
+                k_rs_pass_s<SRC, DST, VALUES><<<ntiles, RS2_THREADS, rs2_smem<VALUES>(), s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
+                    keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q, lb);         \
             } else {                                                                              \
                 k_rs_pass<SRC, DST, VALUES><<<ntiles, RS_THREADS, 0, s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
-                    keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q);         \
+                    keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q, lb);         \
             }                                                                                     \
         } while (0)
         if (first && last)      { if (src0 == 0) RS_LAUNCH(0, 0); else RS_LAUNCH(2, 0); }
