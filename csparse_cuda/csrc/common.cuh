@@ -205,6 +205,23 @@ namespace csb {
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 
+// Lanes holding the same NBITS-bit value as this lane (valid lanes only), from NBITS + 1 ballots.
+// The hardware MATCH.ANY takes ~900 cycles per warp at full occupancy on sm_100 (it was a third of the
+// radix pass's stall samples, profiles/r2_notes.md); ballots issue at full rate and do not depend on
+// the shared-memory chain of the ranking loop, so consecutive rounds overlap.
+template <int NBITS>
+__device__ __forceinline__ unsigned match_bits(int d, bool valid)
+{
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < NBITS; b++) {
+        const bool bit = (d >> b) & 1;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 // streaming (read-once) loads: bypass L1 allocation
 __device__ __forceinline__ int4 ldg_stream(const int4 *p)
 {

@@ -25,7 +25,10 @@
 
 namespace csb {
 
-constexpr int RS_THREADS = 512;
+#ifndef RS_THREADS_DEF
+#define RS_THREADS_DEF 512
+#endif
+constexpr int RS_THREADS = RS_THREADS_DEF;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_EPT = 16;                      // entries per thread
 constexpr int RS_TILE = RS_THREADS * RS_EPT;    // 4096 entries per tile
@@ -37,6 +40,31 @@ struct __align__(16) RsRec { int key; int a; double v; };
 struct __align__(8) RsRecP { int key; int a; };
 
 constexpr unsigned long long RS_AGG = 1ull << 62, RS_PREFIX = 2ull << 62;
+
+// One 128-bit (64-bit for pattern-only records) access per record: a plain struct copy of
+// {int, int, double} compiles to two 64-bit accesses.
+__device__ __forceinline__ RsRec ld_rec(const RsRec *p)
+{
+    const int4 t = __ldg(reinterpret_cast<const int4 *>(p));
+    RsRec r;
+    r.key = t.x; r.a = t.y; r.v = __hiloint2double(t.w, t.z);
+    return r;
+}
+__device__ __forceinline__ RsRecP ld_rec(const RsRecP *p)
+{
+    const int2 t = __ldg(reinterpret_cast<const int2 *>(p));
+    RsRecP r;
+    r.key = t.x; r.a = t.y;
+    return r;
+}
+__device__ __forceinline__ void st_rec(RsRec *p, const RsRec &r)
+{
+    *reinterpret_cast<int4 *>(p) = make_int4(r.key, r.a, __double2loint(r.v), __double2hiint(r.v));
+}
+__device__ __forceinline__ void st_rec(RsRecP *p, const RsRecP &r)
+{
+    *reinterpret_cast<int2 *>(p) = make_int2(r.key, r.a);
+}
 
 __global__ void __launch_bounds__(256)
 k_rs_hist(const int *__restrict__ key, long long nnz, int npasses, unsigned long long *__restrict__ hist)
@@ -128,8 +156,10 @@ __device__ __forceinline__ long long rs_look_back(volatile unsigned long long *s
 // SRC: 0 = separate key / a / v arrays, 1 = records, 2 = separate key / v arrays with the
 //      int payload derived as "the column of Ap that holds this position" (cs_transpose)
 // DST: 0 = separate arrays (last pass; the sorted keys are written too), 1 = records
+constexpr int rs_pass_smem() { return RS_WARPS * RS_BINS * (int)sizeof(int) + RS_TILE * (int)sizeof(unsigned); }
+
 template <int SRC, int DST, bool VALUES>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, 1024 / RS_THREADS)
 k_rs_pass(long long nnz, int shift,
           const int *__restrict__ key_in, const int *__restrict__ a_in, const double *__restrict__ v_in,
           const void *__restrict__ rec_in, const csi *__restrict__ Ap, int ncols,
@@ -137,12 +167,12 @@ k_rs_pass(long long nnz, int shift,
           const unsigned long long *__restrict__ digit_start, volatile unsigned long long *status, unsigned *ticket, int lb)
 {
     using Rec = typename std::conditional<VALUES, RsRec, RsRecP>::type;
-    __shared__ int cnt[RS_WARPS][RS_BINS];
-    __shared__ long long gbase[RS_BINS];
+    extern __shared__ __align__(16) unsigned char rs_dyn[];      // rs_pass_smem() bytes: the counters and the permutation
+    int (*cnt)[RS_BINS] = reinterpret_cast<int (*)[RS_BINS]>(rs_dyn);
+    unsigned *perm = reinterpret_cast<unsigned *>(rs_dyn + RS_WARPS * RS_BINS * sizeof(int));   // (digit << 16) | source slot inside the tile
+    __shared__ long long gbase[RS_BINS];            // first global slot of the digit's run of this tile MINUS its first slot in the tile
     __shared__ int toff[RS_BINS];
     __shared__ int wtot[RS_BINS / 32];
-    __shared__ unsigned short perm[RS_TILE];
-    __shared__ unsigned char sdig[RS_TILE];
     __shared__ unsigned s_tile;
     __shared__ int s_col[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -171,11 +201,10 @@ k_rs_pass(long long nnz, int shift,
     }
 #pragma unroll
     for (int u = 0; u < RS_EPT; u++) {
-        // warp-uniform control flow: lanes past the end get a digit of their own (256 + lane) so
-        // that they match nobody; a shuffle whose mask differs between lanes would split the warp
+        // warp-uniform control flow: lanes past the end are in nobody's peer mask (their own is unused)
         const bool valid = key[u] >= 0;
-        const int d = valid ? ((key[u] >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int d = (key[u] >> shift) & (RS_BINS - 1);
+        const unsigned peers = match_bits<8>(d, valid);
         const int leader = __ffs(peers) - 1;
         int r = 0;
         if (valid && lane == leader) { r = cnt[wid][d]; cnt[wid][d] = r + __popc(peers); }
@@ -214,6 +243,7 @@ k_rs_pass(long long nnz, int shift,
             int before = inc - my_total;
             for (int w = 0; w < wid; w++) before += wtot[w];
             toff[tid] = before;
+            gbase[tid] -= before;                  // written by this thread above: slot = gbase[d] + position in the tile
         }
     }
     __syncthreads();
@@ -225,8 +255,7 @@ k_rs_pass(long long nnz, int shift,
         if (key[u] < 0) continue;
         const int d = (key[u] >> shift) & (RS_BINS - 1);
         const int tpos = toff[d] + cnt[wid][d] + rank[u];
-        perm[tpos] = (unsigned short)(wid * RS_SEG + u * 32 + lane);
-        sdig[tpos] = (unsigned char)d;
+        perm[tpos] = ((unsigned)d << 16) | (unsigned)(wid * RS_SEG + u * 32 + lane);
     }
     __syncthreads();
     const int tile_n = (int)min((long long)RS_TILE, nnz - base);
@@ -271,25 +300,26 @@ k_rs_pass(long long nnz, int shift,
     for (int k = 0; k < RS_EPT; k++) {
         const int tpos = k * RS_THREADS + tid;
         if (tpos >= tile_n) continue;
-        const long long e = base + perm[tpos];
-        const int d = sdig[tpos];
-        const long long pos = gbase[d] + (tpos - toff[d]);
+        const unsigned pw = perm[tpos];
+        const int src = (int)(pw & 0xffffu);
+        const long long e = base + src;
+        const long long pos = gbase[pw >> 16] + tpos;
         int kk, a;
         double v = 0.0;
         if (SRC == 1) {
-            const Rec r = rin[e];
+            const Rec r = ld_rec(rin + e);
             kk = r.key; a = r.a;
             if constexpr (VALUES) v = r.v;
         } else {
             kk = key_in[e];
-            a = SRC == 2 ? (marked ? j_lo + (int)colof[perm[tpos]] : upper_row(Ap, j_lo, j_hi, (int)e)) : a_in[e];
+            a = SRC == 2 ? (marked ? j_lo + (int)colof[src] : upper_row(Ap, j_lo, j_hi, (int)e)) : a_in[e];
             if (VALUES) v = v_in[e];
         }
         if (DST == 1) {
             Rec r;
             r.key = kk; r.a = a;
             if constexpr (VALUES) r.v = v;
-            reinterpret_cast<Rec *>(rec_out)[pos] = r;
+            st_rec(reinterpret_cast<Rec *>(rec_out) + pos, r);
         } else {
             key_out[pos] = kk;
             a_out[pos] = a;
@@ -355,7 +385,7 @@ k_rs_pass_s(long long nnz, int shift,
         key[u] = -1; pay[u] = 0; val[u] = 0.0;
         if (e < nnz) {
             if (SRC == 1) {
-                const Rec r = rin[e];
+                const Rec r = ld_rec(rin + e);
                 key[u] = r.key; pay[u] = r.a;
                 if constexpr (VALUES) val[u] = r.v;
             } else {
@@ -370,8 +400,8 @@ k_rs_pass_s(long long nnz, int shift,
 #pragma unroll
     for (int u = 0; u < RS2_EPT; u++) {
         const bool valid = key[u] >= 0;
-        const int d = valid ? ((key[u] >> shift) & (RS_BINS - 1)) : RS_BINS + lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int d = (key[u] >> shift) & (RS_BINS - 1);
+        const unsigned peers = match_bits<8>(d, valid);
         const int leader = __ffs(peers) - 1;
         int r = 0;
         if (valid && lane == leader) { r = cnt[wid][d]; cnt[wid][d] = r + __popc(peers); }
@@ -466,7 +496,7 @@ k_rs_pass_s(long long nnz, int shift,
         Rec r;
         r.key = key[u]; r.a = pay[u];
         if constexpr (VALUES) r.v = val[u];
-        srec[tpos[u]] = r;
+        st_rec(srec + tpos[u], r);
     }
     __syncthreads();
 #pragma unroll
@@ -477,7 +507,7 @@ k_rs_pass_s(long long nnz, int shift,
         const int d = (r.key >> shift) & (RS_BINS - 1);
         const long long pos = gbase[d] + (tp - toff[d]);
         if (DST == 1) {
-            reinterpret_cast<Rec *>(rec_out)[pos] = r;
+            st_rec(reinterpret_cast<Rec *>(rec_out) + pos, r);
         } else {
             key_out[pos] = r.key;
             a_out[pos] = r.a;
@@ -547,7 +577,8 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
                 k_rs_pass_s<SRC, DST, VALUES><<<ntiles, RS2_THREADS, rs2_smem<VALUES>(), s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
                     keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q, lb);         \
             } else {                                                                              \
-                k_rs_pass<SRC, DST, VALUES><<<ntiles, RS_THREADS, 0, s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
+                RS_CUDA(cudaFuncSetAttribute(k_rs_pass<SRC, DST, VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs_pass_smem())); \
+                k_rs_pass<SRC, DST, VALUES><<<ntiles, RS_THREADS, rs_pass_smem(), s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
                     keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q, lb);         \
             }                                                                                     \
         } while (0)
