@@ -178,6 +178,7 @@ struct csb200_mat {
     int canon = -1;              // 1: every column strictly increasing (=> no duplicate entries)
     csi max_col_len = -1;        // longest column
     int mirror = -1;             // 1: square, canonical and pattern-symmetric (cs_transpose's one-pass path); 0: known not to be
+    int wide_rows = -1;          // 1: a 4096-entry tile's rows span more buckets than the bucket sort's window (cs_transpose takes the radix sort)
     csb200_mat *csr = nullptr;   // cached transpose with values == CSR view of this matrix
     SpmvPlan *plan = nullptr;    // gaxpy plan over this matrix interpreted as a CSR view (columns = rows)
     int forced_plan = 0;

@@ -117,6 +117,20 @@ k_rs_starts(int npasses, unsigned long long *hist)
 // reads one predecessor per step is a chain of dependent L2 round trips (the whole CTA waits at the
 // next barrier meanwhile); `lb` statuses are read at once and consumed in order, so a walk of k tiles
 // costs ceil(k / lb) round trips.  A status that is not published yet ends the batch: the walk resumes there.
+// the same walk, one predecessor per step, starting from a status word that is already on its way
+__device__ __forceinline__ long long rs_look_back_from(volatile unsigned long long *status, unsigned tile, int d,
+                                                       unsigned long long w)
+{
+    long long prefix = 0;
+    for (long long t = (long long)tile - 1;; ) {
+        volatile unsigned long long *pst = status + (size_t)t * RS_BINS + d;
+        while ((w >> 62) == 0) w = *pst;
+        prefix += (long long)(w & 0xffffffffull);
+        if ((w & (2ull << 62)) || --t < 0) break;
+        w = status[(size_t)t * RS_BINS + d];
+    }
+    return prefix;
+}
 constexpr int RS_LB_MAX = 8;
 __device__ __forceinline__ long long rs_look_back(volatile unsigned long long *status, unsigned tile, int d, int lb)
 {
@@ -156,7 +170,10 @@ __device__ __forceinline__ long long rs_look_back(volatile unsigned long long *s
 // SRC: 0 = separate key / a / v arrays, 1 = records, 2 = separate key / v arrays with the
 //      int payload derived as "the column of Ap that holds this position" (cs_transpose)
 // DST: 0 = separate arrays (last pass; the sorted keys are written too), 1 = records
-constexpr int rs_pass_smem() { return RS_WARPS * RS_BINS * (int)sizeof(int) + RS_TILE * (int)sizeof(unsigned); }
+// dynamic shared memory of k_rs_pass: the per-warp counters, then either one word per entry (records:
+// digit and source slot) or the tile's keys in sorted order plus a 16-bit source slot (separate arrays:
+// the key then needs no gather of its own)
+constexpr int rs_pass_smem(int src) { return RS_WARPS * RS_BINS * (int)sizeof(int) + RS_TILE * (src == 1 ? 4 : 6); }
 
 template <int SRC, int DST, bool VALUES>
 __global__ void __launch_bounds__(RS_THREADS, 1024 / RS_THREADS)
@@ -169,7 +186,8 @@ k_rs_pass(long long nnz, int shift,
     using Rec = typename std::conditional<VALUES, RsRec, RsRecP>::type;
     extern __shared__ __align__(16) unsigned char rs_dyn[];      // rs_pass_smem() bytes: the counters and the permutation
     int (*cnt)[RS_BINS] = reinterpret_cast<int (*)[RS_BINS]>(rs_dyn);
-    unsigned *perm = reinterpret_cast<unsigned *>(rs_dyn + RS_WARPS * RS_BINS * sizeof(int));   // (digit << 16) | source slot inside the tile
+    unsigned *perm = reinterpret_cast<unsigned *>(rs_dyn + RS_WARPS * RS_BINS * sizeof(int));   // SRC == 1: (digit << 16) | source slot inside the tile; else the key
+    unsigned short *perm16 = reinterpret_cast<unsigned short *>(perm + RS_TILE);                   // SRC != 1: the source slot
     __shared__ long long gbase[RS_BINS];            // first global slot of the digit's run of this tile MINUS its first slot in the tile
     __shared__ int toff[RS_BINS];
     __shared__ int wtot[RS_BINS / 32];
@@ -213,8 +231,13 @@ k_rs_pass(long long nnz, int shift,
     }
     __syncthreads();
 
-    // ---- tile counts -> look-back -> global base of every digit ---------------------------
-    int my_total = 0;
+    // ---- tile counts -> published; the look-back itself waits until the permutation is written --------
+    // The first predecessor's status is requested right after this tile's counts are out and consumed
+    // only after the permutation phase: one L2 round trip of the walk is hidden, and the predecessors
+    // have had that much longer to publish their prefixes.
+    int my_total = 0, before = 0;
+    unsigned long long w_first = 0;
+    long long early_prefix = 0;
     if (tid < RS_BINS) {
         const int d = tid;
         int sum = 0;
@@ -222,15 +245,17 @@ k_rs_pass(long long nnz, int shift,
         for (int w = 0; w < RS_WARPS; w++) { const int c = cnt[w][d]; cnt[w][d] = sum; sum += c; }
         my_total = sum;
         volatile unsigned long long *mine = status + (size_t)tile * RS_BINS + d;
-        long long prefix = 0;
         if (tile == 0) {
             *mine = RS_PREFIX | (unsigned long long)sum;
         } else {
             *mine = RS_AGG | (unsigned long long)sum;
-            prefix = rs_look_back(status, tile, d, lb);
-            *mine = RS_PREFIX | (unsigned long long)(prefix + sum);
+            if (lb == 0) {                         // A/B: the whole walk right here
+                early_prefix = rs_look_back(status, tile, d, 1);
+                *mine = RS_PREFIX | (unsigned long long)(early_prefix + sum);
+            } else {
+                w_first = status[(size_t)(tile - 1) * RS_BINS + d];
+            }
         }
-        gbase[d] = (long long)digit_start[d] + prefix;
     }
     // first slot of every digit inside the tile's own sorted order (exclusive scan of the totals)
     {
@@ -240,10 +265,9 @@ k_rs_pass(long long nnz, int shift,
         if (tid < RS_BINS && lane == 31) wtot[wid] = inc;
         __syncthreads();
         if (tid < RS_BINS) {
-            int before = inc - my_total;
+            before = inc - my_total;
             for (int w = 0; w < wid; w++) before += wtot[w];
             toff[tid] = before;
-            gbase[tid] -= before;                  // written by this thread above: slot = gbase[d] + position in the tile
         }
     }
     __syncthreads();
@@ -255,7 +279,23 @@ k_rs_pass(long long nnz, int shift,
         if (key[u] < 0) continue;
         const int d = (key[u] >> shift) & (RS_BINS - 1);
         const int tpos = toff[d] + cnt[wid][d] + rank[u];
-        perm[tpos] = ((unsigned)d << 16) | (unsigned)(wid * RS_SEG + u * 32 + lane);
+        if (SRC == 1) {
+            perm[tpos] = ((unsigned)d << 16) | (unsigned)(wid * RS_SEG + u * 32 + lane);
+        } else {
+            perm[tpos] = (unsigned)key[u];
+            perm16[tpos] = (unsigned short)(wid * RS_SEG + u * 32 + lane);
+        }
+    }
+    // ---- look-back -> global base of every digit ----------------------------------------------------------
+    if (tid < RS_BINS) {
+        const int d = tid;
+        long long prefix = 0;
+        if (tile > 0 && lb == 0) prefix = early_prefix;
+        else if (tile > 0) {
+            prefix = lb > 1 ? rs_look_back(status, tile, d, lb) : rs_look_back_from(status, tile, d, w_first);
+            status[(size_t)tile * RS_BINS + d] = RS_PREFIX | (unsigned long long)(prefix + my_total);
+        }
+        gbase[d] = (long long)digit_start[d] + prefix - before;      // slot = gbase[d] + position in the tile
     }
     __syncthreads();
     const int tile_n = (int)min((long long)RS_TILE, nnz - base);
@@ -301,9 +341,9 @@ k_rs_pass(long long nnz, int shift,
         const int tpos = k * RS_THREADS + tid;
         if (tpos >= tile_n) continue;
         const unsigned pw = perm[tpos];
-        const int src = (int)(pw & 0xffffu);
+        const int src = SRC == 1 ? (int)(pw & 0xffffu) : (int)perm16[tpos];
         const long long e = base + src;
-        const long long pos = gbase[pw >> 16] + tpos;
+        const long long pos = gbase[SRC == 1 ? (pw >> 16) : ((pw >> shift) & (RS_BINS - 1))] + tpos;
         int kk, a;
         double v = 0.0;
         if (SRC == 1) {
@@ -311,7 +351,7 @@ k_rs_pass(long long nnz, int shift,
             kk = r.key; a = r.a;
             if constexpr (VALUES) v = r.v;
         } else {
-            kk = key_in[e];
+            kk = (int)pw;
             a = SRC == 2 ? (marked ? j_lo + (int)colof[src] : upper_row(Ap, j_lo, j_hi, (int)e)) : a_in[e];
             if (VALUES) v = v_in[e];
         }
@@ -517,6 +557,8 @@ k_rs_pass_s(long long nnz, int shift,
 }
 
 // Cp[r] = number of entries with key < r, r = 0..nkeys (keys sorted ascending)
+// (one streamed pass over the keys with the lanes of a warp filling the rows between two different
+// neighbours measured the same 0.4 ms on R-MAT 2^24 and lost on matrices without empty rows)
 __global__ void k_rs_bounds(const int *__restrict__ keys, long long nnz, int nkeys, csi *__restrict__ Cp)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -541,7 +583,7 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
     const int npasses = (bits + 7) / 8;
     static const bool staged = getenv("CSB200_RS_STAGED") && atoi(getenv("CSB200_RS_STAGED"));   // A/B switch: measured slower (12.8 vs 11.3 ms on R-MAT 2^24), off by default
     static const int lb_env = getenv("CSB200_RS_LB") ? atoi(getenv("CSB200_RS_LB")) : 1;    // batched look-back: A/B switch (helps the staged pass only)
-    const int lb = lb_env < 1 ? 1 : (lb_env > RS_LB_MAX ? RS_LB_MAX : lb_env);
+    const int lb = lb_env < 0 ? 0 : (lb_env > RS_LB_MAX ? RS_LB_MAX : lb_env);
     const int ntiles = ceil_div(nnz, staged ? RS2_TILE : RS_TILE);
     const size_t recsz = VALUES ? sizeof(RsRec) : sizeof(RsRecP);
 
@@ -577,8 +619,8 @@ static int sort_impl(long long nnz, int nkeys, const int *key, const int *a, con
                 k_rs_pass_s<SRC, DST, VALUES><<<ntiles, RS2_THREADS, rs2_smem<VALUES>(), s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
                     keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q, lb);         \
             } else {                                                                              \
-                RS_CUDA(cudaFuncSetAttribute(k_rs_pass<SRC, DST, VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs_pass_smem())); \
-                k_rs_pass<SRC, DST, VALUES><<<ntiles, RS_THREADS, rs_pass_smem(), s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
+                RS_CUDA(cudaFuncSetAttribute(k_rs_pass<SRC, DST, VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs_pass_smem(SRC))); \
+                k_rs_pass<SRC, DST, VALUES><<<ntiles, RS_THREADS, rs_pass_smem(SRC), s>>>(nnz, 8 * q, key, a, v, rin, Ap, ncols, \
                     keys_sorted.ptr, a_out, v_out, rout, ds, status.ptr, ticket.ptr + q, lb);         \
             }                                                                                     \
         } while (0)

@@ -1116,7 +1116,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
             return CSB200_OK;
         }
     }
-    if (tls().force_transpose == 1 || !packable) return radix_path();
+    if (tls().force_transpose == 1 || !packable || A->wide_rows == 1) return radix_path();      // wide_rows: found by an earlier call's histogram
     TR_CUDA(cudaMemsetAsync(bfill.ptr, 0, ((size_t)nbuckets + 2) * sizeof(int), s));
     const int nht = ceil_div(nnz, TR_TILE);
     std::vector<int> h_range((size_t)2 * nht);
@@ -1129,6 +1129,7 @@ int transpose_impl(const csb200_mat *A, bool values, csb200_mat **out)
         TR_CUDA(cudaMemcpyAsync(&h_wide, wide, sizeof(int), cudaMemcpyDeviceToHost, s));
         TR_CUDA(cudaMemcpyAsync(h_range.data(), tile_range.ptr, h_range.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
         TR_CUDA(cudaStreamSynchronize(s));
+        const_cast<csb200_mat *>(A)->wide_rows = h_wide > 0 ? 1 : 0;      // a fact about A, remembered like `mirror`
         if (h_wide > 0) return radix_path();
     }
     // bstart = exclusive scan of the counts; bfill <- bstart (the fill cursors)
