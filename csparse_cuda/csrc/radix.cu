@@ -30,7 +30,10 @@ namespace csb {
 #endif
 constexpr int RS_THREADS = RS_THREADS_DEF;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_EPT = 16;                      // entries per thread
+#ifndef RS_EPT_DEF
+#define RS_EPT_DEF 16
+#endif
+constexpr int RS_EPT = RS_EPT_DEF;              // entries per thread
 constexpr int RS_TILE = RS_THREADS * RS_EPT;    // 4096 entries per tile
 constexpr int RS_SEG = 32 * RS_EPT;             // consecutive entries owned by one warp
 constexpr int RS_BINS = 256;
@@ -175,8 +178,11 @@ __device__ __forceinline__ long long rs_look_back(volatile unsigned long long *s
 // the key then needs no gather of its own)
 constexpr int rs_pass_smem(int src) { return RS_WARPS * RS_BINS * (int)sizeof(int) + RS_TILE * (src == 1 ? 4 : 6); }
 
+#ifndef RS_MINB_DEF
+#define RS_MINB_DEF (1024 / RS_THREADS)
+#endif
 template <int SRC, int DST, bool VALUES>
-__global__ void __launch_bounds__(RS_THREADS, 1024 / RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB_DEF)
 k_rs_pass(long long nnz, int shift,
           const int *__restrict__ key_in, const int *__restrict__ a_in, const double *__restrict__ v_in,
           const void *__restrict__ rec_in, const csi *__restrict__ Ap, int ncols,

@@ -54,7 +54,10 @@ constexpr int BK_CAP = BK_THREADS * BK_EPT;   // 3072 entries staged per bucket
 constexpr int BK_RB_MAX = 1024;               // rows per bucket (power of two)
 constexpr int BK_SMEM = BK_CAP * 12 + 2 * (BK_RB_MAX + 1) * 4 + 64;
 constexpr int FIX_SHORT = 32;                 // rows up to this length: one thread (global-memory path)
-constexpr int FIX_THREAD = 8;                 // staged rows up to this length: one thread; up to 32: warp rank sort
+#ifndef FIX_THREAD_DEF
+#define FIX_THREAD_DEF 8
+#endif
+constexpr int FIX_THREAD = FIX_THREAD_DEF;                 // staged rows up to this length: one thread; up to 32: warp rank sort
 
 
 // ---- tile -> first column ------------------------------------------------------
@@ -367,6 +370,33 @@ __device__ __forceinline__ bool warp_rank_sort(csi *ci, V *cv, int len, int lane
     const int c = lane < len ? ci[lane] : INT_MAX;
     V v = V();
     if (HAS_V && lane < len) v = cv[lane];
+    // Keys below 2^26 (any matrix of < 67 M columns): a bitonic network on (key << 5 | lane), 15
+    // compare-exchange steps of one shuffle each instead of `len` rounds of shuffle + two compares
+    // (the rank loop was 45 % of k_bucket_sort's stall samples on the 27-point stencil); the low
+    // bits keep equal keys in their order of arrival and name the lane whose value follows.
+    if (__all_sync(0xffffffffu, lane >= len || (unsigned)c < (1u << 26))) {
+        unsigned w = lane < len ? ((unsigned)c << 5) | (unsigned)lane : 0xffffffffu;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const unsigned o = __shfl_xor_sync(0xffffffffu, w, j);
+                const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+                w = keep_min ? min(w, o) : max(w, o);
+            }
+        }
+        const unsigned wprev = __shfl_up_sync(0xffffffffu, w, 1);
+        const bool tie2 = lane > 0 && lane < len && (wprev >> 5) == (w >> 5);
+        V vv = V();
+        if (HAS_V) {
+            if constexpr (sizeof(V) == 8) vv = __shfl_sync(0xffffffffu, v, (int)(w & 31u));
+            else vv = (V)__shfl_sync(0xffffffffu, (int)v, (int)(w & 31u));
+        }
+        __syncwarp();
+        if (lane < len) { ci[lane] = (int)(w >> 5); if (HAS_V) cv[lane] = vv; }
+        __syncwarp();
+        return __any_sync(0xffffffffu, tie2);
+    }
     int rank = 0;
     bool tie = false;
     for (int u = 0; u < len; u++) {
