@@ -174,22 +174,24 @@ class DeviceMatrix(object):
             raise ValueError(_lib.last_error())
         return DeviceMatrix(out.value)
 
-    def download(self, trim: bool = False) -> cs:
-        """Back to a list-backed ``cs``.  ``trim`` selects cs_multiply's shape
-        convention (nzmax == nnz, possibly 0) instead of cs_spalloc's max(nnz, 1)."""
+    def download(self, trim: bool = False, numpy: bool = False) -> cs:
+        """Back to a host ``cs``: list-backed like the reference's, or numpy-backed (``numpy=True``:
+        int32 p / i, float64 x, no per-element conversion -- what the module functions return
+        when their operands were numpy-backed).  ``trim`` selects cs_multiply's shape convention
+        (nzmax == nnz, possibly 0) instead of cs_spalloc's max(nnz, 1)."""
         p, i, x = self.arrays()
         A = cs()
         A.m, A.n, A.nz = self.m, self.n, -1
-        A.p = p.tolist()
-        A.i = i.tolist()
-        A.x = None if x is None else x.tolist()
+        A.p = p if numpy else p.tolist()
+        A.i = i if numpy else i.tolist()
+        A.x = None if x is None else (x if numpy else x.tolist())
         if trim:
             A.nzmax = self.nnz
         else:
             A.nzmax = max(self.nnz, 1)
             if self.nnz == 0:
-                A.i = [0]
-                A.x = None if x is None else [0.0]
+                A.i = np.zeros(1, np.int32) if numpy else [0]
+                A.x = None if x is None else (np.zeros(1, np.float64) if numpy else [0.0])
         return A
 
     # device-pointer forms (async on the stream set with set_stream); x / y are raw
@@ -275,6 +277,12 @@ def from_device(m, n, p_ptr: int, i_ptr: int, x_ptr: int = 0) -> DeviceMatrix:
     return DeviceMatrix(out.value)
 
 
+def _numpy_backed(*ops) -> bool:
+    """True when a host operand keeps its row indices in a numpy array: results then stay numpy
+    arrays (a list-backed cs in gives a list-backed cs out, as the reference's callers expect)."""
+    return any(isinstance(getattr(o, "i", None), np.ndarray) for o in ops if not isinstance(o, DeviceMatrix))
+
+
 def _as_device(A):
     """(DeviceMatrix, temporary?) for a cs or DeviceMatrix operand."""
     if isinstance(A, DeviceMatrix):
@@ -329,7 +337,7 @@ def cs_transpose(A, values):
     if not tmp:
         return dC
     dA.free()
-    return dC.download(trim=False)
+    return dC.download(trim=False, numpy=_numpy_backed(A))
 
 
 def cs_gaxpy(A, x, y):
@@ -392,17 +400,23 @@ def cs_multiply(A, B):
         dB.free()
     if isinstance(A, DeviceMatrix) and isinstance(B, DeviceMatrix):
         return dC
-    return dC.download(trim=True)
+    return dC.download(trim=True, numpy=_numpy_backed(A, B))
 
 
 # ---- the callers and data formats either side of the hot path ----------
 
-def _padded(dC: "DeviceMatrix", nzmax: int) -> cs:
-    """Download into a cs whose i / x lists have cs_spalloc's length nzmax (zero tail)."""
+def _padded(dC: "DeviceMatrix", nzmax: int, numpy: bool = False) -> cs:
+    """Download into a cs whose i / x have cs_spalloc's length nzmax (zero tail); lists, or numpy
+    arrays when the operands were numpy-backed."""
     p, i, x = dC.arrays()
     A = cs()
     A.m, A.n, A.nz, A.nzmax = dC.m, dC.n, -1, nzmax
     pad = nzmax - len(i)
+    if numpy:
+        A.p = p
+        A.i = np.concatenate([i, np.zeros(pad, np.int32)]) if pad else i
+        A.x = None if x is None else (np.concatenate([x, np.zeros(pad, np.float64)]) if pad else x)
+        return A
     A.p = p.tolist()
     A.i = i.tolist() + [0] * pad
     A.x = None if x is None else x.tolist() + [0.0] * pad
@@ -437,7 +451,7 @@ def cs_add(A, B, alpha, beta):
         dB.free()
     if isinstance(A, DeviceMatrix) and isinstance(B, DeviceMatrix):
         return dC
-    return _padded(dC, nzmax)
+    return _padded(dC, nzmax, _numpy_backed(A, B))
 
 
 def force_add_path(path: Optional[str]):
@@ -483,7 +497,7 @@ def cs_compress(T):
     their input order (stable radix sort on the column index)."""
     if not CS_TRIPLET(T):
         return None
-    return compress_device(T).download(trim=False)
+    return compress_device(T).download(trim=False, numpy=_numpy_backed(T))
 
 
 def cs_dupl(A):
@@ -669,7 +683,7 @@ def cs_permute(A, pinv, q, values):
     dC = DeviceMatrix(out.value)
     if not tmp:
         return dC
-    return _padded(dC, nzmax)
+    return _padded(dC, nzmax, _numpy_backed(A))
 
 
 def cs_symperm(A, pinv, values):
@@ -690,7 +704,7 @@ def cs_symperm(A, pinv, values):
     if not tmp:
         return dC
     dA.free()
-    return _padded(dC, nzmax)
+    return _padded(dC, nzmax, _numpy_backed(A))
 
 
 def set_stream(cuda_stream: int = 0):

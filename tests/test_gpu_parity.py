@@ -462,3 +462,23 @@ def test_monkeypatched_reference_callers():
         Ci[q], Cx[q] = int(Ti[k]), float(Tx[k])
     A = g.A()
     assert Cp == A.p.tolist() and Ci == A.i.tolist() and Cx == A.x.tolist()
+
+
+@pytest.mark.parametrize("name", ["bcsstk01", "west0067", "ash219"])
+def test_numpy_backed_operands_give_numpy_backed_results(name):
+    """A cs whose p / i / x are numpy arrays comes back numpy-backed (no per-element conversion);
+    the same call on a list-backed cs gives lists with the same contents and shape conventions."""
+    M = Golden(name).A()
+    An, Al = to_cs(M, lists=False), to_cs(M, lists=True)
+    Tn, Tl = cc.cs_transpose(An, True), cc.cs_transpose(Al, True)
+    assert isinstance(Tn.i, np.ndarray) and isinstance(Tn.p, np.ndarray) and isinstance(Tn.x, np.ndarray)
+    assert isinstance(Tl.i, list) and isinstance(Tl.p, list) and isinstance(Tl.x, list)
+    assert Tn.i.dtype == np.int32 and Tn.x.dtype == np.float64
+    assert_same_matrix(Tn, Tl, name + " transpose")
+    Cn, Cl = cc.cs_multiply(An, Tn), cc.cs_multiply(Al, Tl)
+    assert isinstance(Cn.i, np.ndarray) and isinstance(Cl.i, list)
+    assert_same_matrix(Cn, Cl, name + " multiply")
+    if M.m == M.n:
+        Sn, Sl = cc.cs_add(An, Tn, 1.0, 2.0), cc.cs_add(Al, Tl, 1.0, 2.0)
+        assert isinstance(Sn.i, np.ndarray) and isinstance(Sl.i, list)
+        assert_same_matrix(Sn, Sl, name + " add")

@@ -1,4 +1,3 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_mirror.py tests/test_gpu_next_rows.py -x -q --timeout 200 -p no:cacheprovider 2>&1 | tail -1
-Q='python tools/quick_perf.py --only transpose --lap 4096 --st 128 --rmat 0'
-$Q 2>&1 | grep "transpose\[bucket\]" | cut -c1-120
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_next_rows.py tests/test_dropin_reference.py -x -q --timeout 200 -p no:cacheprovider 2>&1 | tail -2
+python tools/small_probe.py 2>&1 | tail -2
