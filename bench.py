@@ -915,9 +915,49 @@ def extras(a, torch, cc, synth, peak):
                                                                          "frac_of_peak": b / ms / 1e6 / peak}
         hold.clear(); dA.free()
         del ti, tj, tx
-        # CPU baseline of the second headline metric: oracle cs_multiply on a bounded sample
+        # BASELINE.json configs 1 and 2: the reference's own test matrices (tests/golden holds them), the
+        # CSparseTest1 operations cs_transpose and cs_multiply A*A' -- device handles, host `cs` objects
+        # backed by numpy arrays (upload, kernels, download: what a caller of the module pays), and the
+        # C port of the reference on the same inputs (the Python reference is ~100x slower than the port)
         from oracle import oracle as orc
         orc.build()
+        import json as _json
+
+        def wall(fn, warm, iters):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(iters):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            return float(np.median(ts))
+
+        for name in ("bcsstk01", "bcsstk16"):
+            z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", name + ".npz"))
+            meta = _json.loads(str(z["meta"]))
+            mm, nn = meta["A"]["m"], meta["A"]["n"]
+            zp, zi, zx = z["A_p"], z["A_i"], z["A_x"]
+            dS = cc.from_arrays(mm, nn, zp, zi, zx)
+            dST = cc.cs_transpose(dS, True)
+            S = cc.cs()
+            S.m, S.n, S.nzmax, S.nz, S.p, S.i, S.x = mm, nn, len(zi), -1, zp.copy(), zi.copy(), zx.copy()
+            ST = cc.cs_transpose(S, True)
+            oS = orc.csc(mm, nn, zp, zi, zx)
+            t0 = time.perf_counter(); oT = orc.cs_transpose(oS, True); t_ot = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter(); oC = orc.cs_multiply(oS, oT); t_oc = (time.perf_counter() - t0) * 1e3
+            ex[f"{name} (BASELINE config {1 if name == 'bcsstk01' else 2}): cs_transpose, cs_multiply A*A'"] = {
+                "nnz": int(len(zi)), "nnzC": int(oC.nnz),
+                "transpose ms: device handle": wall(lambda: hold.__setitem__("t", cc.cs_transpose(dS, True)), 3, 20),
+                "transpose ms: host cs (numpy-backed, up + kernels + down)": wall(lambda: cc.cs_transpose(S, True), 2, 10),
+                "transpose ms: C port of the reference, 1 core": t_ot,
+                "multiply ms: device handles": wall(lambda: hold.__setitem__("c", cc.cs_multiply(dS, dST)), 3, 20),
+                "multiply ms: host cs (numpy-backed, up + kernels + down)": wall(lambda: cc.cs_multiply(S, ST), 2, 10),
+                "multiply ms: C port of the reference, 1 core": t_oc}
+            hold.clear(); dS.free(); dST.free()
+        # CPU baseline of the second headline metric: oracle cs_multiply on a bounded sample
         ms_, ns_, ps_, is_, xs_ = synth.st27(64)
         Ao = orc.csc(ms_, ns_, ps_, is_, xs_)
         t0 = time.perf_counter()

@@ -216,9 +216,9 @@ __device__ __forceinline__ unsigned match_bits(int d, bool valid)
     unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
     for (int b = 0; b < NBITS; b++) {
-        const bool bit = (d >> b) & 1;
+        const bool bit = (d & (1 << b)) != 0;                 // LOP3 into a predicate, VOTE, SEL, LOP3: four instructions per bit
         const unsigned bal = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? bal : ~bal;
+        peers &= bal ^ (bit ? 0u : 0xffffffffu);
     }
     return peers;
 }
