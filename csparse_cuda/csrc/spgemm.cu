@@ -962,7 +962,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
     DevBuf<unsigned char> tpl_table, tpl_pos, tpl_soa, tpl_mode;
     DevBuf<int> left_list;
     DevBuf<unsigned char> tpl_tend;
-    DevBuf<int2> tpl_terms;
+    DevBuf<int> tpl_terms;
     DevBuf<int2> blkbuf;
     DevBuf<double> acc;
     // the blocked numeric path keeps BLK_STRIDE pairs per column (512 B): only while that stays modest
@@ -1088,7 +1088,7 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             do {                                                                                               \
                 MM_CUDA(cudaFuncSetAttribute(k_num_soa<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOA_SMEM)); \
                 k_num_soa<MINB><<<grid, SOA_THREADS, SOA_SMEM, s>>>(n, cb.ptr, tpl_cnt.ptr, tpl_mode.ptr, tpl_terms.ptr, tpl_tend.ptr, \
-                                                                  tpl_wptr.ptr, tpl_rows.ptr, A->soa_x, B->soa_x, C->p, C->i, C->x);    \
+                                                                  tpl_wptr.ptr, tpl_rows.ptr, A->soa_x, B->soa_x, A->n, n, C->p, C->i, C->x); \
             } while (0)
             if (soa_ctas >= 6) SOA_LAUNCH(6); else if (soa_ctas == 5) SOA_LAUNCH(5); else SOA_LAUNCH(4);
 #undef SOA_LAUNCH

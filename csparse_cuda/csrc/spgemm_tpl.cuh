@@ -39,6 +39,13 @@ constexpr int SOA_WARPS = SOA_THREADS / 32;
 constexpr int SOA_CHUNKS = SOA_CNT / 32;
 constexpr int SOA_BATCH = 8;             // terms a warp takes per step (its lists are padded to a multiple)
 constexpr int SOA_TERMS = SOA_UB + SOA_CHUNKS * SOA_WARPS * (SOA_BATCH - 1);
+// A term of k_num_soa in one 32-bit word: e (entry of the A column, 6 bits) | d (entry of B(:,j), 6 bits) |
+// k - j (signed, 20 bits).  The term lists are read by all lanes of a warp at once, and a uniform
+// shared-memory load costs a wavefront per 4 bytes like any other: {A offset, B offset} pairs of 8 bytes
+// were a third of the kernel's shared-memory + L1 wavefronts (profiles/r2_notes.md).
+constexpr int SOA_DK_LIM = 1 << 19;
+__host__ __device__ __forceinline__ int soa_term(int e, int d, int dk) { return (e & 63) | ((d & 63) << 6) | (dk << 12); }
+static_assert(SOA_MAXLEN <= 64, "six bits per entry number");
 
 struct ClsTable {
     unsigned long long *keys;            // CLS_SLOTS, 0 = empty
@@ -236,14 +243,14 @@ k_cls_hash_b(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi, cons
 // A's columns are canonical (distinct rows per column), so the rows of a 32-entry step are distinct.
 // For k_num_soa the same trace is also stored inverted: for every row t of the column the products
 // that land on it, in the reference's order, as offsets into the entry-major copies of A and B
-// (term = {e * nA + (k - j),  d * nB} for the e-th entry of the A column named by the d-th entry of
+// (term = one word, soa_term(e, d, k - j), for the e-th entry of the A column named by the d-th entry of
 // B(:,j)); tpl_soa[c] says whether the class fits that kernel.
 __global__ void __launch_bounds__(32)
 k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, const csi *__restrict__ Bp,
             const csi *__restrict__ Bi, const int *__restrict__ ub, int *__restrict__ tpl_cnt,
             unsigned char *__restrict__ tpl_pos, int *__restrict__ tpl_rows,
             int nA, int nB, int soa_len_a, int soa_len_b, unsigned char *__restrict__ tpl_soa,
-            int2 *__restrict__ tpl_terms, unsigned char *__restrict__ tpl_tend, int *__restrict__ tpl_wptr)
+            int *__restrict__ tpl_terms, unsigned char *__restrict__ tpl_tend, int *__restrict__ tpl_wptr)
 {
     constexpr int LOGH = 10, H = 1 << LOGH;
     static_assert(H >= 2 * (TPL_CAP + 32), "the table never fills");
@@ -302,7 +309,7 @@ k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, 
     __shared__ int rstart[SOA_CNT];                  // where the list of row r starts in the reordered table
     __shared__ int rlen[SOA_CNT];
     for (int q = lane; q < SOA_TERMS; q += 32) {     // padding terms read a(0) * b(0) of the column; their sum is dropped
-        tpl_terms[(size_t)c * SOA_TERMS + q] = make_int2(0, 0);
+        tpl_terms[(size_t)c * SOA_TERMS + q] = 0;
         tpl_tend[(size_t)c * SOA_TERMS + q] = 0;
     }
     for (int r = lane; r < cnt; r += 32) rlen[r] = tcount[r];
@@ -348,6 +355,7 @@ k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, 
     for (int r = lane; r < cnt; r += 32) tcount[r] = rstart[r];      // from here on: the fill cursor of row r
     __syncwarp();
     q0 = 0;
+    bool far = false;
     for (int pb = pb_begin; pb < pb_end; pb++) {     // the same walk again: products in the reference's order
         const int k = Bi[pb];
         const int ab = Ap[k], ae = Ap[k + 1];
@@ -358,7 +366,8 @@ k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, 
                 const int e = pa - ab;
                 const int r = tpl_pos[(size_t)c * TPL_UB + q0 + e];
                 const int idx = tcount[r]++;         // distinct rows in a step
-                tpl_terms[(size_t)c * SOA_TERMS + idx] = make_int2(e * nA + (k - j), d * nB);
+                tpl_terms[(size_t)c * SOA_TERMS + idx] = soa_term(e, d, k - j);
+                if (k - j >= SOA_DK_LIM || k - j < -SOA_DK_LIM) far = true;
                 if (idx == rstart[r] + rlen[r] - 1)                       // the row's last term: 1 + row inside the chunk
                     tpl_tend[(size_t)c * SOA_TERMS + idx] = (unsigned char)((r & 31) + 1);
             }
@@ -366,7 +375,7 @@ k_tpl_build(ClsTable t, const csi *__restrict__ Ap, const csi *__restrict__ Ai, 
         }
         q0 += ae - ab;
     }
-    if (lane == 0) tpl_soa[c] = 1;
+    if (!__any_sync(0xffffffffu, far) && lane == 0) tpl_soa[c] = 1;      // a column of A too far from j for the 20-bit field: k_num_tpl
 }
 
 // ---- verification and hand-out, one thread per column ----------------------------------------------
@@ -588,8 +597,8 @@ __global__ void k_max_col_len(int n, const csi *__restrict__ Ap, int *out)
 // for it) and shared memory is kept small -- rows are staged 32 at a time and leave as 256-byte runs.
 // Columns whose class has fewer than SOA_MIN_LANES members inside the 32-column block (grid
 // boundaries) are left to k_num_tpl (k_tpl_apply makes that choice and lists them).
-struct SoaTables {
-    int2 terms[SOA_TERMS];
+struct __align__(16) SoaTables {
+    int terms[SOA_TERMS];
     unsigned char tend[SOA_TERMS];
     int wptr[SOA_CHUNKS * SOA_WARPS + 1];
     int rows[SOA_CNT];
@@ -600,8 +609,8 @@ constexpr int SOA_SMEM = (int)sizeof(SoaTables) + 2 * 32 * 33 * 8;
 template <int MINB>
 __global__ void __launch_bounds__(SOA_THREADS, MINB)
 k_num_soa(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt, const unsigned char *__restrict__ mode,
-          const int2 *__restrict__ tpl_terms, const unsigned char *__restrict__ tpl_tend, const int *__restrict__ tpl_wptr,
-          const int *__restrict__ tpl_rows, const double *__restrict__ AxT, const double *__restrict__ BxT,
+          const int *__restrict__ tpl_terms, const unsigned char *__restrict__ tpl_tend, const int *__restrict__ tpl_wptr,
+          const int *__restrict__ tpl_rows, const double *__restrict__ AxT, const double *__restrict__ BxT, int nA, int nB,
           const csi *__restrict__ Cp, csi *__restrict__ Ci, double *__restrict__ Cx)
 {
     constexpr int NW = SOA_WARPS, BATCH = SOA_BATCH;
@@ -643,9 +652,15 @@ k_num_soa(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt, co
             }
             __syncthreads();
             const double *Aj = AxT + j, *Bj = BxT + j;     // this lane's column in the entry-major copies
+            // opaque to the compiler from here on: an operand address is then ONE IMAD.WIDE (offset * 8 + pointer)
+            // instead of the four-instruction 64-bit sum (base + (j + offset) * 8) it otherwise rebuilds per load --
+            // 64 of the 167 instructions of a step of eight terms (profiles/r2_notes.md)
+            asm volatile("" : "+l"(Aj), "+l"(Bj));
             int buf = 0;
             for (int t0 = 0; t0 < cnt; t0 += 32, buf ^= 1) {
                 double *sC = sCbuf + buf * (32 * 33) + lane * 33;
+                // shared-space byte address of sC[-1]: a completed row e (1-based) is stored at sCm1 + 8 e
+                const unsigned sCm1 = (unsigned)__cvta_generic_to_shared(sC) - 8u;
                 // this warp's share of the chunk: one flat list of terms, eight per step -- sixteen
                 // independent loads in flight, then the sums in list order.  -0.0 is the exact additive
                 // identity: the first product of a row lands as the reference's first-touch assignment
@@ -654,22 +669,27 @@ k_num_soa(int n, const int *__restrict__ cb, const int *__restrict__ tpl_cnt, co
                 if (active) {
                     double acc = -0.0;
                     for (int q = tb.wptr[(t0 >> 5) * NW + w]; q < Q1; q += BATCH) {
-                        int2 tm[BATCH];
+                        int tm[BATCH];
                         double a[BATCH], b[BATCH];
 #pragma unroll
-                        for (int u = 0; u < BATCH; u += 2) {
-                            const int4 two = *reinterpret_cast<const int4 *>(&tb.terms[q + u]);
-                            tm[u] = make_int2(two.x, two.y);
-                            tm[u + 1] = make_int2(two.z, two.w);
+                        for (int u = 0; u < BATCH; u += 4) {
+                            const int4 four = *reinterpret_cast<const int4 *>(&tb.terms[q + u]);
+                            tm[u] = four.x; tm[u + 1] = four.y; tm[u + 2] = four.z; tm[u + 3] = four.w;
                         }
                         const unsigned long long marks = *reinterpret_cast<const unsigned long long *>(&tb.tend[q]);
 #pragma unroll
-                        for (int u = 0; u < BATCH; u++) { b[u] = Bj[tm[u].y]; a[u] = Aj[tm[u].x]; }
+                        for (int u = 0; u < BATCH; u++) {
+                            b[u] = __ldg(Bj + ((tm[u] >> 6) & 63) * nB);
+                            a[u] = __ldg(Aj + ((tm[u] & 63) * nA + (tm[u] >> 12)));
+                        }
 #pragma unroll
                         for (int u = 0; u < BATCH; u++) {
                             acc = __dadd_rn(acc, __dmul_rn(b[u], a[u]));
                             const int e = (int)((marks >> (8 * u)) & 0xffull);
-                            if (e) { sC[e - 1] = acc; acc = -0.0; }          // warp-uniform: the row is complete
+                            if (e) {                                        // warp-uniform: the row is complete
+                                asm volatile("st.shared.f64 [%0], %1;" :: "r"(sCm1 + 8u * (unsigned)e), "d"(acc) : "memory");
+                                acc = -0.0;
+                            }
                         }
                     }
                 }
