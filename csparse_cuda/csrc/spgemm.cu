@@ -1084,11 +1084,15 @@ int multiply_impl(csb200_mat *A, csb200_mat *B, csb200_mat **out, bool ordered)
             // few CTAs per SM: each works on ~100 KB of A that should stay in its SM's L1
             static const int soa_ctas = getenv("CSB200_SOA_CTAS") ? atoi(getenv("CSB200_SOA_CTAS")) : 4;
             const int grid = (int)min((long long)ceil_div(n, 32), (long long)sm_count() * soa_ctas);
+            static const int soa_stride = getenv("CSB200_SOA_STRIDE") ? atoi(getenv("CSB200_SOA_STRIDE")) : 2;   // blocks per ticket; 0: round robin (A/B)
+            DevBuf<int> soa_tickets;
+            MM_TRY(soa_tickets.alloc((size_t)ceil_div(n, 32) + 1));
+            if (soa_stride > 0) MM_CUDA(cudaMemsetAsync(soa_tickets.ptr, 0, ((size_t)ceil_div(n, 32) + 1) * sizeof(int), s));
 #define SOA_LAUNCH(MINB)                                                                                       \
             do {                                                                                               \
                 MM_CUDA(cudaFuncSetAttribute(k_num_soa<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SOA_SMEM)); \
                 k_num_soa<MINB><<<grid, SOA_THREADS, SOA_SMEM, s>>>(n, cb.ptr, tpl_cnt.ptr, tpl_mode.ptr, tpl_terms.ptr, tpl_tend.ptr, \
-                                                                  tpl_wptr.ptr, tpl_rows.ptr, A->soa_x, B->soa_x, A->n, n, C->p, C->i, C->x); \
+                                                                  tpl_wptr.ptr, tpl_rows.ptr, A->soa_x, B->soa_x, A->n, n, C->p, C->i, C->x, soa_stride, soa_tickets.ptr); \
             } while (0)
             if (soa_ctas >= 6) SOA_LAUNCH(6); else if (soa_ctas == 5) SOA_LAUNCH(5); else SOA_LAUNCH(4);
 #undef SOA_LAUNCH
