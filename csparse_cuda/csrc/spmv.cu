@@ -721,12 +721,7 @@ struct SplitStreams {
         int dev = 0;
         CSB_CUDA(cudaGetDevice(&dev));
         if (device == dev) return CSB200_OK;
-        // highest priority: the short kernels' CTAs are placed as soon as a slot frees, mixed in with the
-        // long-row kernel's all the way instead of queueing behind its grid (A/B: CSB200_SPLIT_PRIO=0)
-        static const bool prio = !(getenv("CSB200_SPLIT_PRIO") && !atoi(getenv("CSB200_SPLIT_PRIO")));
-        int lo = 0, hi = 0;
-        CSB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CSB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio ? hi : lo));
+        CSB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));     // (highest stream priority for this one: 1.23 against 1.14 ms)
         CSB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         CSB_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         device = dev;
