@@ -1,6 +1,3 @@
 #!/bin/bash
-run() { env "$@" timeout 300 python tools/rmat_probe.py --scale 24 --iters 5 --no-transpose --plans auto 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$*', round(d['ms_median'],4), round(d['ms_best'],4))"; }
-run CSB200_SPLIT_PRIO=0
-run CSB200_SPLIT_PRIO=1
-run CSB200_SPLIT_PRIO=0
-run CSB200_SPLIT_PRIO=1
+Q='python tools/quick_perf.py --only transpose --lap 4096 --st 128 --rmat 0'
+for a in 0 1 0 1; do echo affine=$a; CSB200_MIRROR_AFFINE=$a $Q 2>&1 | grep "transpose\[mirror\]" | cut -c1-110; done
