@@ -224,11 +224,13 @@ k_cls_hash_b(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi, cons
             if (ok) {
                 const int c = ca[k];
                 if (c < 0) ok = false;
-                h += mix64(mix64((unsigned long long)(p - b) + 1) ^ (unsigned long long)(unsigned)(k - j) ^
-                           ((unsigned long long)(unsigned)c << 32));
+                // order-dependent polynomial hash, one 64-bit multiply-add per entry (two mix64 per entry made
+                // this kernel issue-bound: 75 instructions per entry); a collision only costs the comparison
+                // with the class representative that follows anyway
+                h = h * 0x9E3779B97F4A7C15ull + (((unsigned long long)(unsigned)c << 32) | (unsigned long long)(unsigned)(k - j));
             }
         }
-        h += mix64(0x5A5A5A5Aull + (unsigned long long)(e - b));
+        h = mix64(h + mix64(0x5A5A5A5Aull + (unsigned long long)(e - b)));
         if (h == 0ull) h = 1ull;
         ub[j] = (int)min(s, (long long)INT_MAX);
     }
@@ -402,9 +404,21 @@ k_cls_verify_apply(int n, const csi *__restrict__ Bp, const csi *__restrict__ Bi
             if (r != j) {
                 const int b = Bp[j], len = Bp[j + 1] - b, br = Bp[r];
                 ok = (Bp[r + 1] - br) == len;
-                for (int e = 0; ok && e < len; e++) {
-                    const int k = Bi[b + e], kr = Bi[br + e];
-                    ok = k - j == kr - r && ca[k] == ca[kr];
+                // four entries per round, their loads in flight together (one entry per round with an early
+                // exit made this a chain of dependent loads: 82 % of its samples were long-scoreboard stalls)
+                for (int e = 0; ok && e < len; e += 4) {
+                    int k[4], kr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int eu = min(e + u, len - 1);            // past the end: the last entry again
+                        k[u] = Bi[b + eu];
+                        kr[u] = Bi[br + eu];
+                    }
+                    int ck[4], ckr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { ck[u] = ca[k[u]]; ckr[u] = ca[kr[u]]; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) ok &= (k[u] - j == kr[u] - r) && ck[u] == ckr[u];
                 }
             }
             if (ok) c = t.dense[slot];

@@ -4,4 +4,4 @@ timeout 600 python -m pytest tests/test_gpu_fullsize.py -x -q --timeout 500 -p n
 M='python tools/quick_perf.py --only multiply --lap 0 --rmat 0 --st 128 --mul-paths auto'
 $M 2>&1 | grep multiply | cut -c1-130
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2y_mm.csv $M --once > /dev/null 2>&1
-python tools/ncu_summary.py launches gpurun_out/r2y_mm.csv | grep "k_" | cut -c1-90 | head -12
+python tools/ncu_summary.py launches gpurun_out/r2y_mm.csv | grep "k_" | cut -c1-90 | head -6
