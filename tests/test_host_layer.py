@@ -157,3 +157,21 @@ def test_path_controls_need_no_gpu():
         cc.force_multiply_path("blocked_v9")
     assert L.csb200_multiply_force_path(9) != 0
     assert L.csb200_transpose_force_path(0) == 0 and L.csb200_multiply_force_path(0) == 0
+
+
+def test_numpy_backed_detection():
+    """Results keep the container kind of the operands: numpy-backed cs objects are recognised by their
+    row-index array; list-backed ones (the reference's own kind) and device handles are not."""
+    import numpy as np
+    import csparse_cuda as cc
+    A = cc.cs()
+    A.m = A.n = 2
+    A.nzmax, A.nz = 2, -1
+    A.p, A.i, A.x = [0, 1, 2], [0, 1], [1.0, 2.0]
+    B = cc.cs()
+    B.m = B.n = 2
+    B.nzmax, B.nz = 2, -1
+    B.p, B.i, B.x = np.array([0, 1, 2], np.int32), np.array([0, 1], np.int32), np.array([1.0, 2.0])
+    assert cc._numpy_backed(A) is False
+    assert cc._numpy_backed(B) is True
+    assert cc._numpy_backed(A, B) is True
