@@ -23,6 +23,7 @@ struct ThreadState {
     int multiply_templates = 0;       // pattern-class path: 0 automatic, 1 off, 2 on at any size, 3 like 2 without the lane-per-column kernel
     int64_t last_templated = 0;       // columns the last cs_multiply of this thread formed from class templates
     int add_force_spgemm = 0;         // 1: cs_add on the SpGEMM kernels even for canonical operands
+    long long *host_scalar = nullptr; // 64 bytes of pinned, device-visible host memory: a kernel's scalar result lands here without a copy
 };
 ThreadState &tls();
 extern std::atomic<int64_t> g_launches;
