@@ -857,9 +857,34 @@ def extras(a, torch, cc, synth, peak):
                                             "frac_of_peak": b / ms / 1e6 / peak, "nnzC": nnzc,
                                             "GFLOP/s": 2 * cc.last_multiply_flops() / ms / 1e6}
         hold.clear()
+        # the same product through the general kernels (what a matrix without translation-invariant columns gets)
+        cc.force_multiply_path("no_templates")
+        try:
+            ms = timed(mul, 2, 3)
+        finally:
+            cc.force_multiply_path(None)
+        ex["cs_multiply st27 128^3 A*A (general kernels, pattern classes switched off)"] = {
+            "ms": ms, "nnz(C)/s": nnzc / ms * 1e3, "GB/s": b / ms / 1e6, "frac_of_peak": b / ms / 1e6 / peak}
+        hold.clear()
         tr_paths("st27 128^3", dA, synth.transpose_bytes(m, n, len(i)))
         hold.clear(); dA.free()
         ex["cs_multiply st27 128^3 A*A e2e (host buffers through the C ABI)"] = e2e_multiply(torch, cc, m, n, p, i, x, nnzc)
+        # cs_cumsum (csparse.py:767-784) on 2^24 counts: one API call = memset + launch + the synchronize that
+        # returns the total (written by the kernel into pinned host memory)
+        import ctypes as C
+        from csparse_cuda import _lib
+        nc = 1 << 24
+        # c <- p[0..n-1] is part of the contract, so repeated calls on one array square the counts: zeros are
+        # the only input that stays put (the kernel's work does not depend on the values)
+        cvec = torch.zeros(nc, dtype=torch.int32, device="cuda")
+        pvec = torch.empty(nc + 1, dtype=torch.int32, device="cuda")
+        tot = C.c_int64()
+        ms = timed(lambda: _lib.check(_lib.lib().csb200_cumsum_dev(C.c_void_p(pvec.data_ptr()), C.c_void_p(cvec.data_ptr()),
+                                                                   nc, C.byref(tot))), 3, 10)
+        b = synth.cumsum_bytes(nc)
+        ex["cs_cumsum n = 2^24 (device arrays, total returned to the host)"] = {"ms": ms, "GB/s": b / ms / 1e6,
+                                                                              "frac_of_peak": b / ms / 1e6 / peak}
+        del cvec, pvec
         m, n, tp, ti, tx = synth.rmat_torch(24, 16)
         nnz = int(ti.numel())
         dA = cc.from_device(m, n, tp.data_ptr(), ti.data_ptr(), tx.data_ptr())
